@@ -1,0 +1,580 @@
+// K4: pose scoring -- batched affine least squares, Procrustes, and the single-person decision.
+//
+// Replaces, in one launch over a whole pose database, the per-pair Python of the reference:
+//   common.find_transformation (common.py:37-101, np.linalg.lstsq :84)
+//   common.feature_scaling (common.py:688-708), handle_undetected_points (common.py:281-348),
+//   split_in_face_legs_torso_v2 / unsplit (common.py:269-279)
+//   pose_comparison.* (posematching/pose_comparison.py:8-81)
+//   single_person.match_single (posematching/single_person.py:80-189)
+//   procrustes.procrustes (posematching/procrustes.py:150-259, np.linalg.svd :218)
+//
+// The reference works in float64 and its thresholds sit at 3 significant digits, so the arithmetic here
+// is FP64 as well (B200 keeps a full-rate FP64 pipe; the path is a few hundred FMAs per 144-byte pose).
+// One thread owns one pose pair: the query pose sits in shared memory (broadcast reads), the database
+// pose in registers as the raw float32 it was stored as; masking and min/max scaling are recomputed on
+// the fly per body part instead of materialising 72 doubles per thread.
+#include <float.h>
+#include <math.h>
+#include "common.cuh"
+
+namespace hpusm {
+
+constexpr int NJ = HPUSM_POSE_JOINTS;  // 18 COCO joints
+
+// ---- 3x3 symmetric eigen (cyclic Jacobi), only used on the rank-deficient path -------------------
+__device__ __noinline__ void jacobi3(double M[3][3], double V[3][3], double w[3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(M[0][1]) + fabs(M[0][2]) + fabs(M[1][2]);
+    if (off <= 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (fabs(M[p][q]) <= 1e-300) continue;
+        const double theta = (M[q][q] - M[p][p]) / (2.0 * M[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double mkp = M[k][p], mkq = M[k][q];
+          M[k][p] = c * mkp - s * mkq; M[k][q] = s * mkp + c * mkq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double mpk = M[p][k], mqk = M[q][k];
+          M[p][k] = c * mpk - s * mqk; M[q][k] = s * mpk + c * mqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < 3; ++i) w[i] = M[i][i];
+}
+
+// Raw moments of one least-squares problem  [x y 1] * A = [X Y 1]  over the detected rows.
+struct LsqSums {
+  double n, sx, sy, sxx, sxy, syy;  // moments of the input points
+  double sX, sY;                    // sums of the model points
+  double sxX, syX, sxY, syY;        // cross moments
+};
+
+__device__ __forceinline__ void lsq_add(LsqSums& m, double x, double y, double X, double Y) {
+  m.n += 1.0; m.sx += x; m.sy += y; m.sxx += x * x; m.sxy += x * y; m.syy += y * y;
+  m.sX += X; m.sY += Y; m.sxX += x * X; m.syX += y * X; m.sxY += x * Y; m.syY += y * Y;
+}
+
+// Minimum-norm solution via the pseudo-inverse of the 3x3 normal matrix (what an SVD-based lstsq
+// returns when the design matrix has rank < 3: fewer than three detected joints, or collinear joints).
+__device__ __noinline__ void lsq_solve_deficient(const LsqSums& m, double A[9]) {
+  double M[3][3] = {{m.sxx, m.sxy, m.sx}, {m.sxy, m.syy, m.sy}, {m.sx, m.sy, m.n}};
+  const double R[3][3] = {{m.sxX, m.sxY, m.sx}, {m.syX, m.syY, m.sy}, {m.sX, m.sY, m.n}};  // X^T [X Y 1]
+  double V[3][3], w[3];
+  jacobi3(M, V, w);
+  const double wmax = fmax(fmax(fabs(w[0]), fabs(w[1])), fabs(w[2]));
+  const double tol = wmax * 1e-12;
+  for (int c = 0; c < 3; ++c) {
+    double coef[3];
+    for (int e = 0; e < 3; ++e) {
+      double dot = V[0][e] * R[0][c] + V[1][e] * R[1][c] + V[2][e] * R[2][c];
+      coef[e] = (w[e] > tol) ? dot / w[e] : 0.0;
+    }
+    for (int r = 0; r < 3; ++r) A[3 * r + c] = V[r][0] * coef[0] + V[r][1] * coef[1] + V[r][2] * coef[2];
+  }
+}
+
+// Solve for A (row-major 3x3, row-vector convention). Full-rank problems go through the centred 2x2
+// system (better conditioned than the raw normal equations); the rest through the pseudo-inverse.
+__device__ __forceinline__ void lsq_solve(const LsqSums& m, double A[9]) {
+  const double inv_n = 1.0 / m.n;
+  const double mx = m.sx * inv_n, my = m.sy * inv_n, mX = m.sX * inv_n, mY = m.sY * inv_n;
+  const double cxx = m.sxx - m.sx * mx, cxy = m.sxy - m.sx * my, cyy = m.syy - m.sy * my;
+  const double det = cxx * cyy - cxy * cxy;
+  const double tr = cxx + cyy;
+  if (m.n >= 2.5 && det > 1e-12 * tr * tr) {
+    const double cxX = m.sxX - m.sx * mX, cyX = m.syX - m.sy * mX;
+    const double cxY = m.sxY - m.sx * mY, cyY = m.syY - m.sy * mY;
+    const double id = 1.0 / det;
+    const double a00 = (cyy * cxX - cxy * cyX) * id, a10 = (cxx * cyX - cxy * cxX) * id;
+    const double a01 = (cyy * cxY - cxy * cyY) * id, a11 = (cxx * cyY - cxy * cxY) * id;
+    A[0] = a00; A[1] = a01; A[2] = 0.0;
+    A[3] = a10; A[4] = a11; A[5] = 0.0;
+    A[6] = mX - mx * a00 - my * a10; A[7] = mY - mx * a01 - my * a11; A[8] = 1.0;
+  } else {
+    lsq_solve_deficient(m, A);
+  }
+}
+
+__device__ __forceinline__ double zero_small(double a) { return fabs(a) < 1e-10 ? 0.0 : a; }
+
+// ---- find_transformation, batched (FP64 in/out, arbitrary point count) ----------------------------
+__global__ void affine_lsq_batch_kernel(const double* __restrict__ model, const double* __restrict__ input, int64_t n,
+                                        int npts, double* __restrict__ out, double* __restrict__ Aout,
+                                        uint8_t* __restrict__ has_A) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const double* M = model + b * npts * 2;
+  const double* I = input + b * npts * 2;
+  double* O = out + b * npts * 2;
+  LsqSums m = {};
+  for (int j = 0; j < npts; ++j) {
+    const double x = I[2 * j], y = I[2 * j + 1];
+    if (!(x == 0.0 && y == 0.0)) lsq_add(m, x, y, M[2 * j], M[2 * j + 1]);
+  }
+  if (m.n < 0.5) {  // common.py:70-72: nothing to fit, hand the input back
+    for (int j = 0; j < 2 * npts; ++j) O[j] = I[j];
+    for (int j = 0; j < 9; ++j) Aout[b * 9 + j] = 0.0;
+    has_A[b] = 0;
+    return;
+  }
+  double A[9];
+  lsq_solve(m, A);
+  for (int j = 0; j < npts; ++j) {
+    const double x = I[2 * j], y = I[2 * j + 1];
+    if (x == 0.0 && y == 0.0) { O[2 * j] = 0.0; O[2 * j + 1] = 0.0; }
+    else { O[2 * j] = x * A[0] + y * A[3] + A[6]; O[2 * j + 1] = x * A[1] + y * A[4] + A[7]; }
+  }
+  for (int j = 0; j < 9; ++j) Aout[b * 9 + j] = zero_small(A[j]);
+  has_A[b] = 1;
+}
+
+// ---- Procrustes, batched ---------------------------------------------------------------------------
+__global__ void procrustes_batch_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n, int npts,
+                                        int scaling, int reflection, double* __restrict__ dout, double* __restrict__ Z,
+                                        double* __restrict__ tform) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const double* x = X + b * npts * 2;
+  const double* y = Y + b * npts * 2;
+  double mux = 0, muy = 0, mvx = 0, mvy = 0;
+  for (int j = 0; j < npts; ++j) { mux += x[2 * j]; muy += x[2 * j + 1]; mvx += y[2 * j]; mvy += y[2 * j + 1]; }
+  mux /= npts; muy /= npts; mvx /= npts; mvy /= npts;
+  double ssX = 0, ssY = 0;
+  for (int j = 0; j < npts; ++j) {
+    const double ax = x[2 * j] - mux, ay = x[2 * j + 1] - muy, bx = y[2 * j] - mvx, by = y[2 * j + 1] - mvy;
+    ssX += ax * ax + ay * ay; ssY += bx * bx + by * by;
+  }
+  const double normX = sqrt(ssX), normY = sqrt(ssY);
+  // A = X0^T Y0 on the unit-norm point sets
+  double a = 0, bb = 0, c = 0, d = 0;
+  for (int j = 0; j < npts; ++j) {
+    const double ax = (x[2 * j] - mux) / normX, ay = (x[2 * j + 1] - muy) / normX;
+    const double bx = (y[2 * j] - mvx) / normY, by = (y[2 * j + 1] - mvy) / normY;
+    a += ax * bx; bb += ax * by; c += ay * bx; d += ay * by;
+  }
+  // closed-form 2x2 SVD: A = rotation part + reflection part
+  const double E = 0.5 * (a + d), F = 0.5 * (a - d), G = 0.5 * (c + bb), Hh = 0.5 * (c - bb);
+  const double Q1 = sqrt(E * E + Hh * Hh), R1 = sqrt(F * F + G * G);
+  bool use_reflection;
+  if (reflection == 0) use_reflection = R1 > Q1;          // 'best': whichever fits better (det(A) < 0)
+  else use_reflection = (reflection == 1);
+  // T = V U^T = (orthogonal polar factor of A)^T
+  double T00, T01, T10, T11, trace;
+  if (!use_reflection) {
+    if (Q1 > 0) { T00 = E / Q1; T01 = Hh / Q1; T10 = -Hh / Q1; T11 = E / Q1; }
+    else { T00 = 1; T01 = 0; T10 = 0; T11 = 1; }
+    trace = 2.0 * Q1;
+  } else {
+    if (R1 > 0) { T00 = F / R1; T01 = G / R1; T10 = G / R1; T11 = -F / R1; }
+    else { T00 = 1; T01 = 0; T10 = 0; T11 = -1; }
+    trace = 2.0 * R1;
+  }
+  if (reflection != 0) {
+    // forcing the non-optimal branch flips the sign of the smallest singular value
+    const bool best_is_reflection = R1 > Q1;
+    if (use_reflection != best_is_reflection) trace = 2.0 * (use_reflection ? R1 : Q1);
+  }
+  double bscale, dval, zs;
+  if (scaling) {
+    bscale = trace * normX / normY;
+    dval = 1.0 - trace * trace;
+    zs = normX * trace;
+  } else {
+    bscale = 1.0;
+    dval = 1.0 + ssY / ssX - 2.0 * trace * normY / normX;
+    zs = normY;
+  }
+  double* z = Z + b * npts * 2;
+  for (int j = 0; j < npts; ++j) {
+    const double bx = (y[2 * j] - mvx) / normY, by = (y[2 * j + 1] - mvy) / normY;
+    z[2 * j] = zs * (bx * T00 + by * T10) + mux;
+    z[2 * j + 1] = zs * (bx * T01 + by * T11) + muy;
+  }
+  dout[b] = dval;
+  double* tf = tform + b * 7;
+  tf[0] = T00; tf[1] = T01; tf[2] = T10; tf[3] = T11; tf[4] = bscale;
+  tf[5] = mux - bscale * (mvx * T00 + mvy * T10);
+  tf[6] = muy - bscale * (mvx * T01 + mvy * T11);
+}
+
+// ---- match_single, batched ---------------------------------------------------------------------------
+__constant__ int c_torso[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 11};
+__constant__ int c_legs[7] = {1, 8, 9, 10, 11, 12, 13};
+__constant__ int c_face[5] = {0, 14, 15, 16, 17};
+
+struct PoseParams {
+  double d_torso, tan_torso, rot_torso, d_legs, tan_legs, rot_legs, d_shoulder;
+  int torso_use_tan, legs_use_tan;
+};
+
+// min/max scaling parameters of one masked pose (common.feature_scaling, including its quirk that the
+// minimum runs over BOTH coordinates of the rows whose x (resp. y) is non-zero).
+struct Scale {
+  double xmin, ymin, ix, iy;  // ix = 1/(xmax-xmin)
+  bool valid;
+};
+
+template <typename GetX, typename GetY>
+__device__ __forceinline__ Scale make_scale(GetX gx, GetY gy, unsigned undetected) {
+  double xmax = -DBL_MAX, ymax = -DBL_MAX, xmin = DBL_MAX, ymin = DBL_MAX;
+  bool anyx = false, anyy = false;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const bool u = (undetected >> j) & 1u;
+    const double x = u ? 0.0 : gx(j), y = u ? 0.0 : gy(j);
+    xmax = fmax(xmax, x); ymax = fmax(ymax, y);
+    const double lo = fmin(x, y);
+    if (x != 0.0) { xmin = fmin(xmin, lo); anyx = true; }
+    if (y != 0.0) { ymin = fmin(ymin, lo); anyy = true; }
+  }
+  Scale s;
+  s.valid = anyx && anyy;  // the reference raises ValueError (np.min of an empty array) otherwise
+  s.xmin = xmin; s.ymin = ymin;
+  s.ix = 1.0 / (xmax - xmin); s.iy = 1.0 / (ymax - ymin);
+  return s;
+}
+
+__device__ __forceinline__ double scaled(double v, double lo, double inv, bool undetected) {
+  const double r = ((undetected ? 0.0 : v) - lo) * inv;
+  return r < 0.0 ? 0.0 : r;  // NaN stays NaN, exactly like output[output<0] = 0
+}
+
+struct PartResult {
+  double max_dist, shoulder, A[9];
+  int nz_model, nz_input;
+  bool has_A;
+};
+
+// One body part: fit, transform, distances.  `rows` lists the joints of the part.
+template <int NP, typename GetMX, typename GetMY, typename GetIX, typename GetIY>
+__device__ __forceinline__ PartResult eval_part(const int* rows, GetMX mx, GetMY my, GetIX ix, GetIY iy,
+                                                double* transformed /* optional [NP][2] */) {
+  PartResult r;
+  LsqSums m = {};
+  r.nz_model = 0; r.nz_input = 0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = rows[k];
+    const double xi = ix(j), yi = iy(j), xm = mx(j), ym = my(j);
+    r.nz_model += (xm != 0.0) + (ym != 0.0);
+    r.nz_input += (xi != 0.0) + (yi != 0.0);
+    if (!(xi == 0.0 && yi == 0.0)) lsq_add(m, xi, yi, xm, ym);
+  }
+  r.has_A = m.n > 0.5;
+  if (r.has_A) lsq_solve(m, r.A);
+  else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.A[i] = 0.0;
+  }
+  r.max_dist = -1.0; r.shoulder = -1.0;
+  bool nan_seen = false;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = rows[k];
+    const double xi = ix(j), yi = iy(j), xm = mx(j), ym = my(j);
+    double tx, ty;
+    if (!r.has_A) { tx = xi; ty = yi; }
+    else if (xi == 0.0 && yi == 0.0) { tx = 0.0; ty = 0.0; }
+    else { tx = xi * r.A[0] + yi * r.A[3] + r.A[6]; ty = xi * r.A[1] + yi * r.A[4] + r.A[7]; }
+    if (transformed) { transformed[2 * k] = tx; transformed[2 * k + 1] = ty; }
+    const double dx = xm - tx, dy = ym - ty;
+    const double dist = sqrt(dx * dx + dy * dy);
+    // Python's max() over the array keeps the first element unless a later one compares greater:
+    // a NaN in first position poisons the result, later NaNs are skipped.
+    if (k == 0) { r.max_dist = dist; nan_seen = dist != dist; }
+    else if (!nan_seen && dist > r.max_dist) r.max_dist = dist;
+    if (k == 1) r.shoulder = dist;
+    if (k == 4 && !(r.shoulder != r.shoulder) && dist > r.shoulder) r.shoulder = dist;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.A[i] = zero_small(r.A[i]);
+  return r;
+}
+
+// rot = max(|atan2(-A01, A00)|, |atan2(A10, A11)|) * 57.3 <= thr, without the atan2 when thr < ~86 deg.
+__device__ __forceinline__ bool rotation_ok(const PartResult& r, double tan_thr, double thr, int use_tan) {
+  if (!r.has_A) return true;  // rot_max = 0 for an empty matrix; thresholds are non-negative
+  if (use_tan) {
+    const bool ok1 = r.A[0] >= 0.0 && fabs(r.A[1]) <= tan_thr * r.A[0];
+    const bool ok2 = r.A[4] >= 0.0 && fabs(r.A[3]) <= tan_thr * r.A[4];
+    return ok1 && ok2;
+  }
+  const double r1 = fabs(atan2(-r.A[1], r.A[0]) * 57.3), r2 = fabs(atan2(r.A[3], r.A[4]) * 57.3);
+  return fmax(r2, r1) <= thr;
+}
+
+__device__ __forceinline__ double rotation_value(const PartResult& r) {
+  if (!r.has_A) return 0.0;
+  const double r1 = fabs(atan2(-r.A[1], r.A[0]) * 57.3), r2 = fabs(atan2(r.A[3], r.A[4]) * 57.3);
+  return (r1 > r2) ? r1 : r2;  // Python max(rotation_2, rotation_1): the first argument wins unless the second is greater
+}
+
+constexpr int PM_THREADS = 128;
+
+__global__ void __launch_bounds__(PM_THREADS)
+pose_match_batch_kernel(const float* __restrict__ query, const float* __restrict__ db, int64_t n, int query_is_model,
+                        PoseParams prm, uint8_t* __restrict__ match, float* __restrict__ score,
+                        double* __restrict__ detail) {
+  __shared__ double sq[NJ * 2];
+  __shared__ unsigned sq_undetected;
+  if (threadIdx.x < NJ * 2) sq[threadIdx.x] = (double)query[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned u = 0;
+    for (int j = 0; j < NJ; ++j) if (sq[2 * j] == 0.0 && sq[2 * j + 1] == 0.0) u |= 1u << j;
+    sq_undetected = u;
+  }
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * PM_THREADS + threadIdx.x;
+  if (p >= n) return;
+
+  float pr[NJ * 2];
+  {
+    const float4* src = reinterpret_cast<const float4*>(db + p * (NJ * 2));
+#pragma unroll
+    for (int v = 0; v < NJ * 2 / 4; ++v) {
+      const float4 x = __ldg(src + v);
+      pr[4 * v] = x.x; pr[4 * v + 1] = x.y; pr[4 * v + 2] = x.z; pr[4 * v + 3] = x.w;
+    }
+  }
+  // common.handle_undetected_points: a joint missing on either side is (0,0) on both
+  unsigned und = sq_undetected;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+    if (pr[2 * j] == 0.f && pr[2 * j + 1] == 0.f) und |= 1u << j;
+
+  auto qx = [&](int j) { return sq[2 * j]; };
+  auto qy = [&](int j) { return sq[2 * j + 1]; };
+  auto px = [&](int j) { return (double)pr[2 * j]; };
+  auto py = [&](int j) { return (double)pr[2 * j + 1]; };
+  const Scale s_q = make_scale(qx, qy, und);
+  const Scale s_p = make_scale(px, py, und);
+
+  auto sqx = [&](int j) { return scaled(sq[2 * j], s_q.xmin, s_q.ix, (und >> j) & 1u); };
+  auto sqy = [&](int j) { return scaled(sq[2 * j + 1], s_q.ymin, s_q.iy, (und >> j) & 1u); };
+  auto spx = [&](int j) { return scaled((double)pr[2 * j], s_p.xmin, s_p.ix, (und >> j) & 1u); };
+  auto spy = [&](int j) { return scaled((double)pr[2 * j + 1], s_p.ymin, s_p.iy, (und >> j) & 1u); };
+
+  double* det = detail ? detail + p * HPUSM_POSE_DETAIL : nullptr;
+  double tf_face[10], tf_torso[20], tf_legs[14];
+  PartResult face, torso, legs;
+  if (query_is_model) {
+    torso = eval_part<10>(c_torso, sqx, sqy, spx, spy, det ? tf_torso : nullptr);
+    legs = eval_part<7>(c_legs, sqx, sqy, spx, spy, det ? tf_legs : nullptr);
+    if (det) face = eval_part<5>(c_face, sqx, sqy, spx, spy, tf_face);
+  } else {
+    torso = eval_part<10>(c_torso, spx, spy, sqx, sqy, det ? tf_torso : nullptr);
+    legs = eval_part<7>(c_legs, spx, spy, sqx, sqy, det ? tf_legs : nullptr);
+    if (det) face = eval_part<5>(c_face, spx, spy, sqx, sqy, tf_face);
+  }
+
+  // single_person.py:150-178
+  bool ok_torso, ok_legs;
+  if (torso.nz_model > 4) {
+    if (torso.nz_model - torso.nz_input < 2)
+      ok_torso = torso.max_dist <= prm.d_torso && rotation_ok(torso, prm.tan_torso, prm.rot_torso, prm.torso_use_tan) &&
+                 torso.shoulder <= prm.d_shoulder;
+    else ok_torso = false;
+  } else ok_torso = true;
+  if (legs.nz_model > 8) {
+    if (legs.nz_model - legs.nz_input < 2)
+      ok_legs = legs.max_dist <= prm.d_legs && rotation_ok(legs, prm.tan_legs, prm.rot_legs, prm.legs_use_tan);
+    else ok_legs = false;
+  } else ok_legs = true;
+  const bool valid = s_q.valid && s_p.valid;
+  const double err = valid ? (torso.max_dist + legs.max_dist) * 0.5 : nan("");
+  match[p] = (valid && ok_torso && ok_legs) ? 1 : 0;
+  score[p] = (float)err;
+
+  if (det) {
+    det[0] = torso.max_dist; det[1] = legs.max_dist; det[2] = face.max_dist; det[3] = torso.shoulder;
+    det[4] = rotation_value(torso); det[5] = rotation_value(legs);
+    det[6] = (double)(torso.has_A ? 1 : 0) + 2.0 * (legs.has_A ? 1 : 0) + 4.0 * (face.has_A ? 1 : 0);
+    det[7] = err;
+    for (int i = 0; i < 9; ++i) { det[8 + i] = face.A[i]; det[17 + i] = torso.A[i]; det[26 + i] = legs.A[i]; }
+    // unsplit (common.py:276): face[0], torso (10), legs (7), face[1:5]
+    double* o = det + 35;
+    o[0] = tf_face[0]; o[1] = tf_face[1];
+    for (int i = 0; i < 20; ++i) o[2 + i] = tf_torso[i];
+    for (int i = 0; i < 14; ++i) o[22 + i] = tf_legs[i];
+    for (int i = 0; i < 8; ++i) o[36 + i] = tf_face[2 + i];
+  }
+}
+
+// ---- per-rank top-k of the matching poses ---------------------------------------------------------------
+constexpr int TK_THREADS = 256;
+constexpr int TK_MAXK = 64;
+
+// Block-wide extraction of the k lexicographically smallest (score, index) among candidates produced by
+// `get(i)` for i in [0, count): k rounds of arg-min with the previous winner as a strict lower bound.
+template <typename Get>
+__device__ void block_topk(Get get, int64_t count, int k, float* out_s, int64_t* out_i, float* red_s, int64_t* red_i) {
+  float last_s = -INFINITY;
+  int64_t last_i = -1;
+  for (int r = 0; r < k; ++r) {
+    float bs = INFINITY;
+    int64_t bi = INT64_MAX;
+    for (int64_t i = threadIdx.x; i < count; i += TK_THREADS) {
+      float s; int64_t id;
+      if (!get(i, s, id)) continue;
+      const bool after_last = (s > last_s) || (s == last_s && id > last_i);
+      if (after_last && ((s < bs) || (s == bs && id < bi))) { bs = s; bi = id; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if ((os < bs) || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = bs; red_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < TK_THREADS / 32; ++w)
+        if ((red_s[w] < bs) || (red_s[w] == bs && red_i[w] < bi)) { bs = red_s[w]; bi = red_i[w]; }
+      red_s[0] = bs; red_i[0] = bi;
+      out_s[r] = bs; out_i[r] = bi == INT64_MAX ? -1 : bi;
+    }
+    __syncthreads();
+    last_s = red_s[0]; last_i = red_i[0];
+    __syncthreads();
+    if (last_i == INT64_MAX) {  // ran out of candidates: pad the rest
+      for (int rr = r + 1 + threadIdx.x; rr < k; rr += TK_THREADS) { out_s[rr] = INFINITY; out_i[rr] = -1; }
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+pose_topk_partial_kernel(const uint8_t* __restrict__ match, const float* __restrict__ score, int64_t n,
+                         int64_t index_offset, int k, int64_t per_block, float* __restrict__ part_s,
+                         int64_t* __restrict__ part_i, int32_t* __restrict__ match_count) {
+  __shared__ float red_s[TK_THREADS / 32];
+  __shared__ int64_t red_i[TK_THREADS / 32];
+  const int64_t lo = (int64_t)blockIdx.x * per_block;
+  const int64_t hi = min(n, lo + per_block);
+  int cnt = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += TK_THREADS) cnt += match[i] ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(match_count, cnt);
+  auto get = [&](int64_t i, float& s, int64_t& id) {
+    const int64_t g = lo + i;
+    if (!match[g]) return false;
+    s = score[g];
+    if (s != s) return false;
+    id = g + index_offset;
+    return true;
+  };
+  block_topk(get, hi > lo ? hi - lo : 0, k, part_s + (int64_t)blockIdx.x * k, part_i + (int64_t)blockIdx.x * k, red_s,
+             red_i);
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+pose_topk_final_kernel(const float* __restrict__ part_s, const int64_t* __restrict__ part_i, int64_t count, int k,
+                       float* __restrict__ top_s, int64_t* __restrict__ top_i) {
+  __shared__ float red_s[TK_THREADS / 32];
+  __shared__ int64_t red_i[TK_THREADS / 32];
+  auto get = [&](int64_t i, float& s, int64_t& id) {
+    id = part_i[i];
+    if (id < 0) return false;
+    s = part_s[i];
+    return true;
+  };
+  block_topk(get, count, k, top_s, top_i, red_s, red_i);
+}
+
+static int topk_blocks(int64_t n) {
+  int64_t b = (n + 65535) / 65536;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace hpusm
+
+using namespace hpusm;
+
+extern "C" {
+
+int hpusm_affine_lsq_batch(const double* model, const double* input, int64_t n, int npts, double* out_transform,
+                           double* A, uint8_t* has_A, void* stream) {
+  HPUSM_REQUIRE(n >= 0 && npts > 0, HPUSM_ERR_INVALID, "hpusm_affine_lsq_batch: bad sizes");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(model && input && out_transform && A && has_A, HPUSM_ERR_INVALID,
+                "hpusm_affine_lsq_batch: null pointer");
+  HPUSM_LAUNCH(affine_lsq_batch_kernel, (unsigned)((n + 127) / 128), 128, 0, as_stream(stream), model, input, n, npts,
+               out_transform, A, has_A);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_procrustes_batch(const double* X, const double* Y, int64_t n, int npts, int scaling, int reflection,
+                           double* d, double* Z, double* tform, void* stream) {
+  HPUSM_REQUIRE(n >= 0 && npts > 0 && reflection >= 0 && reflection <= 2, HPUSM_ERR_INVALID,
+                "hpusm_procrustes_batch: bad arguments");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(X && Y && d && Z && tform, HPUSM_ERR_INVALID, "hpusm_procrustes_batch: null pointer");
+  HPUSM_LAUNCH(procrustes_batch_kernel, (unsigned)((n + 127) / 128), 128, 0, as_stream(stream), X, Y, n, npts,
+               scaling, reflection, d, Z, tform);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int query_is_model,
+                           const double* thresholds, uint8_t* match, float* score, double* detail, void* stream) {
+  HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_pose_match_batch: negative size");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(query && db && thresholds && match && score, HPUSM_ERR_INVALID,
+                "hpusm_pose_match_batch: null pointer");
+  HPUSM_REQUIRE(is_aligned(db, 16), HPUSM_ERR_INVALID, "hpusm_pose_match_batch: db must be 16-byte aligned");
+  PoseParams prm;
+  prm.d_torso = thresholds[0]; prm.rot_torso = thresholds[1];
+  prm.d_legs = thresholds[2]; prm.rot_legs = thresholds[3]; prm.d_shoulder = thresholds[4];
+  // rot*57.3 <= thr  <=>  angle <= thr/57.3; usable as a tangent bound while that stays below ~86 degrees
+  const double a_t = prm.rot_torso / 57.3, a_l = prm.rot_legs / 57.3;
+  prm.torso_use_tan = (a_t >= 0.0 && a_t < 1.5) ? 1 : 0;
+  prm.legs_use_tan = (a_l >= 0.0 && a_l < 1.5) ? 1 : 0;
+  prm.tan_torso = prm.torso_use_tan ? tan(a_t) : 0.0;
+  prm.tan_legs = prm.legs_use_tan ? tan(a_l) : 0.0;
+  HPUSM_LAUNCH(pose_match_batch_kernel, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
+               as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+size_t hpusm_pose_topk_workspace_bytes(int64_t n, int k) {
+  const int b = topk_blocks(n > 0 ? n : 1);
+  return align_up((size_t)b * k * sizeof(float), 256) + align_up((size_t)b * k * sizeof(int64_t), 256);
+}
+
+int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t index_offset, int k, float* top_score,
+                    int64_t* top_index, int32_t* match_count, void* ws, size_t ws_bytes, void* stream) {
+  HPUSM_REQUIRE(n >= 0 && k > 0 && k <= TK_MAXK, HPUSM_ERR_INVALID, "hpusm_pose_topk: k must be in 1..%d", TK_MAXK);
+  HPUSM_REQUIRE(top_score && top_index && match_count && (n == 0 || (match && score)), HPUSM_ERR_INVALID,
+                "hpusm_pose_topk: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int b = topk_blocks(n > 0 ? n : 1);
+  const size_t need = hpusm_pose_topk_workspace_bytes(n, k);
+  HPUSM_REQUIRE(ws && is_aligned(ws, 256) && ws_bytes >= need, HPUSM_ERR_WORKSPACE,
+                "hpusm_pose_topk: workspace needs %zu bytes, got %zu", need, ws_bytes);
+  float* ps = reinterpret_cast<float*>(ws);
+  int64_t* pi = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(ws) + align_up((size_t)b * k * sizeof(float), 256));
+  HPUSM_CUDA_OK(cudaMemsetAsync(match_count, 0, sizeof(int32_t), st));
+  const int64_t per_block = (n + b - 1) / b;
+  HPUSM_LAUNCH(pose_topk_partial_kernel, b, TK_THREADS, 0, st, match, score, n, index_offset, k,
+               per_block > 0 ? per_block : 1, ps, pi, match_count);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(pose_topk_final_kernel, 1, TK_THREADS, 0, st, ps, pi, (int64_t)b * k, k, top_score, top_index);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+}  // extern "C"

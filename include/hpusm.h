@@ -1,0 +1,207 @@
+/*
+ * hpusm.h -- C ABI of libhpusm.so, the B200 (sm_100a) matching hot path.
+ *
+ * The reference (gilbeckers/HumanPose-and-UrbanScene-Matching) has NO native/FFI layer: its hot path
+ * calls OpenCV / NumPy binaries from Python.  Each entry point below therefore replaces one of those
+ * third-party call sites; the reference file:line of the call site is cited per function.  The Python
+ * modules under humanpose-and-urbanscene-matching_b200/dropin/ keep the reference's own signatures and
+ * bind these symbols with ctypes (see INTEGRATION.md for the stub a maintainer of the reference adds).
+ *
+ * Conventions (all functions):
+ *   - every data pointer is a DEVICE pointer owned by the caller (the *_host conveniences say so);
+ *   - no allocation escapes the library: scratch is passed in (`ws`, `ws_bytes`), sized by the
+ *     matching hpusm_*_workspace_bytes() query.  `ws` must be 256-byte aligned;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); outputs are valid after the stream is synchronised;
+ *   - return value: HPUSM_OK (0) or a negative HPUSM_ERR_* code; hpusm_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - thread-safe for distinct (stream, workspace) pairs;
+ *   - there is no CPU fallback: without a CUDA device every compute call returns HPUSM_ERR_CUDA.
+ */
+#ifndef HPUSM_H_
+#define HPUSM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPUSM_ABI_VERSION 100
+
+#define HPUSM_OK 0
+#define HPUSM_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported width) */
+#define HPUSM_ERR_CUDA (-2)        /* CUDA runtime/driver error, see hpusm_last_error()             */
+#define HPUSM_ERR_WORKSPACE (-3)   /* workspace missing, misaligned or too small                    */
+#define HPUSM_ERR_UNSUPPORTED (-4) /* shape outside what the sm_100a kernels were built for         */
+
+/* L2 kNN engine selection (hpusm_knn2_l2 `mode`). */
+#define HPUSM_L2_AUTO 0   /* tensor-core path; operand split chosen from the data (exact-int or 3-way) */
+#define HPUSM_L2_SIMT 1   /* exact FP32 CUDA-core brute force (cross-check / tiny inputs)             */
+#define HPUSM_L2_TC_INT 2 /* tcgen05, bf16 operands, caller asserts integer values in [0,256]         */
+#define HPUSM_L2_TC_SPLIT 3 /* tcgen05, hi/lo bf16 split (general float) + top-m FP32 re-rank         */
+
+int hpusm_version(void);
+const char* hpusm_last_error(void);
+/* Number of CUDA devices visible, or a negative error code. */
+int hpusm_device_count(void);
+/* Running count of kernels this library launched from the calling process (for bench `gpu_launches`). */
+int64_t hpusm_launch_count(void);
+
+/* --------------------------------------------------------------------------------------------------
+ * K2  Binary-descriptor kNN, k=2, Hamming norm.
+ * Replaces cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(desc_model, trainDescriptors=desc_input, k=2)
+ * (reference urbanscene/features.py:42 and :59).
+ *   q [nq][nbytes], t [nt][nbytes] uint8, C-contiguous, 16-byte aligned base, nbytes in {32, 64}.
+ *   idx  [nq][2] int32: train index of the nearest / second nearest; -1 where nt < 2 leaves a slot empty.
+ *   dist [nq][2] int32: popcount(q ^ t).  Ties resolve to the LOWER train index (OpenCV behaviour).
+ * ------------------------------------------------------------------------------------------------ */
+size_t hpusm_knn2_hamming_workspace_bytes(int64_t nq, int64_t nt, int nbytes);
+int hpusm_knn2_hamming(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbytes,
+                       int32_t* idx, int32_t* dist, void* ws, size_t ws_bytes, void* stream);
+
+/* Segmented variant for query-vs-database retrieval (dataset/dataset_urbanscene.py:46-84 loops
+ * match_whole over image pairs; every (query image, database image) pair is an independent kNN+ratio).
+ *   t holds the descriptors of nseg database images back to back; seg_offsets [nseg+1] int64 (device)
+ *   gives each image's row range.  For every segment s and query row i the kernel finds the two nearest
+ *   rows INSIDE segment s, applies Lowe's ratio test (features.py:48) in double precision and counts
+ *   survivors:  score[s] = #{ i : seg has >= 2 rows and (double)d0 < (double)d1 * ratio }.
+ *   score [nseg] int32 is overwritten.
+ *   best_idx (optional, may be NULL) [nseg][nq] int32: global row index of the nearest neighbour where
+ *   the ratio test passed, else -1 (feeds the RANSAC stage without a second pass). */
+size_t hpusm_knn2_hamming_segmented_workspace_bytes(int64_t nq, int64_t nt, int64_t nseg, int nbytes);
+int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
+                                 const int64_t* seg_offsets, int64_t nseg, int nbytes, double ratio,
+                                 int32_t* score, int32_t* best_idx, void* ws, size_t ws_bytes,
+                                 void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * K1  Float-descriptor kNN, k=2, L2 norm.
+ * Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) (features.py:42,:59).
+ *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512
+ *   (tensor-core modes: d a multiple of 16 and d <= 128).
+ *   idx  [nq][2] int32 as above.
+ *   dist [nq][2] float32 = sqrtf( sum_k (q_k - t_k)^2 ), the sum taken in FP32 in increasing k with
+ *   fused multiply-add (the "exact FP32 re-rank"); this is what DMatch.distance holds in the reference.
+ *   Ties (equal FP32 distance) resolve to the lower train index.
+ *   `mode` is one of HPUSM_L2_*.
+ * ------------------------------------------------------------------------------------------------ */
+size_t hpusm_knn2_l2_workspace_bytes(int64_t nq, int64_t nt, int d, int mode);
+int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode,
+                  int32_t* idx, float* dist, void* ws, size_t ws_bytes, void* stream);
+/* Which engine the last hpusm_knn2_l2 call on this thread resolved HPUSM_L2_AUTO to (HPUSM_L2_*),
+ * and how many query rows needed the exact brute-force fallback after candidate verification. */
+int hpusm_knn2_l2_last_mode(void);
+int64_t hpusm_knn2_l2_last_fallback_rows(void);
+
+/* Lexicographic (distance, index) merge of `nparts` partial top-2 lists (DB shards or DB splits):
+ *   part_idx/part_dist [nparts][nq][2]; empty slots carry idx -1.  Used after the NCCL all-gather of
+ *   per-rank results; indices must already be global.  In-place safe when nparts == 1. */
+int hpusm_knn2_merge_f32(const int32_t* part_idx, const float* part_dist, int nparts, int64_t nq,
+                         int32_t* idx, float* dist, void* stream);
+int hpusm_knn2_merge_i32(const int32_t* part_idx, const int32_t* part_dist, int nparts, int64_t nq,
+                         int32_t* idx, int32_t* dist, void* stream);
+
+/* Lowe ratio test, replaces the loop of features.filter_matches (features.py:45-55):
+ *   keep[i] = idx[i][1] >= 0 && (double)dist[i][0] < (double)dist[i][1] * ratio      (features.py:48)
+ *   *count (device int32) receives the number of survivors.  dist_is_int selects int32 vs float32. */
+int hpusm_ratio_filter(const void* dist, const int32_t* idx, int64_t nq, int dist_is_int, double ratio,
+                       uint8_t* keep, int32_t* count, void* stream);
+
+/* Order-preserving compaction of the ratio survivors + keypoint gather (features.py:49-53):
+ *   kp_q [nq][2], kp_t [nt][2] float32 keypoint coordinates; for the j-th survivor (increasing query
+ *   row) p_q[j] = kp_q[i], p_t[j] = kp_t[idx[i][0]], sel[j] = i.  *count as above.
+ *   ws: hpusm_gather_matches_workspace_bytes(nq). */
+size_t hpusm_gather_matches_workspace_bytes(int64_t nq);
+int hpusm_gather_matches(const float* kp_q, const float* kp_t, const int32_t* idx, const uint8_t* keep,
+                         int64_t nq, float* p_q, float* p_t, int32_t* sel, int32_t* count, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * K3  Batched RANSAC homography.
+ * Replaces cv2.findHomography(src, dst, cv2.RANSAC, thresh) (features.py:66 and :69), batched over
+ * image pairs.  Pair p owns matches [pair_offsets[p], pair_offsets[p+1]).
+ *   src, dst [total][2] float32; pair_offsets [npairs+1] int64 (device).
+ *   nhyp      hypotheses per pair (cv2 maxIters; reference default 2000).
+ *   confidence  > 0: reproduce the sequential early-exit of RANSAC exactly (hypothesis h is considered
+ *               only while h < the adaptive iteration bound, cv2 default 0.995); <= 0: use all nhyp.
+ *   seed      keys the counter-based sample table (seed, pair, hypothesis) shared with the oracle.
+ *   H    [npairs][9] float64 row-major, H[8] == 1; all NaN when no model with >= 4 inliers exists.
+ *   mask [total] uint8 inlier flags of the winning hypothesis (before refinement, as cv2 returns).
+ *   ninl [npairs] int32 inlier count; best_hyp [npairs] int32 (optional, may be NULL) winning index.
+ *   refine != 0: least-squares DLT on the inliers followed by Levenberg-Marquardt on the reprojection
+ *               error (cv2 does both); refine == 0 returns the winning minimal-sample model.
+ * ------------------------------------------------------------------------------------------------ */
+size_t hpusm_ransac_homography_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp);
+int hpusm_ransac_homography_batch(const float* src, const float* dst, const int64_t* pair_offsets,
+                                  int64_t npairs, int64_t total_matches, float thresh, int nhyp,
+                                  double confidence, uint64_t seed, int refine, double* H,
+                                  uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
+                                  size_t ws_bytes, void* stream);
+/* Hypothesis scoring only (the C4 benchmark kernel): counts [npairs][nhyp] int32 inlier counts,
+ * -1 for a degenerate sample. */
+int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* pair_offsets,
+                             int64_t npairs, int64_t total_matches, float thresh, int nhyp,
+                             uint64_t seed, int32_t* counts, void* stream);
+
+/* Projective transform of points, replaces cv2.perspectiveTransform (features.py:77,
+ * transformation.py:38): pts [n][2] float32, H [9] float64 (device) -> out [n][2] float32. */
+int hpusm_perspective_transform(const float* pts, int64_t n, const double* H, float* out, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * K4  Pose scoring.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Batched affine least squares, replaces common.find_transformation (common.py:37-101, np.linalg.lstsq
+ * at :84).  Problem b: model/input [n][npts][2] float64.  Rows whose INPUT point is (0,0) are left out
+ * of the fit and come back as (0,0); a problem with no rows left returns the input unchanged and
+ * has_A[b] = 0 (the reference returns an empty list).  Rank-deficient fits get the minimum-norm
+ * solution (what SVD-based lstsq returns).
+ *   out_transform [n][npts][2] float64; A [n][9] float64 row-major, row-vector convention
+ *   ([x y 1] * A), entries with |a| < 1e-10 zeroed AFTER the transform was applied (common.py:99). */
+int hpusm_affine_lsq_batch(const double* model, const double* input, int64_t n, int npts,
+                           double* out_transform, double* A, uint8_t* has_A, void* stream);
+
+/* Batched Procrustes superimposition, replaces posematching/procrustes.py:150-259 (np.linalg.svd :218).
+ *   X, Y [n][npts][2] float64.  scaling: 0/1.  reflection: 0 = 'best', 1 = force reflection,
+ *   2 = force no reflection.
+ *   d [n]; Z [n][npts][2]; tform [n][7] = rotation T row-major (4), scale b, translation c (2). */
+int hpusm_procrustes_batch(const double* X, const double* Y, int64_t n, int npts, int scaling,
+                           int reflection, double* d, double* Z, double* tform, void* stream);
+
+/* Batched single-person pose decision, replaces posematching/single_person.match_single
+ * (single_person.py:80-189) = handle_undetected_points (common.py:281) -> feature_scaling x2
+ * (common.py:688) -> split_in_face_legs_torso_v2 (common.py:269) -> find_transformation x3 ->
+ * pose_comparison.max_euclidean_distance / decide_* (pose_comparison.py:8-81).
+ *   query [18][2] float32, db [n][18][2] float32 (OpenPose COCO order, undetected joints = (0,0)).
+ *   query_is_model != 0: the query plays the reference's `model_features`, db rows are `input_features`
+ *   (dataset/Multipose_dataset_actions.py:38-49); 0 swaps the roles.
+ *   thresholds [5] float64 = {SP_DISTANCE_TORSO, SP_ROTATION_TORSO, SP_DISTANCE_LEGS, SP_ROTATION_LEGS,
+ *   SP_DISTANCE_SHOULDER} (thresholds.py:7-13), host pointer.
+ *   match [n] uint8, score [n] float32 (= error_score, single_person.py:184).
+ *   detail (optional, NULL to skip) [n][DETAIL] float64: torso/legs/face max distance, shoulder
+ *   distance, rot torso, rot legs, then the three 3x3 A matrices and the (22,2) transformed input,
+ *   HPUSM_POSE_DETAIL doubles per pose. */
+#define HPUSM_POSE_JOINTS 18
+#define HPUSM_POSE_DETAIL (8 + 27 + 44)
+int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int query_is_model,
+                           const double* thresholds, uint8_t* match, float* score, double* detail,
+                           void* stream);
+
+/* Per-rank top-k smallest scores among matching poses (retrieval answer that is all-gathered over
+ * NCCL): writes k (score, index+index_offset) pairs, score = +inf padding. ws from
+ * hpusm_pose_topk_workspace_bytes(n, k). */
+size_t hpusm_pose_topk_workspace_bytes(int64_t n, int k);
+int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t index_offset, int k,
+                    float* top_score, int64_t* top_index, int32_t* match_count, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* Integer-pipe micro-benchmark: every thread issues `iters` dependent-free POPC.32; returns nothing
+ * useful in `sink`.  bench.py uses it as the measured denominator of the Hamming roofline. */
+int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPUSM_H_ */
