@@ -1,0 +1,297 @@
+"""Batched entry points over torch CUDA tensors.
+
+torch is the buffer carrier only: every function checks its arguments, allocates outputs and the
+workspace as torch tensors on the inputs' device, and hands ``data_ptr()`` values plus the current CUDA
+stream to the C ABI of libhpusm.so (include/hpusm.h).  There is no CPU path here: a non-CUDA tensor is
+an error, and a failing library call raises ``HpusmError``.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT = _lib.L2_AUTO, _lib.L2_SIMT, _lib.L2_TC_INT, _lib.L2_TC_SPLIT
+POSE_DETAIL = _lib.POSE_DETAIL
+
+# thresholds.py:7-13 of the reference, in the order hpusm_pose_match_batch expects
+DEFAULT_POSE_THRESHOLDS = (0.236, 19.8, 0.082, 24.0, 0.125)
+
+
+def _cuda(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must live on a CUDA device (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _workspace(nbytes, dev):
+    # torch's caching allocator hands out 512-byte aligned blocks; the ABI asks for 256
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def launch_count():
+    """Kernels launched by libhpusm.so in this process so far."""
+    return int(lib.hpusm_launch_count())
+
+
+# ---- K2: Hamming ------------------------------------------------------------------------------------
+def knn2_hamming(q, t):
+    """cv2.BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) (features.py:59): (idx [nq,2] i32, dist [nq,2] i32)."""
+    q = _cuda(q, torch.uint8, "q")
+    t = _cuda(t, torch.uint8, "t")
+    if q.dim() != 2 or t.dim() != 2 or q.shape[1] != t.shape[1]:
+        raise ValueError("descriptor arrays must be [n, nbytes] with equal width")
+    nq, nb = q.shape
+    nt = t.shape[0]
+    with torch.cuda.device(q.device):
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+        dist = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+        ws = _workspace(lib.hpusm_knn2_hamming_workspace_bytes(nq, nt, nb), q.device)
+        check(lib.hpusm_knn2_hamming(_ptr(q), nq, _ptr(t), nt, nb, _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(),
+                                     _stream(q.device)))
+    return idx, dist
+
+
+def knn2_hamming_segmented(q, t, seg_offsets, ratio=0.8, want_best_idx=False):
+    """Per database image: kNN-2 inside the image + Lowe ratio + survivor count (score [nseg] i32)."""
+    q = _cuda(q, torch.uint8, "q")
+    t = _cuda(t, torch.uint8, "t")
+    seg_offsets = _cuda(seg_offsets, torch.int64, "seg_offsets")
+    nq, nb = q.shape
+    nt = t.shape[0]
+    nseg = seg_offsets.numel() - 1
+    with torch.cuda.device(q.device):
+        score = torch.empty((nseg,), dtype=torch.int32, device=q.device)
+        best = torch.empty((nseg, nq), dtype=torch.int32, device=q.device) if want_best_idx else None
+        ws = _workspace(lib.hpusm_knn2_hamming_segmented_workspace_bytes(nq, nt, nseg, nb), q.device)
+        check(lib.hpusm_knn2_hamming_segmented(_ptr(q), nq, _ptr(t), nt, _ptr(seg_offsets), nseg, nb, float(ratio),
+                                               _ptr(score), _ptr(best), _ptr(ws), ws.numel(), _stream(q.device)))
+    return (score, best) if want_best_idx else score
+
+
+# ---- K1: L2 ------------------------------------------------------------------------------------------
+def knn2_l2(q, t, mode=L2_AUTO, out=None, workspace=None):
+    """cv2.BFMatcher(NORM_L2).knnMatch(q, t, k=2) (features.py:59): (idx [nq,2] i32, dist [nq,2] f32 = sqrt)."""
+    q = _cuda(q, torch.float32, "q")
+    t = _cuda(t, torch.float32, "t")
+    if q.dim() != 2 or t.dim() != 2 or q.shape[1] != t.shape[1]:
+        raise ValueError("descriptor arrays must be [n, d] with equal d")
+    nq, d = q.shape
+    nt = t.shape[0]
+    with torch.cuda.device(q.device):
+        if out is None:
+            idx = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+            dist = torch.empty((nq, 2), dtype=torch.float32, device=q.device)
+        else:
+            idx, dist = out
+        need = lib.hpusm_knn2_l2_workspace_bytes(nq, nt, d, mode)
+        ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, q.device)
+        check(lib.hpusm_knn2_l2(_ptr(q), nq, _ptr(t), nt, d, mode, _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(),
+                                _stream(q.device)))
+    return idx, dist
+
+
+def knn2_l2_workspace(nq, nt, d, mode, device):
+    return _workspace(lib.hpusm_knn2_l2_workspace_bytes(nq, nt, d, mode), device)
+
+
+def knn2_l2_last_mode():
+    return int(lib.hpusm_knn2_l2_last_mode())
+
+
+def knn2_l2_last_fallback_rows():
+    return int(lib.hpusm_knn2_l2_last_fallback_rows())
+
+
+def knn2_merge(part_idx, part_dist):
+    """Lexicographic (dist, idx) merge of [nparts, nq, 2] partial top-2 lists (indices already global)."""
+    part_idx = _cuda(part_idx, torch.int32, "part_idx")
+    nparts, nq, _ = part_idx.shape
+    dev = part_idx.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        if part_dist.dtype == torch.float32:
+            part_dist = _cuda(part_dist, torch.float32, "part_dist")
+            dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+            check(lib.hpusm_knn2_merge_f32(_ptr(part_idx), _ptr(part_dist), nparts, nq, _ptr(idx), _ptr(dist),
+                                           _stream(dev)))
+        else:
+            part_dist = _cuda(part_dist, torch.int32, "part_dist")
+            dist = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+            check(lib.hpusm_knn2_merge_i32(_ptr(part_idx), _ptr(part_dist), nparts, nq, _ptr(idx), _ptr(dist),
+                                           _stream(dev)))
+    return idx, dist
+
+
+def ratio_filter(idx, dist, ratio=0.8):
+    """features.filter_matches' test (features.py:48): (keep [nq] u8, count [1] i32 on device)."""
+    idx = _cuda(idx, torch.int32, "idx")
+    is_int = dist.dtype == torch.int32
+    dist = _cuda(dist, torch.int32 if is_int else torch.float32, "dist")
+    nq = idx.shape[0]
+    dev = idx.device
+    with torch.cuda.device(dev):
+        keep = torch.empty((nq,), dtype=torch.uint8, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        check(lib.hpusm_ratio_filter(_ptr(dist), _ptr(idx), nq, 1 if is_int else 0, float(ratio), _ptr(keep),
+                                     _ptr(count), _stream(dev)))
+    return keep, count
+
+
+def gather_matches(kp_q, kp_t, idx, keep):
+    """Order-preserving compaction + keypoint gather (features.py:49-53): (p_q, p_t, sel, count)."""
+    kp_q = _cuda(kp_q, torch.float32, "kp_q")
+    kp_t = _cuda(kp_t, torch.float32, "kp_t")
+    idx = _cuda(idx, torch.int32, "idx")
+    keep = _cuda(keep, torch.uint8, "keep")
+    nq = idx.shape[0]
+    dev = idx.device
+    with torch.cuda.device(dev):
+        p_q = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+        p_t = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+        sel = torch.empty((nq,), dtype=torch.int32, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        ws = _workspace(lib.hpusm_gather_matches_workspace_bytes(nq), dev)
+        check(lib.hpusm_gather_matches(_ptr(kp_q), _ptr(kp_t), _ptr(idx), _ptr(keep), nq, _ptr(p_q), _ptr(p_t),
+                                       _ptr(sel), _ptr(count), _ptr(ws), ws.numel(), _stream(dev)))
+    return p_q, p_t, sel, count
+
+
+# ---- K3: RANSAC ----------------------------------------------------------------------------------------
+def ransac_homography_batch(src, dst, pair_offsets, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, refine=True):
+    """cv2.findHomography(src, dst, RANSAC, thresh) per pair (features.py:66,:69).
+
+    Returns (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32, best_hyp [npairs] i32)."""
+    src = _cuda(src, torch.float32, "src")
+    dst = _cuda(dst, torch.float32, "dst")
+    pair_offsets = _cuda(pair_offsets, torch.int64, "pair_offsets")
+    total = src.shape[0]
+    npairs = pair_offsets.numel() - 1
+    dev = src.device
+    with torch.cuda.device(dev):
+        H = torch.empty((npairs, 3, 3), dtype=torch.float64, device=dev)
+        mask = torch.empty((total,), dtype=torch.uint8, device=dev)
+        ninl = torch.empty((npairs,), dtype=torch.int32, device=dev)
+        best = torch.empty((npairs,), dtype=torch.int32, device=dev)
+        ws = _workspace(lib.hpusm_ransac_homography_workspace_bytes(total, npairs, nhyp), dev)
+        check(lib.hpusm_ransac_homography_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
+                                                int(nhyp), float(confidence), int(seed), 1 if refine else 0, _ptr(H),
+                                                _ptr(mask), _ptr(ninl), _ptr(best), _ptr(ws), ws.numel(), _stream(dev)))
+    return H, mask, ninl, best
+
+
+def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, out=None):
+    """Inlier count of every hypothesis of every pair: counts [npairs, nhyp] i32 (-1 = degenerate sample)."""
+    src = _cuda(src, torch.float32, "src")
+    dst = _cuda(dst, torch.float32, "dst")
+    pair_offsets = _cuda(pair_offsets, torch.int64, "pair_offsets")
+    total = src.shape[0]
+    npairs = pair_offsets.numel() - 1
+    dev = src.device
+    with torch.cuda.device(dev):
+        counts = out if out is not None else torch.empty((npairs, nhyp), dtype=torch.int32, device=dev)
+        check(lib.hpusm_ransac_score_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
+                                           int(nhyp), int(seed), _ptr(counts), _stream(dev)))
+    return counts
+
+
+def perspective_transform(pts, H):
+    """cv2.perspectiveTransform(pts, H) (features.py:77, transformation.py:38)."""
+    pts = _cuda(pts, torch.float32, "pts")
+    H = _cuda(H, torch.float64, "H")
+    n = pts.numel() // 2
+    dev = pts.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(pts)
+        check(lib.hpusm_perspective_transform(_ptr(pts), n, _ptr(H), _ptr(out), _stream(dev)))
+    return out
+
+
+# ---- K4: pose ------------------------------------------------------------------------------------------
+def affine_lsq_batch(model, inp):
+    """common.find_transformation batched (common.py:37-101): (transform [n,npts,2], A [n,3,3], has_A [n] u8)."""
+    model = _cuda(model, torch.float64, "model")
+    inp = _cuda(inp, torch.float64, "input")
+    n, npts, _ = inp.shape
+    dev = inp.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(inp)
+        A = torch.empty((n, 3, 3), dtype=torch.float64, device=dev)
+        has = torch.empty((n,), dtype=torch.uint8, device=dev)
+        check(lib.hpusm_affine_lsq_batch(_ptr(model), _ptr(inp), n, npts, _ptr(out), _ptr(A), _ptr(has), _stream(dev)))
+    return out, A, has
+
+
+def procrustes_batch(X, Y, scaling=True, reflection="best"):
+    """procrustes.procrustes batched (procrustes.py:150-259): (d [n], Z [n,npts,2], tform [n,7])."""
+    X = _cuda(X, torch.float64, "X")
+    Y = _cuda(Y, torch.float64, "Y")
+    n, npts, _ = X.shape
+    refl = 0 if (isinstance(reflection, str) and reflection == "best") else (1 if reflection else 2)
+    dev = X.device
+    with torch.cuda.device(dev):
+        d = torch.empty((n,), dtype=torch.float64, device=dev)
+        Z = torch.empty_like(X)
+        tform = torch.empty((n, 7), dtype=torch.float64, device=dev)
+        check(lib.hpusm_procrustes_batch(_ptr(X), _ptr(Y), n, npts, 1 if scaling else 0, refl, _ptr(d), _ptr(Z),
+                                         _ptr(tform), _stream(dev)))
+    return d, Z, tform
+
+
+def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THRESHOLDS, want_detail=False, out=None):
+    """single_person.match_single of one query against a pose database (single_person.py:80-189).
+
+    Returns (match [n] u8, score [n] f32[, detail [n, POSE_DETAIL] f64])."""
+    query = _cuda(query, torch.float32, "query")
+    db = _cuda(db, torch.float32, "db")
+    if query.numel() != 36 or db.dim() != 3 or db.shape[1:] != (18, 2):
+        raise ValueError("query must be [18,2] and db [n,18,2]")
+    n = db.shape[0]
+    dev = db.device
+    thr = (ctypes.c_double * 5)(*[float(x) for x in thresholds])
+    with torch.cuda.device(dev):
+        if out is None:
+            match = torch.empty((n,), dtype=torch.uint8, device=dev)
+            score = torch.empty((n,), dtype=torch.float32, device=dev)
+        else:
+            match, score = out
+        detail = torch.empty((n, POSE_DETAIL), dtype=torch.float64, device=dev) if want_detail else None
+        check(lib.hpusm_pose_match_batch(_ptr(query), _ptr(db), n, 1 if query_is_model else 0,
+                                         ctypes.cast(thr, ctypes.c_void_p), _ptr(match), _ptr(score), _ptr(detail),
+                                         _stream(dev)))
+    return (match, score, detail) if want_detail else (match, score)
+
+
+def pose_topk(match, score, k=16, index_offset=0):
+    """k best-scoring matching poses: (top_score [k] f32, top_index [k] i64, match_count [1] i32)."""
+    match = _cuda(match, torch.uint8, "match")
+    score = _cuda(score, torch.float32, "score")
+    n = match.numel()
+    dev = match.device
+    with torch.cuda.device(dev):
+        ts = torch.empty((k,), dtype=torch.float32, device=dev)
+        ti = torch.empty((k,), dtype=torch.int64, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        ws = _workspace(lib.hpusm_pose_topk_workspace_bytes(n, k), dev)
+        check(lib.hpusm_pose_topk(_ptr(match), _ptr(score), n, int(index_offset), int(k), _ptr(ts), _ptr(ti), _ptr(cnt),
+                                  _ptr(ws), ws.numel(), _stream(dev)))
+    return ts, ti, cnt
+
+
+def microbench_popc(blocks, threads, iters, device):
+    sink = torch.zeros((1,), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib.hpusm_microbench_popc(int(blocks), int(threads), int(iters), _ptr(sink), _stream(device)))
