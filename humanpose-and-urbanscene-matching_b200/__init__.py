@@ -13,6 +13,7 @@ The directory name carries hyphens, so import it with
 module at the repository root.
 """
 from . import _lib  # noqa: F401
+from . import synth  # noqa: F401
 from .engine import (  # noqa: F401
     knn2_hamming,
     knn2_hamming_segmented,

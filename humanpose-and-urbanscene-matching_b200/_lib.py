@@ -45,6 +45,8 @@ SIGNATURES = {
     "hpusm_last_error": (ctypes.c_char_p, []),
     "hpusm_device_count": (_i32, []),
     "hpusm_launch_count": (_i64, []),
+    "hpusm_profile_enable": (_i32, [_i32]),
+    "hpusm_profile_collect": (_i32, [_p, _p]),
     "hpusm_knn2_hamming_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "hpusm_knn2_hamming": (_i32, [_p, _i64, _p, _i64, _i32, _p, _p, _p, _sz, _p]),
     "hpusm_knn2_hamming_segmented_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),

@@ -1,6 +1,9 @@
 // Library-wide entry points: version, error string, launch accounting, the POPC micro-benchmark.
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "common.cuh"
 
 namespace hpusm {
@@ -13,6 +16,28 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_error, sizeof(t_error), fmt, ap);
   va_end(ap);
+}
+
+// ---- optional event bracketing of the dominant kernels -------------------------------------------------
+static std::atomic<int> g_profile{0};
+static std::mutex g_profile_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
+static cudaEvent_t g_profile_open = nullptr;
+
+void profile_mark(cudaStream_t st, bool begin) {
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  if (begin) {
+    g_profile_open = e;
+  } else if (g_profile_open) {
+    g_profile_events.emplace_back(g_profile_open, e);
+    g_profile_open = nullptr;
+  } else {
+    cudaEventDestroy(e);
+  }
 }
 
 int sm_count() {
@@ -62,6 +87,35 @@ int hpusm_device_count(void) {
 }
 
 int64_t hpusm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hpusm_profile_enable(int on) {
+  g_profile.store(on ? 1 : 0);
+  return HPUSM_OK;
+}
+
+int hpusm_profile_collect(double* total_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  double sum = 0.0;
+  int64_t n = 0;
+  for (auto& pr : g_profile_events) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(pr.second);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.first, pr.second);
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+    if (e != cudaSuccess) {
+      set_error("hpusm_profile_collect: %s", cudaGetErrorString(e));
+      g_profile_events.clear();
+      return HPUSM_ERR_CUDA;
+    }
+    sum += ms;
+    ++n;
+  }
+  g_profile_events.clear();
+  if (total_ms) *total_ms = sum;
+  if (launches) *launches = n;
+  return HPUSM_OK;
+}
 
 int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream) {
   HPUSM_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,

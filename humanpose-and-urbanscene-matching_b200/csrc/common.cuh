@@ -20,6 +20,17 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
     ::hpusm::g_launches.fetch_add(1, std::memory_order_relaxed);                     \
   } while (0)
 
+// Same, bracketed by CUDA events on the launching stream when hpusm_profile_enable(1) is in force: the
+// dominant kernel of each path is launched through this so bench.py can report its duration (roofline).
+void profile_mark(cudaStream_t st, bool begin);
+#define HPUSM_LAUNCH_TIMED(kernel, grid, block, smem, stream, ...)                   \
+  do {                                                                               \
+    ::hpusm::profile_mark((stream), true);                                           \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                      \
+    ::hpusm::profile_mark((stream), false);                                          \
+    ::hpusm::g_launches.fetch_add(1, std::memory_order_relaxed);                     \
+  } while (0)
+
 #define HPUSM_CUDA_OK(expr)                                                          \
   do {                                                                               \
     cudaError_t _e = (expr);                                                         \

@@ -256,9 +256,9 @@ int hpusm_knn2_hamming(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t n
   const int64_t rows_per_split = nt == 0 ? 1 : (nt + splits - 1) / splits;
   dim3 grid((unsigned)tiles, (unsigned)splits);
   if (nbytes == 32)
-    HPUSM_LAUNCH(hamming_knn2_kernel<8>, grid, HAM_THREADS, 0, st, q, nq, t, nt, rows_per_split, pi, pd);
+    HPUSM_LAUNCH_TIMED(hamming_knn2_kernel<8>, grid, HAM_THREADS, 0, st, q, nq, t, nt, rows_per_split, pi, pd);
   else
-    HPUSM_LAUNCH(hamming_knn2_kernel<16>, grid, HAM_THREADS, 0, st, q, nq, t, nt, rows_per_split, pi, pd);
+    HPUSM_LAUNCH_TIMED(hamming_knn2_kernel<16>, grid, HAM_THREADS, 0, st, q, nq, t, nt, rows_per_split, pi, pd);
   HPUSM_CHECK_LAUNCH();
   if (splits > 1) {
     HPUSM_LAUNCH(knn2_merge_kernel<int32_t>, (unsigned)((nq + 255) / 256), 256, 0, st, pi, pd, splits, nq,
@@ -299,10 +299,10 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
     dim3 grid((unsigned)tiles, (unsigned)ns);
     int32_t* bi = best_idx ? best_idx + s0 * nq : nullptr;
     if (nbytes == 32)
-      HPUSM_LAUNCH(hamming_knn2_segmented_kernel<8>, grid, HAM_THREADS, 0, st, q, nq, t, seg_offsets + s0,
+      HPUSM_LAUNCH_TIMED(hamming_knn2_segmented_kernel<8>, grid, HAM_THREADS, 0, st, q, nq, t, seg_offsets + s0,
                    ratio, score + s0, bi);
     else
-      HPUSM_LAUNCH(hamming_knn2_segmented_kernel<16>, grid, HAM_THREADS, 0, st, q, nq, t, seg_offsets + s0,
+      HPUSM_LAUNCH_TIMED(hamming_knn2_segmented_kernel<16>, grid, HAM_THREADS, 0, st, q, nq, t, seg_offsets + s0,
                    ratio, score + s0, bi);
     HPUSM_CHECK_LAUNCH();
   }

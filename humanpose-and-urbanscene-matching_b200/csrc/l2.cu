@@ -51,7 +51,7 @@ int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d,
   t_last_fallback = 0;
 
   int engine = mode;
-  if (mode == HPUSM_L2_AUTO) engine = (tc_shape_ok(d) && nt >= 2) ? HPUSM_L2_AUTO : HPUSM_L2_SIMT;
+  if (mode == HPUSM_L2_AUTO) engine = (l2_tc_available() && tc_shape_ok(d) && nt >= 2) ? HPUSM_L2_AUTO : HPUSM_L2_SIMT;
   if (mode == HPUSM_L2_TC_INT || mode == HPUSM_L2_TC_SPLIT)
     HPUSM_REQUIRE(tc_shape_ok(d), HPUSM_ERR_UNSUPPORTED,
                   "hpusm_knn2_l2: tensor-core modes need d %% 16 == 0 and d <= 128, got %d", d);

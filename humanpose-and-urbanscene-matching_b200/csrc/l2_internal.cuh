@@ -14,6 +14,7 @@ int l2_rerank_finalize(const float* q, int64_t nq, const float* t, int d, const 
                        const int32_t* row_list, int64_t n_list, int32_t* idx, float* dist, cudaStream_t st);
 
 // l2_tc.cu (tcgen05 + TMA engine)
+bool l2_tc_available();
 size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode);
 int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist,
                void* ws, size_t ws_bytes, cudaStream_t st, int* resolved_mode, int64_t* fallback_rows);

@@ -269,7 +269,7 @@ int l2_simt_candidates(const float* q, int64_t nq, const float* t, int64_t nt, i
   const int64_t tiles = (rows + SIMT_TQ - 1) / SIMT_TQ;
   const int64_t rows_per_split = nt == 0 ? 1 : (nt + splits - 1) / splits;
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  HPUSM_LAUNCH(l2_simt_knn2_kernel, grid, SIMT_THREADS, smem, st, q, nq, t, nt, d, rows_per_split, row_list,
+  HPUSM_LAUNCH_TIMED(l2_simt_knn2_kernel, grid, SIMT_THREADS, smem, st, q, nq, t, nt, d, rows_per_split, row_list,
                n_list, part_idx);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;

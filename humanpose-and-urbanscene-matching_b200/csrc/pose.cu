@@ -544,7 +544,7 @@ int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int q
   prm.legs_use_tan = (a_l >= 0.0 && a_l < 1.5) ? 1 : 0;
   prm.tan_torso = prm.torso_use_tan ? tan(a_t) : 0.0;
   prm.tan_legs = prm.legs_use_tan ? tan(a_l) : 0.0;
-  HPUSM_LAUNCH(pose_match_batch_kernel, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
+  HPUSM_LAUNCH_TIMED(pose_match_batch_kernel, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
                as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;

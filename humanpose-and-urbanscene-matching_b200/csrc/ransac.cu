@@ -587,7 +587,7 @@ static int launch_score(const float* src, const float* dst, const int64_t* pair_
   HPUSM_REQUIRE(chunk > 0, HPUSM_ERR_UNSUPPORTED, "ransac: %d hypotheses do not fit in shared memory", nhyp);
   const size_t smem = ransac_smem_bytes(nhyp, chunk);
   HPUSM_CUDA_OK(cudaFuncSetAttribute(ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  HPUSM_LAUNCH(ransac_score_kernel, (unsigned)npairs, RS_THREADS, smem, st, src, dst, pair_offsets, thresh, nhyp,
+  HPUSM_LAUNCH_TIMED(ransac_score_kernel, (unsigned)npairs, RS_THREADS, smem, st, src, dst, pair_offsets, thresh, nhyp,
                confidence, seed, chunk, counts, best_hyp, best_count);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;

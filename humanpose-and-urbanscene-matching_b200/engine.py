@@ -47,6 +47,20 @@ def launch_count():
     return int(lib.hpusm_launch_count())
 
 
+def profile_enable(on=True):
+    """Bracket the dominant kernel of every path with CUDA events (roofline accounting in bench.py)."""
+    check(lib.hpusm_profile_enable(1 if on else 0))
+
+
+def profile_collect():
+    """(summed milliseconds, launches) of the bracketed kernels since the last collect."""
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_int64(0)
+    check(lib.hpusm_profile_collect(ctypes.cast(ctypes.byref(ms), ctypes.c_void_p),
+                                    ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
+    return ms.value, n.value
+
+
 # ---- K2: Hamming ------------------------------------------------------------------------------------
 def knn2_hamming(q, t):
     """cv2.BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) (features.py:59): (idx [nq,2] i32, dist [nq,2] i32)."""

@@ -49,6 +49,13 @@ int hpusm_device_count(void);
 /* Running count of kernels this library launched from the calling process (for bench `gpu_launches`). */
 int64_t hpusm_launch_count(void);
 
+/* Event bracketing of the dominant kernel of each path (the kNN sweep, the RANSAC scoring kernel, the pose
+ * kernel), for roofline accounting: while enabled every such launch is bracketed by two CUDA events on its
+ * own stream.  hpusm_profile_collect() synchronises on them, returns the summed duration and the number of
+ * bracketed launches since the previous collect (HOST pointers), and clears the list. */
+int hpusm_profile_enable(int on);
+int hpusm_profile_collect(double* total_ms, int64_t* launches);
+
 /* --------------------------------------------------------------------------------------------------
  * K2  Binary-descriptor kNN, k=2, Hamming norm.
  * Replaces cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(desc_model, trainDescriptors=desc_input, k=2)

@@ -1,0 +1,244 @@
+"""Records the golden vectors under tests/golden/ from the UNMODIFIED reference -- test infrastructure only.
+
+Run in the build container (needs /root/reference; the GPU box never runs this):
+    python oracle/record_golden.py
+
+The reference ships no tests and no expected outputs, so these files ARE the pins:
+every array below is the output of the reference's own modules (imported from /root/reference with
+the three-line shim of SURVEY 8c: inert matplotlib, numpy.math, cv2.SIFT_create) or of the OpenCV /
+NumPy binaries it calls at the cited call sites, on the shipped fixtures (img/*.jpg, json_data/*.json)
+and on seeded synthetic inputs.  Versions are stored in every file.
+"""
+import glob
+import json
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("HPUSM_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(0, REF)
+np.math = math  # pose_comparison.py:12 uses np.math, removed in numpy 2
+
+import cv2  # noqa: E402
+import common as ref_common  # noqa: E402
+import posematching.pose_comparison as ref_pc  # noqa: E402
+import posematching.procrustes as ref_procrustes  # noqa: E402
+import posematching.single_person as ref_sp  # noqa: E402
+import urbanscene.features as ref_features  # noqa: E402
+
+sys.path.insert(0, ROOT)
+import importlib  # noqa: E402
+synth = importlib.import_module("humanpose-and-urbanscene-matching_b200.synth")
+
+VERSIONS = np.array(["opencv %s" % cv2.__version__, "numpy %s" % np.__version__])
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, versions=VERSIONS, **arrays)
+    print("%-28s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
+def matches_to_arrays(raw, nq):
+    idx = -np.ones((nq, 2), np.int32)
+    dist = np.zeros((nq, 2), np.float32)
+    for i, m in enumerate(raw):
+        for j, mm in enumerate(m[:2]):
+            idx[i, j] = mm.trainIdx
+            dist[i, j] = mm.distance
+            assert mm.queryIdx == i
+    return idx, dist
+
+
+def record_scene_pair(tag, img_model, img_input):
+    """C1: features.match_and_draw on a real image pair, SIFT (L2) and ORB (Hamming), BF matcher."""
+    model = cv2.imread(os.path.join(REF, "img", img_model), 0)
+    inp = cv2.imread(os.path.join(REF, "img", img_input), 0)
+    for det_name in ("sift", "orb"):
+        if det_name == "sift":
+            detector, matcher = cv2.SIFT_create(), cv2.BFMatcher(cv2.NORM_L2)  # features.py:13 no longer exists
+        else:
+            detector, matcher = ref_features.init_feature("orb")
+        kp_m, desc_m = detector.detectAndCompute(model, None)
+        kp_i, desc_i = detector.detectAndCompute(inp, None)
+        raw = matcher.knnMatch(desc_m, trainDescriptors=desc_i, k=2)  # features.py:59
+        idx, dist = matches_to_arrays(raw, len(kp_m))
+        p1, p2, _ = ref_features.filter_matches(kp_m, kp_i, raw)  # features.py:45
+        out = ref_features.match_and_draw("w", matcher, desc_m, desc_i, kp_m, kp_i, model, inp.copy(), False)
+        mask, good_m, good_i, H, H2, n_good = out
+        arrays = dict(
+            desc_model=desc_m.astype(np.uint8) if det_name == "sift" else desc_m,
+            desc_input=desc_i.astype(np.uint8) if det_name == "sift" else desc_i,
+            kp_model=np.float32([k.pt for k in kp_m]), kp_input=np.float32([k.pt for k in kp_i]),
+            model_shape=np.array(model.shape), input_shape=np.array(inp.shape),
+            knn_idx=idx, knn_dist=dist, p_model=p1, p_input=p2)
+        if det_name == "sift":
+            assert np.array_equal(desc_m, np.rint(desc_m)) and desc_m.max() <= 255
+        if H is not None:
+            arrays.update(mask=mask, good_model_pts=good_m, good_input_pts=good_i, H=H, H2=H2, n_good=np.array(n_good),
+                          valid=np.array(ref_features.validate_homography(H)))
+        save("scene_%s_%s.npz" % (tag, det_name), **arrays)
+
+
+def record_knn_synthetic():
+    # L2, SIFT-like integer-valued descriptors (C2 generator, small), with planted matches and exact ties
+    q, t = synth.sift_like(700, 1500, seed=10, planted=0.1)
+    t[7] = t[3]  # duplicate rows -> distance ties that must resolve to the lower index
+    t[1400] = t[9]
+    raw = cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, trainDescriptors=t, k=2)
+    idx, dist = matches_to_arrays(raw, len(q))
+    save("knn_l2_siftlike.npz", q=q.astype(np.uint8), t=t.astype(np.uint8), idx=idx, dist=dist)
+    # L2, general float descriptors
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal((300, 128)).astype(np.float32)
+    t = rng.standard_normal((900, 128)).astype(np.float32)
+    t[100:130] = q[:30] + 0.05 * rng.standard_normal((30, 128)).astype(np.float32)
+    raw = cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, trainDescriptors=t, k=2)
+    idx, dist = matches_to_arrays(raw, len(q))
+    save("knn_l2_float.npz", q=q, t=t, idx=idx, dist=dist)
+    # L2, odd width (64-d, SURF-like) and a single train row
+    q = rng.random((50, 64)).astype(np.float32)
+    t = rng.random((1, 64)).astype(np.float32)
+    raw = cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, trainDescriptors=t, k=2)
+    idx, dist = matches_to_arrays(raw, len(q))
+    save("knn_l2_single_train.npz", q=q, t=t, idx=idx, dist=dist)
+    # Hamming, 256-bit, with planted near-duplicates (many ties by construction)
+    q, t = synth.orb_like(600, 2100, seed=12, planted=0.2)
+    raw = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, trainDescriptors=t, k=2)
+    idx, dist = matches_to_arrays(raw, len(q))
+    save("knn_hamming_256.npz", q=q, t=t, idx=idx.astype(np.int32), dist=dist.astype(np.int32))
+    # Hamming, 512-bit (BRISK width)
+    rng = np.random.default_rng(13)
+    q = rng.integers(0, 256, (200, 64), dtype=np.uint8)
+    t = rng.integers(0, 256, (777, 64), dtype=np.uint8)
+    raw = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, trainDescriptors=t, k=2)
+    idx, dist = matches_to_arrays(raw, len(q))
+    save("knn_hamming_512.npz", q=q, t=t, idx=idx.astype(np.int32), dist=dist.astype(np.int32))
+
+
+def record_ransac_cv2():
+    """cv2.findHomography on inputs with a unique consensus set (features.py:66): pins H and mask."""
+    srcs, dsts, Hs, masks, offs = [], [], [], [], [0]
+    cases = [(400, 0.6, 1.0), (2000, 0.3, 1.0), (161, 0.5, 1.0), (64, 0.8, 1.0), (1000, 0.45, 1.0),
+             (400, 0.6, 0.0), (2000, 0.3, 0.0), (161, 0.5, 0.0), (16, 0.9, 0.0), (1000, 0.45, 0.0)]
+    for k, (n, ratio, noise) in enumerate(cases):
+        src, dst, _ = synth.ransac_pair(n, inlier_ratio=ratio, seed=20 + k, noise=noise)
+        H, mask = cv2.findHomography(src.reshape(-1, 1, 2), dst.reshape(-1, 1, 2), cv2.RANSAC, 5.0)
+        srcs.append(src); dsts.append(dst); Hs.append(H); masks.append(mask.ravel()); offs.append(offs[-1] + n)
+    save("ransac_cv2.npz", src=np.concatenate(srcs), dst=np.concatenate(dsts), H=np.stack(Hs),
+         mask=np.concatenate(masks), pair_offsets=np.array(offs, np.int64), noise=np.array([c[2] for c in cases]))
+    # cv2.perspectiveTransform (features.py:77, transformation.py:38)
+    pts = np.random.default_rng(29).uniform(0, 640, (257, 1, 2)).astype(np.float32)
+    save("perspective_transform.npz", pts=pts, H=Hs[0], out=cv2.perspectiveTransform(pts, Hs[0]))
+
+
+def load_fixture_poses():
+    poses, names = [], []
+    for f in sorted(glob.glob(os.path.join(REF, "json_data", "*.json"))):
+        try:
+            people = ref_common.parse_JSON_multi_person(f)  # common.py:215
+        except Exception:
+            continue
+        for k, p in enumerate(people):
+            if p.shape == (18, 2):
+                poses.append(p)
+                names.append("%s#%d" % (os.path.basename(f), k))
+    return np.stack(poses), names
+
+
+def record_pose():
+    poses, names = load_fixture_poses()
+    print("fixture poses:", poses.shape)
+    rng = np.random.default_rng(30)
+    # --- match_single on fixture pairs + synthetic perturbations of fixture poses
+    pairs = [(int(a), int(b)) for a, b in rng.integers(0, len(poses), (300, 2))]
+    models = [poses[a] for a, _ in pairs]
+    inputs = [poses[b] for _, b in pairs]
+    db = synth.pose_database(poses, 500, seed=31)
+    for k in range(len(db)):
+        models.append(poses[k % 7])
+        inputs.append(db[k].astype(np.float64))
+    M, I = np.stack(models), np.stack(inputs)
+    match = np.zeros(len(M), np.int8)
+    score = np.full(len(M), np.nan)
+    transf = np.full((len(M), 22, 2), np.nan)
+    for k in range(len(M)):
+        try:
+            r = ref_sp.match_single(M[k], I[k], True)  # single_person.py:80
+            match[k], score[k], transf[k] = int(r.match_bool), r.error_score, r.input_transformation
+        except (ValueError, np.linalg.LinAlgError):
+            match[k] = -1  # reference raises: np.min of an empty array (no detected joint) / NaN into LAPACK
+    save("pose_match_single.npz", model=M, input=I, match=match, score=score, input_transformation=transf,
+         fixture_poses=poses)
+    # --- find_transformation on body parts, incl. rank-deficient parts (few detected joints)
+    fm, fi, fo, fA, fh = [], [], [], [], []
+    for k in range(200):
+        a, b = poses[rng.integers(len(poses))], poses[rng.integers(len(poses))]
+        rows = [ref_common.split_in_face_legs_torso_v2(x) for x in (a, b)]
+        part = k % 3
+        m, i = rows[0][part].copy(), rows[1][part].copy()
+        if k % 5 == 0:  # leave only 0..2 detected joints
+            keep = rng.integers(0, 3)
+            i[keep:] = 0
+        out, A = ref_common.find_transformation(m, i)  # common.py:37
+        pad = np.zeros((10, 2))
+        mm, ii, oo = pad.copy(), pad.copy(), pad.copy()
+        mm[:len(m)], ii[:len(i)], oo[:len(i)] = m, i, out
+        fm.append(mm); fi.append(ii); fo.append(oo); fh.append(len(A) != 0)
+        fA.append(np.asarray(A) if len(A) else np.zeros((3, 3)))
+    save("pose_find_transformation.npz", model=np.stack(fm), input=np.stack(fi), out=np.stack(fo), A=np.stack(fA),
+         has_A=np.array(fh), npts=np.array([[5, 10, 7][k % 3] for k in range(200)]))
+    # --- feature_scaling / handle_undetected_points
+    fs = np.stack([ref_common.feature_scaling(ref_common.handle_undetected_points(p, p)[0]) for p in poses[:64]])
+    save("pose_feature_scaling.npz", poses=poses[:64], scaled=fs)
+    # --- procrustes (all option combinations) + superimpose / superimpose_old
+    X, Y, D, Z, T = [], [], [], [], []
+    good = poses[((poses != 0).any(2)).sum(1) >= 6]  # procrustes on fewer joints divides 0/0 in the reference
+    opts = [(True, "best"), (False, "best"), (True, True), (True, False), (False, True), (False, False)]
+    for k in range(120):
+        a, b = good[rng.integers(len(good))], good[rng.integers(len(good))]
+        sc, rf = opts[k % 6]
+        d, z, tf = ref_procrustes.procrustes(a, b, sc, rf)  # procrustes.py:150
+        X.append(a); Y.append(b); D.append(d); Z.append(z)
+        T.append(np.concatenate([tf["rotation"].ravel(), [tf["scale"]], tf["translation"]]))
+    so_Z, si_Z, si_n = [], [], []
+    while len(so_Z) < 60:
+        a, b = good[rng.integers(len(good))], good[rng.integers(len(good))]
+        if (((a != 0).any(1)) & ((b != 0).any(1))).sum() < 3:
+            continue
+        X.append(a); Y.append(b)
+        z, _ = ref_procrustes.superimpose_old(a, b)  # procrustes.py:68
+        so_Z.append(z)
+        z2, _ = ref_procrustes.superimpose(a, b)  # procrustes.py:7
+        pad = np.full((18, 2), np.nan)
+        pad[:len(z2)] = z2
+        si_Z.append(pad); si_n.append(len(z2))
+    save("pose_procrustes.npz", X=np.stack(X), Y=np.stack(Y), d=np.array(D), Z=np.stack(Z), tform=np.stack(T),
+         scaling=np.array([o[0] for o in opts]), reflection=np.array([0 if o[1] == "best" else (1 if o[1] else 2) for o in opts]),
+         superimpose_old_Z=np.stack(so_Z), superimpose_Z=np.stack(si_Z), superimpose_n=np.array(si_n))
+    # --- pose_comparison decisions
+    rows = []
+    for k in range(200):
+        A = np.eye(3) + 0.4 * rng.standard_normal((3, 3))
+        d, sh = rng.uniform(0, 0.4), rng.uniform(0, 0.25)
+        rows.append(np.concatenate([A.ravel(), [d, sh,
+                                                ref_pc.decide_torso_shoulders_incl(d, A, 0.236, 19.8, sh, 0.125),
+                                                ref_pc.decide_legs(d, A, 0.082, 24)]]))
+    save("pose_decide.npz", rows=np.stack(rows))
+
+
+if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
+               record_pose):
+        name = getattr(fn, "__name__", "record_scene_pair")
+        if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
+            fn()

@@ -1,0 +1,75 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/hpusm.h declares, argument
+validation and error reporting work without a GPU, and the host-side helpers behave."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hpusm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hpusm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(hpusm):
+    lib = hpusm._lib.lib
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libhpusm.so does not export %s" % n
+    assert set(names) == set(hpusm._lib.SIGNATURES), "ctypes table and header disagree"
+
+
+def test_version_and_error_string(hpusm):
+    lib = hpusm._lib.lib
+    assert lib.hpusm_version() == 100
+    rc = lib.hpusm_knn2_hamming(None, 4, None, 4, 48, None, None, None, 0, None)  # unsupported width, no GPU needed
+    assert rc == hpusm._lib.ERR_UNSUPPORTED
+    assert "48" in hpusm._lib.last_error()
+    rc = lib.hpusm_knn2_l2(None, -1, None, 4, 128, 0, None, None, None, 0, None)
+    assert rc == hpusm._lib.ERR_INVALID
+    with pytest.raises(hpusm._lib.HpusmError):
+        hpusm._lib.check(rc)
+
+
+def test_workspace_queries_are_pure(hpusm):
+    lib = hpusm._lib.lib
+    assert lib.hpusm_knn2_hamming_workspace_bytes(0, 0, 32) == 256
+    assert lib.hpusm_gather_matches_workspace_bytes(5000) % 256 == 0
+    assert lib.hpusm_pose_topk_workspace_bytes(10 ** 7, 16) > 0
+    assert lib.hpusm_knn2_l2_workspace_bytes(1 << 20, 1 << 20, 128, 0) < (8 << 30)
+
+
+def test_no_cpu_fallback(hpusm):
+    """Compute entry points refuse CPU tensors instead of silently computing on the host."""
+    import torch
+    with pytest.raises(ValueError):
+        hpusm.knn2_hamming(torch.zeros(4, 32, dtype=torch.uint8), torch.zeros(4, 32, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        hpusm.knn2_l2(torch.zeros(4, 128), torch.zeros(4, 128))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "humanpose-and-urbanscene-matching_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_synth_generators_are_seeded(hpusm):
+    a, b = hpusm.synth.sift_like(50, 80, seed=3)
+    c, d = hpusm.synth.sift_like(50, 80, seed=3)
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+    assert a.dtype == np.float32 and np.array_equal(a, np.rint(a)) and a.max() <= 255 and a.min() >= 0
+    norms = np.linalg.norm(b, axis=1)
+    assert 400 < norms.mean() < 620
+    q, db, offs, planted = hpusm.synth.orb_database(20, per_image=64, seed=1, ragged=True)
+    assert offs[0] == 0 and offs[-1] == len(db) and len(offs) == 21
+    P = hpusm.synth.pose_database(hpusm.synth.CANONICAL_POSE, 100, seed=2)
+    assert P.shape == (100, 18, 2) and P.dtype == np.float32

@@ -1,0 +1,298 @@
+"""Parity of the CUDA path (through the C ABI of libhpusm.so) with the CPU oracle and the golden vectors
+recorded from the reference.  Needs a B200: run with `-m gpu`.
+
+Bars (BASELINE.json north_star): match indices bit-exact for Hamming and for L2 after the FP32 re-rank
+(ties within 1e-5 relative distance tolerated for general floats); homographies / transforms within 1e-4;
+inlier sets identical under the shared hypothesis seed."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import knn_oracle, pose_oracle, ransac_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def assert_l2_parity(idx, dist, ref_idx, ref_dist, q, t, rel=1e-5):
+    """Indices equal, except where the competing distances are within `rel` (stated tie tolerance)."""
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    np.testing.assert_allclose(dist, ref_dist, rtol=2e-6, atol=0)
+    bad = np.nonzero((idx != ref_idx).any(1))[0]
+    for r in bad:
+        for c in range(2):
+            if idx[r, c] != ref_idx[r, c]:
+                da = np.sqrt(((q[r].astype(np.float64) - t[idx[r, c]].astype(np.float64)) ** 2).sum())
+                db = np.sqrt(((q[r].astype(np.float64) - t[ref_idx[r, c]].astype(np.float64)) ** 2).sum())
+                assert abs(da - db) <= rel * max(da, db), (r, c, da, db)
+
+
+# ---- K2 Hamming ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["knn_hamming_256.npz", "knn_hamming_512.npz"])
+def test_hamming_golden_cv2(hpusm, cuda_device, name):
+    g = load_golden(name)
+    idx, dist = hpusm.knn2_hamming(dev(g["q"], cuda_device), dev(g["t"], cuda_device))
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["idx"])
+    np.testing.assert_array_equal(dist.cpu().numpy(), g["dist"])
+
+
+def test_hamming_scene_pair_orb(hpusm, cuda_device):
+    """C1 with ORB: 14138 x 9130 descriptors of pisa1 / pisa2, cv2.BFMatcher result recorded from the reference."""
+    g = load_golden("scene_pisa1_pisa2_orb.npz")
+    idx, dist = hpusm.knn2_hamming(dev(g["desc_model"], cuda_device), dev(g["desc_input"], cuda_device))
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["knn_idx"])
+    np.testing.assert_array_equal(dist.cpu().numpy().astype(np.float32), g["knn_dist"])
+    keep, count = hpusm.ratio_filter(idx, dist, 0.8)
+    assert int(count.item()) == len(g["p_model"]) == 250
+    p_q, p_t, sel, cnt = hpusm.gather_matches(dev(g["kp_model"], cuda_device), dev(g["kp_input"], cuda_device), idx, keep)
+    n = int(cnt.item())
+    np.testing.assert_array_equal(p_q[:n].cpu().numpy(), g["p_model"].reshape(-1, 2))
+    np.testing.assert_array_equal(p_t[:n].cpu().numpy(), g["p_input"].reshape(-1, 2))
+
+
+@pytest.mark.parametrize("nq,nt,nb", [(1, 1, 32), (3, 2, 32), (513, 129, 32), (1000, 5000, 32), (37, 70000, 32),
+                                      (4100, 300, 64), (5, 0, 32), (0, 5, 32)])
+def test_hamming_edge_shapes(hpusm, cuda_device, nq, nt, nb):
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = rng.integers(0, 256, (nq, nb), dtype=np.uint8)
+    t = rng.integers(0, 4, (nt, nb), dtype=np.uint8) if nt < 100 else rng.integers(0, 256, (nt, nb), dtype=np.uint8)
+    idx, dist = hpusm.knn2_hamming(dev(q, cuda_device), dev(t, cuda_device))
+    ri, rd = knn_oracle.knn2_hamming(q, t)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+    np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+
+
+def test_hamming_ties_lowest_index(hpusm, cuda_device):
+    q = np.zeros((600, 32), np.uint8)
+    t = np.zeros((3000, 32), np.uint8)  # every distance is 0: the answer must be train rows 0 and 1
+    idx, dist = hpusm.knn2_hamming(dev(q, cuda_device), dev(t, cuda_device))
+    assert (idx.cpu().numpy() == np.array([0, 1])).all() and (dist.cpu().numpy() == 0).all()
+
+
+def test_hamming_segmented_retrieval(hpusm, cuda_device):
+    """C3 shape at small scale: ragged database images incl. nearly empty ones."""
+    query, db, offs, planted = hpusm.synth.orb_database(60, per_image=300, seed=5, ragged=True)
+    score, best = hpusm.knn2_hamming_segmented(dev(query, cuda_device), dev(db, cuda_device), dev(offs, cuda_device), 0.8,
+                                               want_best_idx=True)
+    rs, rb = knn_oracle.segmented_scores(query, db, offs, 0.8)
+    np.testing.assert_array_equal(score.cpu().numpy(), rs)
+    np.testing.assert_array_equal(best.cpu().numpy(), rb)
+    top = np.argsort(-rs, kind="stable")[:len(planted)]
+    assert set(top.tolist()) & set(planted.tolist())
+
+
+def test_knn_merge_equals_unsplit(hpusm, cuda_device):
+    q, t = hpusm.synth.orb_like(700, 9000, seed=3)
+    full_i, full_d = hpusm.knn2_hamming(dev(q, cuda_device), dev(t, cuda_device))
+    bounds = [0, 2500, 2501, 9000]
+    pi, pd = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        i, d = hpusm.knn2_hamming(dev(q, cuda_device), dev(t[a:b], cuda_device))
+        pi.append(torch.where(i >= 0, i + a, i))
+        pd.append(d)
+    mi, md = hpusm.engine.knn2_merge(torch.stack(pi), torch.stack(pd))
+    assert torch.equal(mi, full_i) and torch.equal(md, full_d)
+
+
+# ---- K1 L2 ----------------------------------------------------------------------------------------------
+L2_MODES = ["auto", "simt"]
+
+
+def _mode(hpusm, name):
+    return {"auto": hpusm.engine.L2_AUTO, "simt": hpusm.engine.L2_SIMT, "tc_int": hpusm.engine.L2_TC_INT,
+            "tc_split": hpusm.engine.L2_TC_SPLIT}[name]
+
+
+@pytest.mark.parametrize("mode", L2_MODES)
+@pytest.mark.parametrize("name", ["knn_l2_siftlike.npz", "knn_l2_float.npz", "knn_l2_single_train.npz"])
+def test_l2_golden_cv2(hpusm, cuda_device, name, mode):
+    g = load_golden(name)
+    q, t = g["q"].astype(np.float32), g["t"].astype(np.float32)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=_mode(hpusm, mode))
+    if name == "knn_l2_siftlike.npz":  # integer-valued: bit exact, ties included
+        np.testing.assert_array_equal(idx.cpu().numpy(), g["idx"])
+        np.testing.assert_array_equal(dist.cpu().numpy(), g["dist"])
+    else:
+        assert_l2_parity(idx, dist, g["idx"], g["dist"], q, t)
+
+
+@pytest.mark.parametrize("mode", L2_MODES)
+def test_l2_scene_pair_sift(hpusm, cuda_device, mode):
+    """C1: pisa1 x pisa2 SIFT, 4323 x 1085 x 128; knnMatch + filter_matches recorded from the reference."""
+    g = load_golden("scene_pisa1_pisa2_sift.npz")
+    q, t = g["desc_model"].astype(np.float32), g["desc_input"].astype(np.float32)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=_mode(hpusm, mode))
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["knn_idx"])
+    np.testing.assert_array_equal(dist.cpu().numpy(), g["knn_dist"])
+    keep, count = hpusm.ratio_filter(idx, dist, 0.8)
+    assert int(count.item()) == 161
+    p_q, p_t, sel, cnt = hpusm.gather_matches(dev(g["kp_model"], cuda_device), dev(g["kp_input"], cuda_device), idx, keep)
+    np.testing.assert_array_equal(p_q[:161].cpu().numpy(), g["p_model"].reshape(-1, 2))
+    np.testing.assert_array_equal(p_t[:161].cpu().numpy(), g["p_input"].reshape(-1, 2))
+
+
+@pytest.mark.parametrize("mode", L2_MODES)
+@pytest.mark.parametrize("nq,nt,d,kind", [(1, 2, 128, "int"), (65, 63, 128, "int"), (300, 20000, 128, "int"),
+                                          (2000, 3000, 128, "float"), (129, 4097, 64, "float"), (50, 700, 36, "float"),
+                                          (7, 0, 128, "int"), (0, 7, 128, "int")])
+def test_l2_edge_shapes(hpusm, cuda_device, nq, nt, d, kind, mode):
+    rng = np.random.default_rng(nq + 3 * nt + d)
+    if kind == "int":
+        q, t = hpusm.synth.sift_like(nq, nt, seed=nq + nt, planted=0.2, d=d)
+    else:
+        q = rng.standard_normal((nq, d)).astype(np.float32)
+        t = rng.standard_normal((nt, d)).astype(np.float32)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=_mode(hpusm, mode))
+    ri, rd = knn_oracle.knn2_l2(q, t)
+    if kind == "int":
+        np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+        np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+    else:
+        assert_l2_parity(idx, dist, ri, rd, q, t)
+
+
+def test_l2_auto_equals_simt_at_scale(hpusm, cuda_device):
+    """Size-independent property at a size no CPU oracle reaches quickly: the tensor-core engine and the exact
+    CUDA-core brute force agree bit for bit on integer-valued descriptors (65536 x 262144)."""
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    t = torch.randint(0, 120, (262144, 128), generator=g, device=cuda_device).float()
+    q = torch.randint(0, 120, (65536, 128), generator=g, device=cuda_device).float()
+    q[:1000] = t[5000:6000] + torch.randint(0, 3, (1000, 128), generator=g, device=cuda_device).float()
+    ia, da = hpusm.knn2_l2(q, t, mode=hpusm.engine.L2_AUTO)
+    ib, db_ = hpusm.knn2_l2(q, t, mode=hpusm.engine.L2_SIMT)
+    assert torch.equal(ia, ib) and torch.equal(da, db_)
+    assert (ia[:1000, 0].cpu() == torch.arange(5000, 6000)).all()
+
+
+# ---- K3 RANSAC --------------------------------------------------------------------------------------------
+def test_ransac_counts_identical_to_oracle(hpusm, cuda_device):
+    src, dst, offs = hpusm.synth.ransac_batch(6, 700, inlier_ratio=0.4, seed=8)
+    offs = np.array([0, 700, 1400, 1403, 1407, 3000, 4200], np.int64)  # ragged pairs incl. K < 4 and K == 4
+    counts = hpusm.ransac_score_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device), 5.0, 512, seed=9)
+    ref = ransac_oracle.score_batch(src, dst, offs, 5.0, 512, 9)
+    np.testing.assert_array_equal(counts.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("confidence", [0.995, 0.0])
+def test_ransac_homography_identical_inlier_sets(hpusm, cuda_device, confidence):
+    g = load_golden("ransac_cv2.npz")
+    src, dst, offs = g["src"], g["dst"], g["pair_offsets"]
+    H, mask, ninl, best = hpusm.ransac_homography_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device),
+                                                        5.0, 2000, confidence, seed=7)
+    rH, rmask, rninl, rbest = ransac_oracle.homography_batch(src, dst, offs, 5.0, 2000, confidence, 7)
+    np.testing.assert_array_equal(best.cpu().numpy(), rbest)
+    np.testing.assert_array_equal(mask.cpu().numpy(), rmask)
+    np.testing.assert_array_equal(ninl.cpu().numpy(), rninl)
+    np.testing.assert_allclose(H.cpu().numpy(), rH, rtol=1e-7, atol=1e-7)
+    # and against cv2 itself where its result does not depend on its private sample sequence (noise-free inliers)
+    Hn = H.cpu().numpy()
+    for p in np.nonzero(g["noise"] == 0.0)[0]:
+        np.testing.assert_array_equal(mask.cpu().numpy()[offs[p]:offs[p + 1]], g["mask"][offs[p]:offs[p + 1]])
+        np.testing.assert_allclose(Hn[p], g["H"][p], rtol=1e-4, atol=1e-4 * np.abs(g["H"][p]).max())
+
+
+def test_ransac_scene_pair(hpusm, cuda_device):
+    g = load_golden("scene_pisa1_pisa2_sift.npz")
+    src, dst = g["p_model"].reshape(-1, 2), g["p_input"].reshape(-1, 2)
+    offs = np.array([0, len(src)], np.int64)
+    H, mask, ninl, best = hpusm.ransac_homography_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device),
+                                                        5.0, 2000, 0.995, seed=0)
+    rH, rmask, rninl, rbest = ransac_oracle.homography_batch(src, dst, offs, 5.0, 2000, 0.995, 0)
+    np.testing.assert_array_equal(mask.cpu().numpy(), rmask)
+    np.testing.assert_allclose(H.cpu().numpy(), rH, rtol=1e-6, atol=1e-6)
+
+
+def test_ransac_no_model(hpusm, cuda_device):
+    src = np.zeros((10, 2), np.float32)  # all points coincide: every sample is degenerate
+    offs = np.array([0, 10], np.int64)
+    H, mask, ninl, best = hpusm.ransac_homography_batch(dev(src, cuda_device), dev(src, cuda_device), dev(offs, cuda_device),
+                                                        5.0, 64, 0.995, seed=1)
+    assert torch.isnan(H).all() and int(ninl.item()) == 0 and int(best.item()) == -1 and int(mask.sum()) == 0
+
+
+def test_perspective_transform_cv2(hpusm, cuda_device):
+    g = load_golden("perspective_transform.npz")
+    out = hpusm.perspective_transform(dev(g["pts"], cuda_device), dev(g["H"], cuda_device))
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-6, atol=1e-5)
+
+
+# ---- K4 pose ------------------------------------------------------------------------------------------------
+def test_affine_lsq_reference(hpusm, cuda_device):
+    g = load_golden("pose_find_transformation.npz")
+    for npts in (5, 7, 10):
+        sel = np.nonzero(g["npts"] == npts)[0]
+        out, A, has = hpusm.affine_lsq_batch(dev(g["model"][sel][:, :npts], cuda_device), dev(g["input"][sel][:, :npts], cuda_device))
+        np.testing.assert_array_equal(has.cpu().numpy().astype(bool), g["has_A"][sel])
+        np.testing.assert_allclose(out.cpu().numpy(), g["out"][sel][:, :npts], rtol=1e-4, atol=1e-6)
+        hs = g["has_A"][sel]
+        np.testing.assert_allclose(A.cpu().numpy()[hs], g["A"][sel][hs], rtol=1e-4, atol=1e-6)
+
+
+def test_procrustes_reference(hpusm, cuda_device):
+    g = load_golden("pose_procrustes.npz")
+    n = len(g["d"])
+    for o in range(6):
+        sel = np.arange(o, n, 6)
+        rf = int(g["reflection"][o])
+        refl = "best" if rf == 0 else (rf == 1)
+        d, Z, tf = hpusm.procrustes_batch(dev(g["X"][sel], cuda_device), dev(g["Y"][sel], cuda_device), bool(g["scaling"][o]), refl)
+        np.testing.assert_allclose(d.cpu().numpy(), g["d"][sel], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(Z.cpu().numpy(), g["Z"][sel], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(tf.cpu().numpy(), g["tform"][sel], rtol=1e-4, atol=1e-6)
+
+
+def _pose_groups(M, I):
+    """Group the golden (model, input) pairs by model pose so each group is one `query vs db` launch."""
+    keys = {}
+    for k in range(len(M)):
+        keys.setdefault(M[k].tobytes(), []).append(k)
+    return list(keys.values())
+
+
+def test_pose_match_single_reference(hpusm, cuda_device):
+    """GPU vs the oracle on the float32-rounded poses (tight), and vs the reference's own float64 results (1e-4)."""
+    g = load_golden("pose_match_single.npz")
+    M32, I32 = g["model"].astype(np.float32), g["input"].astype(np.float32)
+    n_tight = n_ref = n_flip = 0
+    for rows in _pose_groups(M32, I32):
+        q = M32[rows[0]]
+        match, score, detail = hpusm.pose_match_batch(dev(q, cuda_device), dev(I32[rows], cuda_device), True, want_detail=True)
+        match, score, detail = match.cpu().numpy(), score.cpu().numpy(), detail.cpu().numpy()
+        for j, k in enumerate(rows):
+            with np.errstate(all="ignore"):
+                try:
+                    r = pose_oracle.match_single(q.astype(np.float64), I32[k].astype(np.float64))
+                except (ValueError, np.linalg.LinAlgError):
+                    assert match[j] == 0
+                    continue
+            if not np.isfinite(r["error_score"]):
+                continue
+            assert bool(match[j]) == r["match"], k
+            np.testing.assert_allclose(detail[j, 7], r["error_score"], rtol=1e-7, atol=1e-10)
+            np.testing.assert_allclose(detail[j, 35:].reshape(22, 2), r["input_transformation"], rtol=1e-6, atol=1e-8)
+            n_tight += 1
+            if g["match"][k] >= 0 and np.isfinite(g["score"][k]):
+                np.testing.assert_allclose(score[j], g["score"][k], rtol=1e-4, atol=1e-6)
+                n_flip += int(bool(match[j]) != bool(g["match"][k]))  # float32 storage of the database can flip a borderline
+                n_ref += 1
+    assert n_tight > 600 and n_ref > 600 and n_flip <= 2
+
+
+def test_pose_topk(hpusm, cuda_device):
+    rng = np.random.default_rng(4)
+    n = 200000
+    match = (rng.random(n) < 0.3).astype(np.uint8)
+    score = rng.random(n).astype(np.float32)
+    score[rng.integers(0, n, 50)] = np.nan
+    score[1234] = score[77] = 0.0  # tie at the top: lower index first
+    match[1234] = match[77] = 1
+    ts, ti, cnt = hpusm.pose_topk(dev(match, cuda_device), dev(score, cuda_device), k=16, index_offset=1000)
+    ok = (match == 1) & ~np.isnan(score)
+    order = np.lexsort((np.arange(n), np.where(ok, score, np.inf)))[:16]
+    np.testing.assert_array_equal(ti.cpu().numpy(), order + 1000)
+    np.testing.assert_array_equal(ts.cpu().numpy(), score[order])
+    assert int(cnt.item()) == int(match.sum())

@@ -1,0 +1,161 @@
+"""The CPU oracle (oracle/) against the golden vectors recorded from the unmodified reference + cv2/numpy
+(oracle/record_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import knn_oracle, pose_oracle, ransac_oracle
+from conftest import load_golden
+
+
+@pytest.mark.parametrize("name,exact", [("knn_l2_siftlike.npz", True), ("knn_l2_float.npz", False),
+                                        ("knn_l2_single_train.npz", False)])
+def test_knn_l2_matches_cv2(name, exact):
+    g = load_golden(name)
+    q, t = g["q"].astype(np.float32), g["t"].astype(np.float32)
+    idx, dist = knn_oracle.knn2_l2(q, t)
+    np.testing.assert_array_equal(idx, g["idx"])  # these fixtures hold no near-ties beyond exact duplicates
+    if exact:
+        np.testing.assert_array_equal(dist, g["dist"])  # integer-valued descriptors: every step is exact
+    else:
+        np.testing.assert_allclose(dist, g["dist"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["knn_hamming_256.npz", "knn_hamming_512.npz"])
+def test_knn_hamming_matches_cv2(name):
+    g = load_golden(name)
+    idx, dist = knn_oracle.knn2_hamming(g["q"], g["t"])
+    np.testing.assert_array_equal(idx, g["idx"])
+    np.testing.assert_array_equal(dist, g["dist"])
+
+
+@pytest.mark.parametrize("det", ["sift", "orb"])
+def test_scene_pair_knn_and_ratio(det):
+    """C1: pisa1 x pisa2 through knnMatch (features.py:59) and filter_matches (features.py:45-55)."""
+    g = load_golden("scene_pisa1_pisa2_%s.npz" % det)
+    if det == "sift":
+        idx, dist = knn_oracle.knn2_l2(g["desc_model"].astype(np.float32), g["desc_input"].astype(np.float32))
+        np.testing.assert_array_equal(dist, g["knn_dist"])
+    else:
+        idx, dist = knn_oracle.knn2_hamming(g["desc_model"], g["desc_input"])
+        np.testing.assert_array_equal(dist.astype(np.float32), g["knn_dist"])
+    np.testing.assert_array_equal(idx, g["knn_idx"])
+    p1, p2, _ = knn_oracle.filter_matches_points(g["kp_model"], g["kp_input"], idx, dist)
+    np.testing.assert_array_equal(p1, g["p_model"])
+    np.testing.assert_array_equal(p2, g["p_input"])
+    assert len(p1) == {"sift": 161, "orb": 250}[det]
+
+
+def test_ransac_matches_cv2():
+    """findHomography (features.py:66).  cv2's sampler cannot be seeded, so what can be pinned on it is:
+    (a) noise-free inliers: the consensus set is unique -> identical mask, H within 1e-4;
+    (b) noisy inliers: the winning minimal model (hence the mask) depends on the sample sequence, so the
+        refinement is pinned instead: our least-squares + LM fit ON cv2's OWN MASK gives cv2's H within
+        1e-4, and our own mask is a subset of the true consensus that overlaps cv2's by >= 90 %."""
+    g = load_golden("ransac_cv2.npz")
+    offs = g["pair_offsets"]
+    H, mask, ninl, best = ransac_oracle.homography_batch(g["src"], g["dst"], offs, 5.0, 2000, 0.995, 7)
+    for p in range(len(H)):
+        lo, hi = offs[p], offs[p + 1]
+        Hc, mc = g["H"][p], g["mask"][lo:hi]
+        tol = dict(rtol=1e-4, atol=1e-4 * np.abs(Hc).max())
+        assert abs(H[p, 2, 2] - 1.0) < 1e-15
+        if g["noise"][p] == 0.0:
+            np.testing.assert_array_equal(mask[lo:hi], mc)
+            np.testing.assert_allclose(H[p], Hc, **tol)
+        else:
+            Hr = ransac_oracle.refine(g["src"][lo:hi], g["dst"][lo:hi], mc, Hc)
+            np.testing.assert_allclose(Hr, Hc, **tol)
+            both = (mask[lo:hi] & mc).sum()
+            assert both >= 0.9 * mc.sum() and both >= 0.9 * mask[lo:hi].sum()
+
+
+def test_ransac_scene_pair_low_inlier_ratio():
+    """C1 matches (161, ~11 % inliers): the consensus set is not unique, so only sanity is asserted."""
+    g = load_golden("scene_pisa1_pisa2_sift.npz")
+    src, dst = g["p_model"].reshape(-1, 2), g["p_input"].reshape(-1, 2)
+    H, mask, ninl, best = ransac_oracle.homography_batch(src, dst, [0, len(src)], 5.0, 2000, 0.995, 0)
+    assert ninl[0] == mask.sum() and ninl[0] >= 8
+    counts = ransac_oracle.score_batch(src, dst, [0, len(src)], 5.0, 2000, 0)
+    assert counts.max() == counts[0, best[0]] or counts[0, best[0]] > 0
+
+
+def test_ransac_sample_table_properties():
+    for K in (4, 5, 17, 2000):
+        seen = set()
+        for h in range(200):
+            s = ransac_oracle.sample4(3, 1, h, K)
+            assert len(set(s.tolist())) == 4 and s.max() < K
+            seen.update(s.tolist())
+        assert len(seen) == min(K, len(seen))
+    assert not np.array_equal(ransac_oracle.sample4(3, 1, 0, 100), ransac_oracle.sample4(3, 2, 0, 100))
+
+
+def test_pose_match_single_matches_reference():
+    g = load_golden("pose_match_single.npz")
+    M, I = g["model"], g["input"]
+    n_checked = 0
+    for k in range(len(M)):
+        ref_match = int(g["match"][k])
+        with np.errstate(all="ignore"):
+            try:
+                r = pose_oracle.match_single(M[k], I[k])
+            except (ValueError, np.linalg.LinAlgError):
+                assert ref_match == -1
+                continue
+        if ref_match == -1 or not np.isfinite(g["score"][k]):
+            continue  # the reference itself fed NaN to LAPACK here; nothing to pin
+        assert int(r["match"]) == ref_match, k
+        np.testing.assert_allclose(r["error_score"], g["score"][k], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r["input_transformation"], g["input_transformation"][k], rtol=1e-8, atol=1e-10)
+        n_checked += 1
+    assert n_checked > 600
+
+
+def test_pose_find_transformation_matches_reference():
+    g = load_golden("pose_find_transformation.npz")
+    for k in range(len(g["npts"])):
+        n = int(g["npts"][k])
+        out, A = pose_oracle.find_transformation(g["model"][k][:n], g["input"][k][:n])
+        assert (len(A) != 0) == bool(g["has_A"][k])
+        np.testing.assert_allclose(out, g["out"][k][:n], rtol=1e-9, atol=1e-9)
+        if len(A):
+            np.testing.assert_allclose(A, g["A"][k], rtol=1e-8, atol=1e-9)
+
+
+def test_pose_feature_scaling_matches_reference():
+    g = load_golden("pose_feature_scaling.npz")
+    for p, s in zip(g["poses"], g["scaled"]):
+        with np.errstate(all="ignore"):
+            got = pose_oracle.feature_scaling(pose_oracle.handle_undetected_points(p, p)[0])
+        np.testing.assert_allclose(got, s, rtol=1e-12, equal_nan=True)
+    # the documented quirk: the minimum runs over both columns
+    q = np.array([[100.0, 20.0], [150.0, 50.0], [200.0, 80.0]])
+    assert pose_oracle.feature_scaling(q)[0, 0] == (100.0 - 20.0) / (200.0 - 20.0)
+
+
+def test_pose_procrustes_matches_reference():
+    g = load_golden("pose_procrustes.npz")
+    for k in range(len(g["d"])):
+        sc, rf = bool(g["scaling"][k % 6]), int(g["reflection"][k % 6])
+        refl = "best" if rf == 0 else (rf == 1)
+        d, Z, tf = pose_oracle.procrustes(g["X"][k], g["Y"][k], sc, refl)
+        np.testing.assert_allclose(d, g["d"][k], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(Z, g["Z"][k], rtol=1e-9, atol=1e-9)
+        got = np.concatenate([tf["rotation"].ravel(), [tf["scale"]], tf["translation"]])
+        np.testing.assert_allclose(got, g["tform"][k], rtol=1e-8, atol=1e-9)
+    n0 = len(g["d"])
+    for j in range(len(g["superimpose_old_Z"])):
+        a, b = g["X"][n0 + j], g["Y"][n0 + j]
+        Z, _ = pose_oracle.superimpose_old(a, b)
+        np.testing.assert_allclose(Z, g["superimpose_old_Z"][j], rtol=1e-9, atol=1e-9)
+        Z2, _ = pose_oracle.superimpose(a, b)
+        assert len(Z2) == g["superimpose_n"][j]
+        np.testing.assert_allclose(Z2, g["superimpose_Z"][j][:len(Z2)], rtol=1e-9, atol=1e-9)
+
+
+def test_pose_decide_matches_reference():
+    rows = load_golden("pose_decide.npz")["rows"]
+    for r in rows:
+        A, d, sh = r[:9].reshape(3, 3), r[9], r[10]
+        assert pose_oracle.decide_torso_shoulders_incl(d, A, 0.236, 19.8, sh, 0.125) == bool(r[11])
+        assert pose_oracle.decide_legs(d, A, 0.082, 24) == bool(r[12])
