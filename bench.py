@@ -118,13 +118,26 @@ class ClockSampler:
 
 
 # ---- reference CPU path (cv2.BFMatcher.knnMatch + the ratio loop of features.filter_matches) --------------------
+CV2_MAX_TRAIN = 1 << 17  # cv2.BFMatcher asserts train rows < 2**18 (IMGIDX_ONE): sweep the database in chunks
+
+
 def reference_step(q_np, t_np, ratio=0.8):
-    """features.py:59 + :45-55 without the keypoint gather: returns the number of ratio survivors."""
+    """features.py:59 + :45-55 without the keypoint gather: returns the number of ratio survivors.  The database is
+    swept in chunks below cv2's 2**18-row limit and the per-chunk top-2 lists are merged (lowest index wins ties)."""
     import cv2
-    raw = cv2.BFMatcher(cv2.NORM_L2).knnMatch(q_np, trainDescriptors=t_np, k=2)
+    matcher = cv2.BFMatcher(cv2.NORM_L2)
+    nq = len(q_np)
+    if len(t_np) <= CV2_MAX_TRAIN:
+        raw = matcher.knnMatch(q_np, trainDescriptors=t_np, k=2)
+        return sum(1 for m in raw if len(m) == 2 and m[0].distance < m[1].distance * ratio)
+    best_d = np.full((nq, 2), np.inf, np.float32)
+    for lo in range(0, len(t_np), CV2_MAX_TRAIN):
+        raw = matcher.knnMatch(q_np, trainDescriptors=t_np[lo:lo + CV2_MAX_TRAIN], k=2)
+        d = np.array([[m[0].distance, m[1].distance if len(m) > 1 else np.inf] for m in raw], np.float32)
+        best_d = np.sort(np.concatenate([best_d, d], 1), axis=1, kind="stable")[:, :2]
     kept = 0
-    for m in raw:
-        if len(m) == 2 and m[0].distance < m[1].distance * ratio:
+    for d0, d1 in best_d.tolist():  # the ratio test stays a Python-double comparison as in features.py:48
+        if d1 != float("inf") and d0 < d1 * ratio:
             kept += 1
     return kept
 

@@ -9,7 +9,7 @@ namespace hpusm {
 static thread_local int t_last_mode = HPUSM_L2_SIMT;
 static thread_local int64_t t_last_fallback = 0;
 
-static bool tc_shape_ok(int d) { return d % 16 == 0 && d >= 16 && d <= 128; }
+static bool tc_shape_ok(int d) { return d == 128; }  // SIFT width; other widths take the FP32 engine
 
 }  // namespace hpusm
 
@@ -54,7 +54,7 @@ int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d,
   if (mode == HPUSM_L2_AUTO) engine = (l2_tc_available() && tc_shape_ok(d) && nt >= 2) ? HPUSM_L2_AUTO : HPUSM_L2_SIMT;
   if (mode == HPUSM_L2_TC_INT || mode == HPUSM_L2_TC_SPLIT)
     HPUSM_REQUIRE(tc_shape_ok(d), HPUSM_ERR_UNSUPPORTED,
-                  "hpusm_knn2_l2: tensor-core modes need d %% 16 == 0 and d <= 128, got %d", d);
+                  "hpusm_knn2_l2: the tensor-core engine is built for d == 128, got %d", d);
 
   if (engine == HPUSM_L2_SIMT) {
     t_last_mode = HPUSM_L2_SIMT;

@@ -1,12 +1,462 @@
-// placeholder until the tcgen05 engine lands: AUTO resolves to the exact SIMT engine.
+// K1 (tensor-core engine): brute-force L2 kNN (k=2) as a dense contraction on tcgen05, sm_100a only.
+//
+// Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) at reference urbanscene/features.py:59.
+//
+//   ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t      ->  per query, order the database by  key = ||t||^2 - 2 q.t
+//
+// OpenCV SIFT descriptors are integer valued (0..255) stored as float32, so bf16 operands are exact and
+// the FP32 accumulation of 128 products (< 2^23) is exact: key is the exact integer, the fused top-2 on
+// (key, index) is the exact answer, and ties fall to the lower index exactly as OpenCV resolves them.  The
+// prep kernel verifies that property for every value; when it does not hold the kernel is skipped on the
+// device (no host round trip) and the FP32 CUDA-core engine produces the candidates instead.  Either way the
+// candidates go through l2_rerank_finalize (l2_simt.cu): exact FP32 distances from the ORIGINAL float32
+// rows, lexicographic (d2, index) top-2, sqrtf -- the numbers DMatch.distance carries.
+//
+// Kernel shape (one persistent CTA per SM, 384 threads, warp specialised):
+//   warp 0     TMA producer: the unit's 256 queries (2 x [128 x 128] bf16, SWIZZLE_128B, 64 KB, loaded once per
+//              unit) and a 4-stage ring of database tiles ([128 rows x 128] bf16, 32 KB per stage)
+//   warp 1     MMA issuer: per database tile 2 x 8 tcgen05.mma (M=128, N=128, K=16, kind::f16, cta_group::1)
+//              into one of two TMEM accumulator buffers (2 x 2 x 128 columns = all 512 columns)
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, key = fma(-2, acc, tn),
+//              min over 8 keys + one compare guards the (rare) top-2 insertion; the running top-2 lives in
+//              registers for the whole database sweep, so there is no reduction anywhere.
+// A unit is (256 queries) x (one split of the database); a CTA walks units round-robin so all CTAs sweep the
+// database in the same order and every database tile is fetched from HBM once and then served by L2.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <float.h>
 #include "common.cuh"
 #include "l2_internal.cuh"
+
 namespace hpusm {
-bool l2_tc_available() { return false; }
-size_t l2_tc_workspace_bytes(int64_t, int64_t, int, int) { return 256; }
-int l2_tc_knn2(const float*, int64_t, const float*, int64_t, int, int, int32_t*, float*, void*, size_t, cudaStream_t,
-               int*, int64_t*) {
-  set_error("tcgen05 L2 engine not built");
-  return HPUSM_ERR_UNSUPPORTED;
+
+constexpr int TC_D = 128;            // descriptor length the engine is built for
+constexpr int TC_QB = 256;           // queries per unit (two M=128 MMA tiles)
+constexpr int TC_TN = 128;           // database rows per tile (MMA N)
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 384;
+constexpr int TC_HALF_BYTES = 128 * 128;                    // [128 rows][64 bf16] = 16 KB, one swizzle-128B slab
+constexpr int TC_A_BYTES = 2 * 2 * TC_HALF_BYTES;           // 2 query tiles x 2 k-halves
+constexpr int TC_B_BYTES = 2 * TC_HALF_BYTES;               // per stage
+constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows 128 B apart inside an 8-row group,
+// 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128.
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TN >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---- operand preparation --------------------------------------------------------------------------------
+// One warp per row: float32 -> bf16, ||row||^2 (database side), and the exactness check.  A value passes when
+// it is an integer with |v| <= 256: then bf16 holds it exactly and every partial sum of the contraction is
+// below 2^24.  flag[0] |= 1 otherwise.
+__global__ void __launch_bounds__(256)
+l2_tc_prep_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, __nv_bfloat16* __restrict__ xb,
+                  float* __restrict__ norm2, int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  if (row >= n) {  // padding rows of the norm array: never selected
+    if (norm2 && lane == 0) norm2[row] = __int_as_float(0x7f800000);
+    return;
+  }
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * TC_D) + lane);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  bool bad = false;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bad |= !(fabsf(f[i]) <= 256.f) || f[i] != rintf(f[i]);
+    s = fmaf(f[i], f[i], s);
+  }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 packed;
+  packed.x = *reinterpret_cast<uint32_t*>(&lo);
+  packed.y = *reinterpret_cast<uint32_t*>(&hi);
+  reinterpret_cast<uint2*>(xb + row * TC_D)[lane] = packed;
+  if (norm2) {
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) norm2[row] = s;
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 1);
+}
+
+// ---- the contraction + fused top-2 ------------------------------------------------------------------------
+struct TcTop2 {
+  float k0, k1;
+  int i0, i1;
+};
+
+__device__ __forceinline__ void tc_insert(TcTop2& t, float v, int col) {
+  if (v < t.k1) {  // strict: columns reach a thread in increasing index order, so ties keep the lower index
+    if (v < t.k0) { t.k1 = t.k0; t.i1 = t.i0; t.k0 = v; t.i0 = col; }
+    else { t.k1 = v; t.i1 = col; }
+  }
+}
+
+__device__ __forceinline__ void tc_process32(const uint32_t (&acc)[32], const float4 (&tn)[8], int col, TcTop2& t) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+    const float4 ta = tn[2 * g], tb = tn[2 * g + 1];
+    v[0] = fmaf(-2.f, __uint_as_float(acc[8 * g + 0]), ta.x); v[1] = fmaf(-2.f, __uint_as_float(acc[8 * g + 1]), ta.y);
+    v[2] = fmaf(-2.f, __uint_as_float(acc[8 * g + 2]), ta.z); v[3] = fmaf(-2.f, __uint_as_float(acc[8 * g + 3]), ta.w);
+    v[4] = fmaf(-2.f, __uint_as_float(acc[8 * g + 4]), tb.x); v[5] = fmaf(-2.f, __uint_as_float(acc[8 * g + 5]), tb.y);
+    v[6] = fmaf(-2.f, __uint_as_float(acc[8 * g + 6]), tb.z); v[7] = fmaf(-2.f, __uint_as_float(acc[8 * g + 7]), tb.w);
+    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+    if (m < t.k1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc_insert(t, v[j], col + 8 * g + j);
+    }
+  }
+}
+
+// part_idx [splits][nq][2].  `gate` (device int): the kernel does nothing unless *gate == 0.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+                  const float* __restrict__ tn, int64_t nq, int64_t nt, int q_blocks, int splits, int64_t rows_per_split,
+                  int32_t* __restrict__ part_idx, const int* __restrict__ gate) {
+  if (*gate != 0) return;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;                          // [2 tiles][2 halves][16 KB]
+  uint8_t* smem_b = smem + TC_A_BYTES;             // [stages][2 halves][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);
+  uint64_t* full = bars;                           // [stages]   TMA -> MMA
+  uint64_t* empty = bars + TC_STAGES;              // [stages]   MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;      // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2; // [2]        epilogue -> MMA
+  uint64_t* a_full = bars + 2 * TC_STAGES + 4;     // query tiles landed
+  uint64_t* a_empty = bars + 2 * TC_STAGES + 5;    // all MMAs of the unit retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_units = q_blocks * splits;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_t) : "memory");
+      uint32_t it = 0, un = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
+        const int split = u / q_blocks, qb = u - split * q_blocks;
+        const int64_t t_begin = (int64_t)split * rows_per_split;
+        const int64_t t_end = min(nt, t_begin + rows_per_split);
+        const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
+        mbar_wait(a_empty, (un & 1) ^ 1);
+        mbar_expect_tx(a_full, TC_A_BYTES);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem_a + (m * 2 + h) * TC_HALF_BYTES, &map_q, a_full, h * 64, qb * TC_QB + m * 128);
+        for (int j = 0; j < tiles; ++j, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait(empty + s, ((it / TC_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full + s, TC_B_BYTES);
+          const int row0 = (int)(t_begin + (int64_t)j * TC_TN);
+          tma_load_2d(smem_b + s * TC_B_BYTES, &map_t, full + s, 0, row0);
+          tma_load_2d(smem_b + s * TC_B_BYTES + TC_HALF_BYTES, &map_t, full + s, 64, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t it = 0, un = 0;
+      const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
+        const int split = u / q_blocks;
+        const int64_t t_begin = (int64_t)split * rows_per_split;
+        const int64_t t_end = min(nt, t_begin + rows_per_split);
+        const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
+        mbar_wait(a_full, un & 1);
+        for (int j = 0; j < tiles; ++j, ++it) {
+          const int s = it % TC_STAGES, b = it & 1;
+          mbar_wait(full + s, (it / TC_STAGES) & 1);
+          mbar_wait(tmem_empty + b, ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t d_addr = tmem_base + (uint32_t)((b * 2 + m) * TC_TN);
+#pragma unroll
+            for (int k = 0; k < TC_D / 16; ++k) {
+              const uint32_t koff = (uint32_t)((k >> 2) * TC_HALF_BYTES + (k & 3) * 32);
+              tc_mma_bf16(d_addr, umma_desc_sw128(a_addr + m * 2 * TC_HALF_BYTES + koff),
+                          umma_desc_sw128(b_addr + s * TC_B_BYTES + koff), TC_IDESC, k > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(empty + s);       // the stage may be refilled once these MMAs have read it
+          tc_commit(tmem_full + b);   // accumulators ready for the epilogue
+        }
+        tc_commit(a_empty);           // the query tiles may be replaced
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: fused top-2 =====
+    const int ew = warp - 4, quarter = ew & 3, m = ew >> 2;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int split = u / q_blocks, qb = u - split * q_blocks;
+      const int64_t t_begin = (int64_t)split * rows_per_split;
+      const int64_t t_end = min(nt, t_begin + rows_per_split);
+      const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
+      TcTop2 top;
+      top.k0 = top.k1 = __int_as_float(0x7f800000);
+      top.i0 = top.i1 = -1;
+      for (int j = 0; j < tiles; ++j, ++it) {
+        const int b = it & 1;
+        const int col0 = (int)(t_begin + (int64_t)j * TC_TN);
+        const float4* tn4 = reinterpret_cast<const float4*>(tn + col0);
+        uint32_t acc0[32], acc1[32];
+        float4 tn0[8], tn1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tn0[i] = __ldg(tn4 + i);
+        mbar_wait(tmem_full + b, (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + m) * TC_TN);
+        tc_ld32(taddr, acc0);
+        tc_wait_ld();
+        // chunk 1 in flight while chunk 0 is scored, and so on
+        tc_ld32(taddr + 32, acc1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tn1[i] = __ldg(tn4 + 8 + i);
+        tc_process32(acc0, tn0, col0, top);
+        tc_wait_ld();
+        tc_ld32(taddr + 64, acc0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tn0[i] = __ldg(tn4 + 16 + i);
+        tc_process32(acc1, tn1, col0 + 32, top);
+        tc_wait_ld();
+        tc_ld32(taddr + 96, acc1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tn1[i] = __ldg(tn4 + 24 + i);
+        tc_process32(acc0, tn0, col0 + 64, top);
+        tc_wait_ld();
+        // every column of this buffer is in registers: hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + b);
+        tc_process32(acc1, tn1, col0 + 96, top);
+      }
+      const int64_t row = (int64_t)qb * TC_QB + m * 128 + quarter * 32 + lane;
+      if (row < nq) {
+        int32_t* o = part_idx + ((int64_t)split * nq + row) * 2;
+        o[0] = top.i0; o[1] = top.i1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows][128] bf16 row-major, box = 64 columns x 128 rows, 128-byte swizzle, out-of-range rows read as zero
+static int make_map(CUtensorMap* map, const void* base, int64_t rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  HPUSM_REQUIRE(fn, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)TC_D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)TC_D * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HPUSM_REQUIRE(r == CUDA_SUCCESS, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return HPUSM_OK;
+}
+
+bool l2_tc_available() { return true; }
+
+static int tc_splits(int64_t nq, int64_t nt) {
+  const int64_t qbs = (nq + TC_QB - 1) / TC_QB;
+  const int64_t sms = sm_count();
+  if (qbs >= 2 * sms) return 1;
+  int64_t s = (2 * sms + qbs - 1) / qbs;
+  const int64_t max_s = (nt + 2047) / 2048;  // at least 16 tiles per unit
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+
+struct TcLayout {
+  size_t qb, tb, tn, flag, part, total;
+  int splits_tc, splits_simt, nparts;
+  int64_t nt_pad;
+};
+
+static TcLayout tc_layout(int64_t nq, int64_t nt, int mode) {
+  TcLayout L;
+  L.nt_pad = (nt + TC_TN - 1) / TC_TN * TC_TN;
+  L.splits_tc = tc_splits(nq, nt);
+  L.splits_simt = (mode == HPUSM_L2_AUTO) ? l2_simt_splits(nq, nt) : 0;
+  L.nparts = L.splits_tc > L.splits_simt ? L.splits_tc : L.splits_simt;
+  size_t off = 0;
+  L.qb = off; off += align_up((size_t)nq * TC_D * 2, 1024);
+  L.tb = off; off += align_up((size_t)nt * TC_D * 2, 1024);
+  L.tn = off; off += align_up((size_t)L.nt_pad * sizeof(float), 1024);
+  L.flag = off; off += 1024;
+  L.part = off; off += align_up((size_t)L.nparts * nq * 2 * sizeof(int32_t), 1024);
+  L.total = off;
+  return L;
+}
+
+size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode) {
+  if (d != TC_D || nq <= 0 || nt <= 0) return 256;
+  return tc_layout(nq, nt, mode).total;
+}
+
+// Defined in l2_simt.cu: the FP32 engine, launched only when *gate != 0.
+int l2_simt_candidates_gated(const float* q, int64_t nq, const float* t, int64_t nt, int d, int splits, int32_t* part_idx,
+                             const int* gate, cudaStream_t st);
+
+int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist, void* ws,
+               size_t ws_bytes, cudaStream_t st, int* resolved_mode, int64_t* fallback_rows) {
+  HPUSM_REQUIRE(d == TC_D, HPUSM_ERR_UNSUPPORTED, "tensor-core L2 engine is built for d == %d, got %d", TC_D, d);
+  HPUSM_REQUIRE(mode != HPUSM_L2_TC_SPLIT, HPUSM_ERR_UNSUPPORTED,
+                "HPUSM_L2_TC_SPLIT is not built yet: use HPUSM_L2_AUTO (general floats take the FP32 engine)");
+  const TcLayout L = tc_layout(nq, nt, mode);
+  HPUSM_REQUIRE(ws_bytes >= L.total, HPUSM_ERR_WORKSPACE, "l2 tensor engine: workspace needs %zu bytes, got %zu", L.total,
+                ws_bytes);
+  char* base = reinterpret_cast<char*>(ws);
+  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(base + L.qb);
+  __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(base + L.tb);
+  float* tn = reinterpret_cast<float*>(base + L.tn);
+  int* flag = reinterpret_cast<int*>(base + L.flag);
+  int32_t* part = reinterpret_cast<int32_t*>(base + L.part);
+
+  HPUSM_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  HPUSM_CUDA_OK(cudaMemsetAsync(part, 0xff, (size_t)L.nparts * nq * 2 * sizeof(int32_t), st));
+  HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((nq + 7) / 8), 256, 0, st, q, nq, nq, qb, (float*)nullptr, flag);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((L.nt_pad + 7) / 8), 256, 0, st, t, nt, L.nt_pad, tb, tn, flag);
+  HPUSM_CHECK_LAUNCH();
+
+  CUtensorMap map_q, map_t;
+  int rc = make_map(&map_q, qb, nq);
+  if (rc != HPUSM_OK) return rc;
+  rc = make_map(&map_t, tb, nt);
+  if (rc != HPUSM_OK) return rc;
+
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  HPUSM_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_done[dev] = true;
+  }
+  const int q_blocks = (int)((nq + TC_QB - 1) / TC_QB);
+  int64_t rows_per_split = (nt + L.splits_tc - 1) / L.splits_tc;
+  rows_per_split = (rows_per_split + TC_TN - 1) / TC_TN * TC_TN;
+  const int units = q_blocks * L.splits_tc;
+  const int grid = units < sm_count() ? units : sm_count();
+  HPUSM_LAUNCH_TIMED(l2_tc_knn2_kernel, grid, TC_THREADS, TC_SMEM_BYTES, st, map_q, map_t, tn, nq, nt, q_blocks, L.splits_tc,
+                     rows_per_split, part, flag);
+  HPUSM_CHECK_LAUNCH();
+  if (mode == HPUSM_L2_AUTO) {
+    rc = l2_simt_candidates_gated(q, nq, t, nt, d, L.splits_simt, part, flag, st);
+    if (rc != HPUSM_OK) return rc;
+  }
+  *resolved_mode = HPUSM_L2_TC_INT;
+  *fallback_rows = 0;
+  return l2_rerank_finalize(q, nq, t, d, part, L.nparts, 2, nullptr, 0, idx, dist, st);
+}
+
 }  // namespace hpusm

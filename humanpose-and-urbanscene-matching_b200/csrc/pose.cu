@@ -237,7 +237,9 @@ __device__ __forceinline__ Scale make_scale(GetX gx, GetY gy, unsigned undetecte
     if (y != 0.0) { ymin = fmin(ymin, lo); anyy = true; }
   }
   Scale s;
-  s.valid = anyx && anyy;  // the reference raises ValueError (np.min of an empty array) otherwise
+  // The reference raises here instead of returning: ValueError (np.min of an empty array) when no joint is
+  // detected, LinAlgError (NaN/inf into LAPACK) when xmax == xmin or ymax == ymin.  Such poses never match.
+  s.valid = anyx && anyy && xmax != xmin && ymax != ymin;
   s.xmin = xmin; s.ymin = ymin;
   s.ix = 1.0 / (xmax - xmin); s.iy = 1.0 / (ymax - ymin);
   return s;

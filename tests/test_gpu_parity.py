@@ -135,6 +135,20 @@ def test_l2_scene_pair_sift(hpusm, cuda_device, mode):
     np.testing.assert_array_equal(p_t[:161].cpu().numpy(), g["p_input"].reshape(-1, 2))
 
 
+def test_l2_tensor_engine_units_and_splits(hpusm, cuda_device):
+    """Explicit tcgen05 engine (HPUSM_L2_TC_INT): several 256-query units per CTA wave, database splits, ragged
+    tails on both sides, duplicate database rows (ties -> lower index)."""
+    for nq, nt, seed in [(5000, 70001, 1), (257, 1085, 2), (40000, 4323, 3), (1, 129, 4)]:
+        q, t = hpusm.synth.sift_like(nq, nt, seed=seed, planted=0.3)
+        t[nt // 2] = t[3]
+        t[nt - 1] = t[0]
+        idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_TC_INT)
+        assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_INT
+        ri, rd = knn_oracle.knn2_l2(q, t)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+        np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+
+
 @pytest.mark.parametrize("mode", L2_MODES)
 @pytest.mark.parametrize("nq,nt,d,kind", [(1, 2, 128, "int"), (65, 63, 128, "int"), (300, 20000, 128, "int"),
                                           (2000, 3000, 128, "float"), (129, 4097, 64, "float"), (50, 700, 36, "float"),
