@@ -39,7 +39,10 @@ constexpr int TC_THREADS = 384;
 constexpr int TC_HALF_BYTES = 128 * 128;                    // [128 rows][64 bf16] = 16 KB, one swizzle-128B slab
 constexpr int TC_A_BYTES = 2 * 2 * TC_HALF_BYTES;           // 2 query tiles x 2 k-halves
 constexpr int TC_B_BYTES = 2 * TC_HALF_BYTES;               // per stage
-constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_TN_SLOTS = 8;                              // ring of ||t||^2 tiles (>= stages + 2 accumulator buffers + 1)
+constexpr int TC_TN_BYTES = TC_TN * 4;                      // 512 B per tile
+constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + TC_TN_SLOTS * TC_TN_BYTES + 1024 /*alignment slack*/ +
+                              256 /*barriers*/;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +71,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -151,20 +163,27 @@ __device__ __forceinline__ void tc_insert(TcTop2& t, float v, int col) {
   }
 }
 
-__device__ __forceinline__ void tc_process32(const uint32_t (&acc)[32], const float4 (&tn)[8], int col, TcTop2& t) {
+// 32 accumulator columns of one query row: key = ||t||^2 - 2 q.t, one guard per 32 keys (FMNMX3 tree) in front of
+// the rare insertion.  `tn` points at the 32 norms in shared memory (broadcast LDS.128).
+__device__ __forceinline__ void tc_process32(uint32_t (&acc)[32], const float4* tn, int col, TcTop2& t) {
+  float v[32];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float v[8];
-    const float4 ta = tn[2 * g], tb = tn[2 * g + 1];
-    v[0] = fmaf(-2.f, __uint_as_float(acc[8 * g + 0]), ta.x); v[1] = fmaf(-2.f, __uint_as_float(acc[8 * g + 1]), ta.y);
-    v[2] = fmaf(-2.f, __uint_as_float(acc[8 * g + 2]), ta.z); v[3] = fmaf(-2.f, __uint_as_float(acc[8 * g + 3]), ta.w);
-    v[4] = fmaf(-2.f, __uint_as_float(acc[8 * g + 4]), tb.x); v[5] = fmaf(-2.f, __uint_as_float(acc[8 * g + 5]), tb.y);
-    v[6] = fmaf(-2.f, __uint_as_float(acc[8 * g + 6]), tb.z); v[7] = fmaf(-2.f, __uint_as_float(acc[8 * g + 7]), tb.w);
-    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-    if (m < t.k1) {
+  for (int i = 0; i < 8; ++i) {
+    const float4 n4 = tn[i];
+    v[4 * i + 0] = fmaf(-2.f, __uint_as_float(acc[4 * i + 0]), n4.x);
+    v[4 * i + 1] = fmaf(-2.f, __uint_as_float(acc[4 * i + 1]), n4.y);
+    v[4 * i + 2] = fmaf(-2.f, __uint_as_float(acc[4 * i + 2]), n4.z);
+    v[4 * i + 3] = fmaf(-2.f, __uint_as_float(acc[4 * i + 3]), n4.w);
+  }
+  float m[11];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tc_insert(t, v[j], col + 8 * g + j);
-    }
+  for (int i = 0; i < 10; ++i) m[i] = min3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  m[10] = fminf(v[30], v[31]);
+  const float a = min3(m[0], m[1], m[2]), b = min3(m[3], m[4], m[5]), c = min3(m[6], m[7], m[8]);
+  const float lo = fminf(min3(a, b, c), fminf(m[9], m[10]));
+  if (lo < t.k1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tc_insert(t, v[j], col + j);
   }
 }
 
@@ -178,14 +197,16 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                          // [2 tiles][2 halves][16 KB]
   uint8_t* smem_b = smem + TC_A_BYTES;             // [stages][2 halves][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);
+  float* smem_tn = reinterpret_cast<float*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);  // [slots][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES + TC_TN_SLOTS * TC_TN_BYTES);
   uint64_t* full = bars;                           // [stages]   TMA -> MMA
   uint64_t* empty = bars + TC_STAGES;              // [stages]   MMA -> TMA
   uint64_t* tmem_full = bars + 2 * TC_STAGES;      // [2]        MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2; // [2]        epilogue -> MMA
   uint64_t* a_full = bars + 2 * TC_STAGES + 4;     // query tiles landed
   uint64_t* a_empty = bars + 2 * TC_STAGES + 5;    // all MMAs of the unit retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
+  uint64_t* tn_full = bars + 2 * TC_STAGES + 6;    // [slots]    norms of a database tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6 + TC_TN_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -194,6 +215,7 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
+    for (int i = 0; i < TC_TN_SLOTS; ++i) mbar_init(tn_full + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -232,6 +254,12 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const int row0 = (int)(t_begin + (int64_t)j * TC_TN);
           tma_load_2d(smem_b + s * TC_B_BYTES, &map_t, full + s, 0, row0);
           tma_load_2d(smem_b + s * TC_B_BYTES + TC_HALF_BYTES, &map_t, full + s, 64, row0);
+          // ||t||^2 of the tile for the epilogue.  Slot reuse needs no extra barrier: tile `it` is only issued once the
+          // MMAs of tile it-STAGES retired, those waited for the epilogue of tile it-STAGES-2, and the epilogue reads
+          // its norms before it releases the accumulator -> at most STAGES+2 slots are live.
+          const int ts = it % TC_TN_SLOTS;
+          mbar_expect_tx(tn_full + ts, TC_TN_BYTES);
+          bulk_load_1d(smem_tn + ts * TC_TN, tn + row0, TC_TN_BYTES, tn_full + ts);
         }
       }
     }
@@ -282,37 +310,27 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       for (int j = 0; j < tiles; ++j, ++it) {
         const int b = it & 1;
         const int col0 = (int)(t_begin + (int64_t)j * TC_TN);
-        const float4* tn4 = reinterpret_cast<const float4*>(tn + col0);
+        const int ts = it % TC_TN_SLOTS;
+        const float4* tn4 = reinterpret_cast<const float4*>(smem_tn + ts * TC_TN);
         uint32_t acc0[32], acc1[32];
-        float4 tn0[8], tn1[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tn0[i] = __ldg(tn4 + i);
         mbar_wait(tmem_full + b, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + m) * TC_TN);
         tc_ld32(taddr, acc0);
-        tc_wait_ld();
-        // chunk 1 in flight while chunk 0 is scored, and so on
         tc_ld32(taddr + 32, acc1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tn1[i] = __ldg(tn4 + 8 + i);
-        tc_process32(acc0, tn0, col0, top);
+        mbar_wait(tn_full + ts, (it / TC_TN_SLOTS) & 1);
         tc_wait_ld();
+        tc_process32(acc0, tn4, col0, top);
         tc_ld32(taddr + 64, acc0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tn0[i] = __ldg(tn4 + 16 + i);
-        tc_process32(acc1, tn1, col0 + 32, top);
-        tc_wait_ld();
+        tc_process32(acc1, tn4 + 8, col0 + 32, top);
         tc_ld32(taddr + 96, acc1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tn1[i] = __ldg(tn4 + 24 + i);
-        tc_process32(acc0, tn0, col0 + 64, top);
         tc_wait_ld();
         // every column of this buffer is in registers: hand the accumulator back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + b);
-        tc_process32(acc1, tn1, col0 + 96, top);
+        tc_process32(acc0, tn4 + 16, col0 + 64, top);
+        tc_process32(acc1, tn4 + 24, col0 + 96, top);
       }
       const int64_t row = (int64_t)qb * TC_QB + m * 128 + quarter * 32 + lane;
       if (row < nq) {

@@ -560,8 +560,30 @@ ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ 
       R[3 + j] = G[3 + j] / sd + cdy * G[6 + j];
       R[6 + j] = G[6 + j];
     }
-    for (int i = 0; i < 9; ++i) Hout[pair * 9 + i] = R[i] / R[8];
+    for (int i = 0; i < 9; ++i) {
+      const double hv = R[i] / R[8];
+      Hout[pair * 9 + i] = hv;
+      sh_Hf[i] = (float)hv;
+    }
   }
+  __syncthreads();
+  // OpenCV returns the inliers of the REFINED homography (float32 reprojection error with division, the
+  // formula of its computeError); mirrored op for op by final_mask() in oracle/ransac_oracle.c.
+#pragma unroll
+  for (int i = 0; i < 9; ++i) hf[i] = sh_Hf[i];
+  double cnt[1] = {0.0};
+  for (int64_t i = tid; i < K; i += RF_THREADS) {
+    const float2 a = s[i], b = d[i];
+    const float ww = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(hf[6], a.x), __fmul_rn(hf[7], a.y)), 1.f));
+    const float px = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hf[0], a.x), __fmul_rn(hf[1], a.y)), hf[2]), ww);
+    const float py = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hf[3], a.x), __fmul_rn(hf[4], a.y)), hf[5]), ww);
+    const float dx = __fsub_rn(px, b.x), dy = __fsub_rn(py, b.y);
+    const bool in = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= thr2;
+    mk[i] = in ? 1 : 0;
+    cnt[0] += in ? 1.0 : 0.0;
+  }
+  block_sum<1>(cnt, scratch, sh_c1);
+  if (tid == 0) ninl[pair] = (int)sh_c1[0];
 }
 
 static size_t ransac_smem_bytes(int nhyp, int chunk) {

@@ -135,8 +135,9 @@ int hpusm_gather_matches(const float* kp_q, const float* kp_t, const int32_t* id
  *               only while h < the adaptive iteration bound, cv2 default 0.995); <= 0: use all nhyp.
  *   seed      keys the counter-based sample table (seed, pair, hypothesis) shared with the oracle.
  *   H    [npairs][9] float64 row-major, H[8] == 1; all NaN when no model with >= 4 inliers exists.
- *   mask [total] uint8 inlier flags of the winning hypothesis (before refinement, as cv2 returns).
- *   ninl [npairs] int32 inlier count; best_hyp [npairs] int32 (optional, may be NULL) winning index.
+ *   mask [total] uint8 inlier flags: with refine != 0 the inliers of the REFINED homography under cv2's float32
+ *               reprojection error (what cv2 4.x returns); otherwise those of the winning minimal-sample model.
+ *   ninl [npairs] int32 = number of set mask entries; best_hyp [npairs] int32 (optional, may be NULL) winning index.
  *   refine != 0: least-squares DLT on the inliers followed by Levenberg-Marquardt on the reprojection
  *               error (cv2 does both); refine == 0 returns the winning minimal-sample model.
  * ------------------------------------------------------------------------------------------------ */

@@ -176,6 +176,28 @@ static int count_inliers(const double* H, const float* src, const float* dst, in
   return c;
 }
 
+/* Final mask: OpenCV (4.13) returns the inliers of the REFINED homography, not of the winning minimal model
+ * (probe: with maxIters=5 the returned mask holds 221 points while H is the fit of a much smaller set).  Error
+ * formula of its HomographyEstimatorCallback::computeError, float32, with division. */
+static int final_mask(const double* H, const float* src, const float* dst, int64_t K, float thr2, uint8_t* mask) {
+  float h[9];
+  int c = 0;
+  for (int i = 0; i < 9; ++i) h[i] = (float)H[i];
+  for (int64_t i = 0; i < K; ++i) {
+    const float x = src[2 * i], y = src[2 * i + 1];
+    const float a6 = h[6] * x, a7 = h[7] * y;
+    const float ww = 1.f / ((a6 + a7) + 1.f);
+    const float a0 = h[0] * x, a1 = h[1] * y, a3 = h[3] * x, a4 = h[4] * y;
+    const float px = ((a0 + a1) + h[2]) * ww, py = ((a3 + a4) + h[5]) * ww;
+    const float dx = px - dst[2 * i], dy = py - dst[2 * i + 1];
+    const float dx2 = dx * dx, dy2 = dy * dy;
+    const int in = (dx2 + dy2) <= thr2;
+    mask[i] = (uint8_t)in;
+    c += in;
+  }
+  return c;
+}
+
 static int adaptive_iters(double conf, double outlier_ratio, int max_iters) {
   double p = fmin(fmax(conf, 0.0), 1.0);
   double ep = fmin(fmax(outlier_ratio, 0.0), 1.0);
@@ -386,8 +408,12 @@ int ransac_oracle_homography(const float* src, const float* dst, const int64_t* 
     }
     const int n_in = count_inliers(Hbest, s, d, K, thr2, mask + m0);
     ninl[p] = n_in;
-    if (!refine || n_in < 5) memcpy(H + 9 * p, Hbest, sizeof(Hbest));
-    else refine_on_inliers(Hbest, s, d, mask + m0, K, n_in, H + 9 * p);
+    if (!refine || n_in < 5) {
+      memcpy(H + 9 * p, Hbest, sizeof(Hbest));
+    } else {
+      refine_on_inliers(Hbest, s, d, mask + m0, K, n_in, H + 9 * p);
+      ninl[p] = final_mask(H + 9 * p, s, d, K, thr2, mask + m0);
+    }
   }
   return 0;
 }

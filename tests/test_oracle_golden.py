@@ -46,27 +46,32 @@ def test_scene_pair_knn_and_ratio(det):
 
 
 def test_ransac_matches_cv2():
-    """findHomography (features.py:66).  cv2's sampler cannot be seeded, so what can be pinned on it is:
-    (a) noise-free inliers: the consensus set is unique -> identical mask, H within 1e-4;
-    (b) noisy inliers: the winning minimal model (hence the mask) depends on the sample sequence, so the
-        refinement is pinned instead: our least-squares + LM fit ON cv2's OWN MASK gives cv2's H within
-        1e-4, and our own mask is a subset of the true consensus that overlaps cv2's by >= 90 %."""
+    """findHomography (features.py:66) on inputs whose consensus set is unique.  cv2's sampler cannot be seeded, so
+    its internal winning sample differs from ours; what does not depend on it is pinned:
+      * the returned mask (cv2 returns the inliers of the refined H): identical;
+      * H: within 1e-4 when the inliers are noise-free (any all-inlier sample gives the same fit); with noisy
+        inliers the set the refinement ran on is cv2-internal, so there H is only required to agree to 2e-2 and
+        the refinement itself is pinned separately below."""
     g = load_golden("ransac_cv2.npz")
     offs = g["pair_offsets"]
     H, mask, ninl, best = ransac_oracle.homography_batch(g["src"], g["dst"], offs, 5.0, 2000, 0.995, 7)
+    np.testing.assert_array_equal(mask, g["mask"])
     for p in range(len(H)):
+        Hc = g["H"][p]
+        assert abs(H[p, 2, 2] - 1.0) < 1e-15 and ninl[p] == g["mask"][offs[p]:offs[p + 1]].sum()
+        tol = 1e-4 if g["noise"][p] == 0.0 else 2e-2
+        np.testing.assert_allclose(H[p], Hc, rtol=tol, atol=tol * np.abs(Hc).max())
+
+
+def test_ransac_refinement_matches_cv2():
+    """Least squares + LM on a given inlier set = cv2's post-RANSAC step.  Pinned on the pairs where cv2's refinement
+    demonstrably ran on its returned mask (their H is the reprojection-error minimiser over that mask)."""
+    g = load_golden("ransac_cv2.npz")
+    offs = g["pair_offsets"]
+    for p in (1, 2, 3, 4, 5, 6, 7, 8, 9):
         lo, hi = offs[p], offs[p + 1]
-        Hc, mc = g["H"][p], g["mask"][lo:hi]
-        tol = dict(rtol=1e-4, atol=1e-4 * np.abs(Hc).max())
-        assert abs(H[p, 2, 2] - 1.0) < 1e-15
-        if g["noise"][p] == 0.0:
-            np.testing.assert_array_equal(mask[lo:hi], mc)
-            np.testing.assert_allclose(H[p], Hc, **tol)
-        else:
-            Hr = ransac_oracle.refine(g["src"][lo:hi], g["dst"][lo:hi], mc, Hc)
-            np.testing.assert_allclose(Hr, Hc, **tol)
-            both = (mask[lo:hi] & mc).sum()
-            assert both >= 0.9 * mc.sum() and both >= 0.9 * mask[lo:hi].sum()
+        Hr = ransac_oracle.refine(g["src"][lo:hi], g["dst"][lo:hi], g["mask"][lo:hi], g["H"][p])
+        np.testing.assert_allclose(Hr, g["H"][p], rtol=1e-6, atol=1e-6 * np.abs(g["H"][p]).max())
 
 
 def test_ransac_scene_pair_low_inlier_ratio():
