@@ -320,10 +320,32 @@ __device__ __forceinline__ double rotation_value(const PartResult& r) {
   return (r1 > r2) ? r1 : r2;  // Python max(rotation_2, rotation_1): the first argument wins unless the second is greater
 }
 
+// common.feature_scaling on n independent point sets (FP64, arbitrary point count), one thread each.
+__global__ void feature_scaling_batch_kernel(const double* __restrict__ pts, int64_t n, int npts, double* __restrict__ out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const double* P = pts + b * npts * 2;
+  double* O = out + b * npts * 2;
+  double xmax = -DBL_MAX, ymax = -DBL_MAX, xmin = DBL_MAX, ymin = DBL_MAX;
+  for (int j = 0; j < npts; ++j) {
+    const double x = P[2 * j], y = P[2 * j + 1];
+    xmax = fmax(xmax, x); ymax = fmax(ymax, y);
+    const double lo = fmin(x, y);
+    if (x != 0.0) xmin = fmin(xmin, lo);
+    if (y != 0.0) ymin = fmin(ymin, lo);
+  }
+  for (int j = 0; j < npts; ++j) {
+    const double sx = (P[2 * j] - xmin) / (xmax - xmin), sy = (P[2 * j + 1] - ymin) / (ymax - ymin);
+    O[2 * j] = sx < 0.0 ? 0.0 : sx;
+    O[2 * j + 1] = sy < 0.0 ? 0.0 : sy;
+  }
+}
+
 constexpr int PM_THREADS = 128;
 
+template <typename T>
 __global__ void __launch_bounds__(PM_THREADS)
-pose_match_batch_kernel(const float* __restrict__ query, const float* __restrict__ db, int64_t n, int query_is_model,
+pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, int64_t n, int query_is_model,
                         PoseParams prm, uint8_t* __restrict__ match, float* __restrict__ score,
                         double* __restrict__ detail) {
   __shared__ double sq[NJ * 2];
@@ -339,20 +361,27 @@ pose_match_batch_kernel(const float* __restrict__ query, const float* __restrict
   const int64_t p = (int64_t)blockIdx.x * PM_THREADS + threadIdx.x;
   if (p >= n) return;
 
-  float pr[NJ * 2];
-  {
+  T pr[NJ * 2];
+  if constexpr (sizeof(T) == 4) {
     const float4* src = reinterpret_cast<const float4*>(db + p * (NJ * 2));
 #pragma unroll
     for (int v = 0; v < NJ * 2 / 4; ++v) {
       const float4 x = __ldg(src + v);
       pr[4 * v] = x.x; pr[4 * v + 1] = x.y; pr[4 * v + 2] = x.z; pr[4 * v + 3] = x.w;
     }
+  } else {
+    const double2* src = reinterpret_cast<const double2*>(db + p * (NJ * 2));
+#pragma unroll
+    for (int v = 0; v < NJ; ++v) {
+      const double2 x = __ldg(src + v);
+      pr[2 * v] = x.x; pr[2 * v + 1] = x.y;
+    }
   }
   // common.handle_undetected_points: a joint missing on either side is (0,0) on both
   unsigned und = sq_undetected;
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
-    if (pr[2 * j] == 0.f && pr[2 * j + 1] == 0.f) und |= 1u << j;
+    if (pr[2 * j] == T(0) && pr[2 * j + 1] == T(0)) und |= 1u << j;
 
   auto qx = [&](int j) { return sq[2 * j]; };
   auto qy = [&](int j) { return sq[2 * j + 1]; };
@@ -530,14 +559,7 @@ int hpusm_procrustes_batch(const double* X, const double* Y, int64_t n, int npts
   return HPUSM_OK;
 }
 
-int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int query_is_model,
-                           const double* thresholds, uint8_t* match, float* score, double* detail, void* stream) {
-  HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_pose_match_batch: negative size");
-  if (n == 0) return HPUSM_OK;
-  HPUSM_REQUIRE(query && db && thresholds && match && score, HPUSM_ERR_INVALID,
-                "hpusm_pose_match_batch: null pointer");
-  HPUSM_REQUIRE(is_aligned(db, 16), HPUSM_ERR_INVALID, "hpusm_pose_match_batch: db must be 16-byte aligned");
-  PoseParams prm;
+static void pose_params(const double* thresholds, PoseParams& prm) {
   prm.d_torso = thresholds[0]; prm.rot_torso = thresholds[1];
   prm.d_legs = thresholds[2]; prm.rot_legs = thresholds[3]; prm.d_shoulder = thresholds[4];
   // rot*57.3 <= thr  <=>  angle <= thr/57.3; usable as a tangent bound while that stays below ~86 degrees
@@ -546,8 +568,43 @@ int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int q
   prm.legs_use_tan = (a_l >= 0.0 && a_l < 1.5) ? 1 : 0;
   prm.tan_torso = prm.torso_use_tan ? tan(a_t) : 0.0;
   prm.tan_legs = prm.legs_use_tan ? tan(a_l) : 0.0;
-  HPUSM_LAUNCH_TIMED(pose_match_batch_kernel, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
-               as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+}
+
+int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int query_is_model,
+                           const double* thresholds, uint8_t* match, float* score, double* detail, void* stream) {
+  HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_pose_match_batch: negative size");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(query && db && thresholds && match && score, HPUSM_ERR_INVALID,
+                "hpusm_pose_match_batch: null pointer");
+  HPUSM_REQUIRE(is_aligned(db, 16), HPUSM_ERR_INVALID, "hpusm_pose_match_batch: db must be 16-byte aligned");
+  PoseParams prm;
+  pose_params(thresholds, prm);
+  HPUSM_LAUNCH_TIMED(pose_match_batch_kernel<float>, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
+                     as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n, int query_is_model,
+                               const double* thresholds, uint8_t* match, float* score, double* detail, void* stream) {
+  HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_pose_match_batch_f64: negative size");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(query && db && thresholds && match && score, HPUSM_ERR_INVALID,
+                "hpusm_pose_match_batch_f64: null pointer");
+  HPUSM_REQUIRE(is_aligned(db, 16), HPUSM_ERR_INVALID, "hpusm_pose_match_batch_f64: db must be 16-byte aligned");
+  PoseParams prm;
+  pose_params(thresholds, prm);
+  HPUSM_LAUNCH_TIMED(pose_match_batch_kernel<double>, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
+                     as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_feature_scaling_batch(const double* pts, int64_t n, int npts, double* out, void* stream) {
+  HPUSM_REQUIRE(n >= 0 && npts > 0, HPUSM_ERR_INVALID, "hpusm_feature_scaling_batch: bad sizes");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(pts && out, HPUSM_ERR_INVALID, "hpusm_feature_scaling_batch: null pointer");
+  HPUSM_LAUNCH(feature_scaling_batch_kernel, (unsigned)((n + 127) / 128), 128, 0, as_stream(stream), pts, n, npts, out);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

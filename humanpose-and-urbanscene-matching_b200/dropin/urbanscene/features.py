@@ -1,0 +1,155 @@
+"""urbanscene/features.py of the reference with the same signatures; kNN, ratio filter, RANSAC homography, inlier
+gather and the corner projection run on the GPU (features.py:42,:45-55,:57-105,:177-234)."""
+import logging
+
+import numpy as np
+import torch
+
+from .. import thresholds
+from .._dev import engine, up, down
+
+NORM_L2, NORM_HAMMING = 4, 6  # cv2's constants, so callers can keep passing them
+
+
+class DMatch(object):
+    """The fields of cv2.DMatch the reference reads (features.py:48-51)."""
+    __slots__ = ("queryIdx", "trainIdx", "imgIdx", "distance")
+
+    def __init__(self, queryIdx, trainIdx, distance):
+        self.queryIdx, self.trainIdx, self.imgIdx, self.distance = int(queryIdx), int(trainIdx), 0, float(distance)
+
+
+class BFMatcher(object):
+    """Duck-type of cv2.BFMatcher(norm) (crossCheck off) as features.match_and_draw uses it."""
+
+    def __init__(self, normType=NORM_L2, seed=0):
+        self.normType = normType
+        self.last = None  # device tensors of the last knnMatch: (idx, dist) -- lets filter_matches stay on the GPU
+
+    def knn2(self, queryDescriptors, trainDescriptors):
+        if self.normType == NORM_HAMMING:
+            idx, dist = engine.knn2_hamming(up(queryDescriptors, np.uint8), up(trainDescriptors, np.uint8))
+        else:
+            idx, dist = engine.knn2_l2(up(queryDescriptors, np.float32), up(trainDescriptors, np.float32))
+        self.last = (idx, dist)
+        return idx, dist
+
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2):
+        if queryDescriptors is None or trainDescriptors is None:
+            raise ValueError("knnMatch: descriptors are None (image without keypoints)")  # cv2 raises cv2.error here
+        if k != 2:
+            raise ValueError("this matcher implements the reference's call, knnMatch(..., k=2)")
+        idx, dist = self.knn2(queryDescriptors, trainDescriptors)
+        idx, dist = down(idx), down(dist).astype(np.float32)
+        out = []
+        for i in range(idx.shape[0]):
+            out.append([DMatch(i, idx[i, j], dist[i, j]) for j in range(2) if idx[i, j] >= 0])
+        return out
+
+
+def init_feature(name):
+    """(detector, matcher) as features.py:10-43.  Detection stays with OpenCV (out of the path's scope); the
+    brute-force matcher is ours.  FLANN variants are not part of the replaced path."""
+    import cv2
+    chunks = name.split('-')
+    if chunks[0] == 'sift':
+        detector = cv2.SIFT_create() if hasattr(cv2, "SIFT_create") else cv2.xfeatures2d.SIFT_create()
+        norm = NORM_L2
+    elif chunks[0] == 'surf':
+        detector = cv2.xfeatures2d.SURF_create(800)
+        norm = NORM_L2
+    elif chunks[0] == 'orb':
+        detector = cv2.ORB_create(nfeatures=100000, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                                  scoreType=cv2.ORB_FAST_SCORE, patchSize=31)
+        norm = NORM_HAMMING
+    elif chunks[0] == 'akaze':
+        detector = cv2.AKAZE_create()
+        norm = NORM_HAMMING
+    elif chunks[0] == 'brisk':
+        detector = cv2.BRISK_create()
+        norm = NORM_HAMMING
+    else:
+        return None, None
+    if 'flann' in chunks:
+        raise NotImplementedError("FLANN matchers are outside the replaced path; use the brute-force names")
+    return detector, BFMatcher(norm)
+
+
+def _pt(kp):
+    return kp.pt if hasattr(kp, "pt") else (float(kp[0]), float(kp[1]))
+
+
+def filter_matches(kp1, kp2, matches, ratio=thresholds.FILTER_RATIO):
+    mkp1, mkp2 = [], []
+    for m in matches:
+        if len(m) == 2 and m[0].distance < m[1].distance * ratio:
+            m = m[0]
+            mkp1.append(kp1[m.queryIdx])
+            mkp2.append(kp2[m.trainIdx])
+    p1 = np.float32([_pt(kp) for kp in mkp1]).reshape(-1, 1, 2)
+    p2 = np.float32([_pt(kp) for kp in mkp2]).reshape(-1, 1, 2)
+    return p1, p2, list(zip(mkp1, mkp2))
+
+
+def find_homography_ransac(src, dst, thresh=5.0, maxIters=2000, confidence=0.995, seed=0):
+    """cv2.findHomography(src, dst, cv2.RANSAC, thresh) -> (H float64 (3,3) or None, mask uint8 (K,1))."""
+    src = np.float32(src).reshape(-1, 2)
+    dst = np.float32(dst).reshape(-1, 2)
+    offs = torch.tensor([0, len(src)], dtype=torch.int64, device=up(src, np.float32).device)
+    H, mask, ninl, best = engine.ransac_homography_batch(up(src, np.float32), up(dst, np.float32), offs, thresh, maxIters,
+                                                         confidence, seed)
+    if int(down(best)[0]) < 0:
+        return None, None
+    return down(H)[0], down(mask).reshape(-1, 1)
+
+
+def match_and_draw(win, matcher, desc_model, desc_input, kp_model, kp_input, model_img, input_img, show_win):
+    raw_matches = matcher.knnMatch(desc_model, trainDescriptors=desc_input, k=2)
+    p_model, p_input, kp_pairs = filter_matches(kp_model, kp_input, raw_matches)
+    if len(p_model) >= thresholds.MIN_MATCH_COUNT:
+        H, mask = find_homography_ransac(p_model, p_input, 5.0)
+        H2, mask2 = find_homography_ransac(p_input, p_model, 5.0)
+        if H is None or H2 is None:
+            return (None, None, None, None, None, None)
+        logging.debug('%d / %d  inliers/matched' % (np.sum(mask), len(mask)))
+        h, w = model_img.shape
+        homography_pts = np.float32([[0, 0], [0, h - 1], [w - 1, h - 1], [w - 1, 0]]).reshape(-1, 1, 2)
+        homography_dst = down(engine.perspective_transform(up(homography_pts, np.float32), up(H, np.float64)))
+        try:  # the reference draws the projected model outline INTO input_img (callers rely on that side effect)
+            import cv2
+            cv2.polylines(input_img, [np.int32(homography_dst)], True, 255, 3, cv2.LINE_AA)
+        except ImportError:
+            pass
+        my_mask = np.asarray(mask).astype(bool)
+        good_model_pts = np.squeeze(p_model[np.array(my_mask)][:])
+        good_input_pts = np.squeeze(p_input[np.array(my_mask)][:])
+    else:
+        H, mask = None, None
+        logging.debug('%d matches found, not enough for homography estimation' % len(p_model))
+        return (mask, None, None, H, None, None)
+    return (mask, good_model_pts, good_input_pts, H, H2, len(good_model_pts))
+
+
+def validate_homography(perspective_trans_matrix):
+    H = perspective_trans_matrix
+    if H[0, 0] * H[1, 1] - H[0, 1] * H[1, 0] < 0:
+        return False
+    N1 = (H[0, 0] * H[0, 0] + H[0, 1] * H[0, 1]) ** 0.5
+    if N1 > 4 or N1 < 0.1:
+        return False
+    N2 = (H[1, 0] * H[1, 0] + H[1, 1] * H[1, 1]) ** 0.5
+    if N2 > 4 or N2 < 0.1:
+        return False
+    N3 = (H[2, 0] * H[2, 0] + H[2, 1] * H[2, 1]) ** 0.5
+    if N3 > 0.002:
+        return False
+    return True
+
+
+def euclidean_distance(model, transformed_input):
+    d = np.abs(model - transformed_input)
+    return ((d[:, 0]) ** 2 + d[:, 1] ** 2) ** 0.5
+
+
+def max_euclidean_distance(model, transformed_input):
+    return max(euclidean_distance(model, transformed_input))

@@ -269,8 +269,9 @@ def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THR
     """single_person.match_single of one query against a pose database (single_person.py:80-189).
 
     Returns (match [n] u8, score [n] f32[, detail [n, POSE_DETAIL] f64])."""
-    query = _cuda(query, torch.float32, "query")
-    db = _cuda(db, torch.float32, "db")
+    f64 = db.dtype == torch.float64
+    query = _cuda(query, torch.float64 if f64 else torch.float32, "query")
+    db = _cuda(db, torch.float64 if f64 else torch.float32, "db")
     if query.numel() != 36 or db.dim() != 3 or db.shape[1:] != (18, 2):
         raise ValueError("query must be [18,2] and db [n,18,2]")
     n = db.shape[0]
@@ -283,10 +284,20 @@ def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THR
         else:
             match, score = out
         detail = torch.empty((n, POSE_DETAIL), dtype=torch.float64, device=dev) if want_detail else None
-        check(lib.hpusm_pose_match_batch(_ptr(query), _ptr(db), n, 1 if query_is_model else 0,
-                                         ctypes.cast(thr, ctypes.c_void_p), _ptr(match), _ptr(score), _ptr(detail),
-                                         _stream(dev)))
+        fn = lib.hpusm_pose_match_batch_f64 if f64 else lib.hpusm_pose_match_batch
+        check(fn(_ptr(query), _ptr(db), n, 1 if query_is_model else 0,
+                 ctypes.cast(thr, ctypes.c_void_p), _ptr(match), _ptr(score), _ptr(detail), _stream(dev)))
     return (match, score, detail) if want_detail else (match, score)
+
+
+def feature_scaling_batch(pts):
+    """common.feature_scaling on [n, npts, 2] float64 point sets (common.py:688-708)."""
+    pts = _cuda(pts, torch.float64, "pts")
+    n, npts, _ = pts.shape
+    with torch.cuda.device(pts.device):
+        out = torch.empty_like(pts)
+        check(lib.hpusm_feature_scaling_batch(_ptr(pts), n, npts, _ptr(out), _stream(pts.device)))
+    return out
 
 
 def pose_topk(match, score, k=16, index_offset=0):

@@ -197,6 +197,16 @@ int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int q
                            const double* thresholds, uint8_t* match, float* score, double* detail,
                            void* stream);
 
+/* Same with float64 poses (the reference's own dtype); used by the drop-in single_person.match_single. */
+int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n, int query_is_model,
+                               const double* thresholds, uint8_t* match, float* score, double* detail,
+                               void* stream);
+
+/* Batched min/max normalisation, replaces common.feature_scaling (common.py:688-708) including its quirk that
+ * each minimum runs over BOTH coordinates of the rows whose x (resp. y) is non-zero; negatives clamp to 0.
+ *   pts, out [n][npts][2] float64. */
+int hpusm_feature_scaling_batch(const double* pts, int64_t n, int npts, double* out, void* stream);
+
 /* Per-rank top-k smallest scores among matching poses (retrieval answer that is all-gathered over
  * NCCL): writes k (score, index+index_offset) pairs, score = +inf padding. ws from
  * hpusm_pose_topk_workspace_bytes(n, k). */

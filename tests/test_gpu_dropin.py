@@ -1,0 +1,137 @@
+"""The drop-in modules (reference names and signatures) against the golden vectors recorded from the reference."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import ransac_oracle
+
+pytestmark = pytest.mark.gpu
+DROPIN = "humanpose-and-urbanscene-matching_b200.dropin"
+
+
+@pytest.fixture(scope="module")
+def mods(cuda_device):
+    names = ["common", "thresholds", "urbanscene.features", "urbanscene.transformation", "posematching.procrustes",
+             "posematching.pose_comparison", "posematching.single_person"]
+    return {n: importlib.import_module(DROPIN + "." + n) for n in names}
+
+
+def test_match_single_equals_reference_float64(mods):
+    """single_person.match_single(model, input) on the reference's own float64 poses: same decision, same score,
+    same (22,2) transformed input."""
+    sp = mods["posematching.single_person"]
+    g = load_golden("pose_match_single.npz")
+    n = 0
+    for k in range(0, len(g["model"]), 2):
+        ref = int(g["match"][k])
+        if ref == -1:
+            with pytest.raises(ValueError):
+                sp.match_single(g["model"][k], g["input"][k])
+            continue
+        if not np.isfinite(g["score"][k]):
+            continue
+        r = sp.match_single(g["model"][k], g["input"][k])
+        assert r.match_bool == bool(ref), k
+        np.testing.assert_allclose(r.error_score, g["score"][k], rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(r.input_transformation, g["input_transformation"][k], rtol=1e-6, atol=1e-8)
+        n += 1
+    assert n > 300
+    assert sp.match_single(g["model"][0], g["input"][0], normalise=False).match_bool is None
+
+
+def test_common_functions_equal_reference(mods):
+    common = mods["common"]
+    g = load_golden("pose_find_transformation.npz")
+    for k in range(0, len(g["npts"]), 3):
+        n = int(g["npts"][k])
+        out, A = common.find_transformation(g["model"][k][:n], g["input"][k][:n])
+        assert (len(A) != 0) == bool(g["has_A"][k])
+        if len(A):
+            np.testing.assert_allclose(out, g["out"][k][:n], rtol=1e-4, atol=1e-7)
+            np.testing.assert_allclose(A, g["A"][k], rtol=1e-4, atol=1e-7)
+    g = load_golden("pose_feature_scaling.npz")
+    for p, s in list(zip(g["poses"], g["scaled"]))[:20]:
+        got = common.feature_scaling(common.handle_undetected_points(p, p)[0])
+        np.testing.assert_allclose(got, s, rtol=1e-12, equal_nan=True)
+    face, torso, legs = common.split_in_face_legs_torso_v2(g["poses"][0])
+    assert common.unsplit(face, torso, legs).shape == (22, 2)
+
+
+def test_procrustes_equals_reference(mods):
+    pr = mods["posematching.procrustes"]
+    g = load_golden("pose_procrustes.npz")
+    for k in range(0, len(g["d"]), 5):
+        rf = int(g["reflection"][k % 6])
+        d, Z, tf = pr.procrustes(g["X"][k], g["Y"][k], bool(g["scaling"][k % 6]), "best" if rf == 0 else (rf == 1))
+        np.testing.assert_allclose(d, g["d"][k], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(Z, g["Z"][k], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(tf["rotation"].ravel(), g["tform"][k][:4], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(tf["translation"], g["tform"][k][5:], rtol=1e-4, atol=1e-6)
+    n0 = len(g["d"])
+    for j in range(0, len(g["superimpose_old_Z"]), 4):
+        a, b = g["X"][n0 + j], g["Y"][n0 + j]
+        Z, _ = pr.superimpose_old(a, b)
+        np.testing.assert_allclose(Z, g["superimpose_old_Z"][j], rtol=1e-4, atol=1e-6)
+        Z2, _ = pr.superimpose(a, b)
+        np.testing.assert_allclose(Z2, g["superimpose_Z"][j][:len(Z2)], rtol=1e-4, atol=1e-6)
+
+
+def test_pose_comparison_equals_reference(mods):
+    pc = mods["posematching.pose_comparison"]
+    for r in load_golden("pose_decide.npz")["rows"]:
+        A, d, sh = r[:9].reshape(3, 3), r[9], r[10]
+        assert pc.decide_torso_shoulders_incl(d, A, 0.236, 19.8, sh, 0.125) == bool(r[11])
+        assert pc.decide_legs(d, A, 0.082, 24) == bool(r[12])
+    assert pc.decide_legs(0.01, [], 0.082, 24) is True
+
+
+@pytest.mark.parametrize("det", ["sift", "orb"])
+def test_match_and_draw_scene_pair(mods, det):
+    """C1 through features.match_and_draw: kNN + ratio are pinned on the reference (cv2) bit for bit; the homography
+    stage is pinned on the oracle under the shared sample seed (cv2's sampler is private)."""
+    ft = mods["urbanscene.features"]
+    g = load_golden("scene_pisa1_pisa2_%s.npz" % det)
+    matcher = ft.BFMatcher(ft.NORM_L2 if det == "sift" else ft.NORM_HAMMING)
+    dm = g["desc_model"].astype(np.float32) if det == "sift" else g["desc_model"]
+    di = g["desc_input"].astype(np.float32) if det == "sift" else g["desc_input"]
+    raw = matcher.knnMatch(dm, trainDescriptors=di, k=2)
+    assert [m[0].trainIdx for m in raw] == g["knn_idx"][:, 0].tolist()
+    assert np.array_equal(np.float32([m[1].distance for m in raw]), g["knn_dist"][:, 1])
+    p1, p2, pairs = ft.filter_matches(g["kp_model"], g["kp_input"], raw)
+    np.testing.assert_array_equal(p1, g["p_model"])
+    np.testing.assert_array_equal(p2, g["p_input"])
+    model_img = np.zeros(tuple(g["model_shape"]), np.uint8)
+    input_img = np.zeros(tuple(g["input_shape"]), np.uint8)
+    mask, good_m, good_i, H, H2, n = ft.match_and_draw("w", matcher, dm, di, g["kp_model"], g["kp_input"], model_img,
+                                                       input_img, False)
+    src, dst = g["p_model"].reshape(-1, 2), g["p_input"].reshape(-1, 2)
+    rH, rmask, rn, _ = ransac_oracle.homography_batch(src, dst, [0, len(src)], 5.0, 2000, 0.995, 0)
+    rH2, _, _, _ = ransac_oracle.homography_batch(dst, src, [0, len(src)], 5.0, 2000, 0.995, 0)
+    np.testing.assert_array_equal(mask.ravel(), rmask)
+    np.testing.assert_allclose(H, rH[0], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(H2, rH2[0], rtol=1e-6, atol=1e-6)
+    assert n == int(rn[0]) == len(good_m) == len(good_i) and mask.shape == (len(src), 1) and mask.dtype == np.uint8
+    assert input_img.any()  # the projected model outline was drawn into input_img, as the reference does
+    assert ft.validate_homography(g["H"]) == bool(g["valid"])
+    # too few matches -> the reference's sentinel tuple
+    out = ft.match_and_draw("w", matcher, dm[:20], di, g["kp_model"][:20], g["kp_input"], model_img, input_img, False)
+    assert out == (None, None, None, None, None, None)
+
+
+def test_transformation_functions(mods):
+    tr = mods["urbanscene.transformation"]
+    g = load_golden("perspective_transform.npz")
+    pts = g["pts"].reshape(-1, 2)
+    p_trans, pose_trans, _ = tr.perspective_correction(g["H"], pts, pts, pts[:18], pts[-18:], None, None)
+    np.testing.assert_allclose(p_trans, g["out"].reshape(-1, 2), rtol=1e-6, atol=1e-5)
+    np.testing.assert_array_equal(pose_trans, p_trans[-18:])
+    assert tr.affine_multi(pts[:3], pts[:3], pts[:18], pts[:18], 480, 640, 480, 640, "x", None, None, None) == 1
+    import random
+    A = np.array([[0.9, 0.1], [-0.1, 0.9]])
+    model_bg, model_pose = pts[:40].astype(np.float64), pts[40:58].astype(np.float64)
+    input_bg, input_pose = model_bg @ A + 5.0, model_pose @ A + 5.0
+    s = tr.affine_multi(model_bg, input_bg, model_pose, input_pose, 480, 640, 480, 640, "x", None, None, None,
+                        rng=random.Random(3))
+    assert s < 1e-9  # an exact affine relation is recovered exactly
