@@ -2,25 +2,30 @@
 //
 // Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) at reference urbanscene/features.py:59.
 //
-//   ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t      ->  per query, order the database by  key = ||t||^2 - 2 q.t
+//   ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t      ->  per query, order the database by  s = 2 q.t - ||t||^2  (largest first)
+//
+// The norm is folded INTO the contraction: operand rows are 144 wide, A = [2q | 1 1 1 0..], B = [t | -p0 -p1 -p2 0..]
+// with ||t||^2 = p0 + p1 + p2 split into three 8-bit-significand pieces, so the accumulator already holds s and the
+// epilogue is a pure max-scan (no FMA, no norm traffic) at the price of a ninth K=16 MMA step per tile.
 //
 // OpenCV SIFT descriptors are integer valued (0..255) stored as float32, so bf16 operands are exact and
-// the FP32 accumulation of 128 products (< 2^23) is exact: key is the exact integer, the fused top-2 on
-// (key, index) is the exact answer, and ties fall to the lower index exactly as OpenCV resolves them.  The
+// the FP32 accumulation (every partial sum is an integer of magnitude <= 2^24) is exact: s is the exact integer, the
+// fused top-2 on (s, index) is the exact answer, and ties fall to the lower index exactly as OpenCV resolves them.  The
 // prep kernel verifies that property for every value; when it does not hold the kernel is skipped on the
 // device (no host round trip) and the FP32 CUDA-core engine produces the candidates instead.  Either way the
 // candidates go through l2_rerank_finalize (l2_simt.cu): exact FP32 distances from the ORIGINAL float32
 // rows, lexicographic (d2, index) top-2, sqrtf -- the numbers DMatch.distance carries.
 //
 // Kernel shape (one persistent CTA per SM, 384 threads, warp specialised):
-//   warp 0     TMA producer: the unit's 256 queries (2 x [128 x 128] bf16, SWIZZLE_128B, 64 KB, loaded once per
-//              unit) and a 4-stage ring of database tiles ([128 rows x 128] bf16, 32 KB per stage)
-//   warp 1     MMA issuer: per database tile 2 x 8 tcgen05.mma (M=128, N=128, K=16, kind::f16, cta_group::1)
+//   warp 0     TMA producer: the unit's 256 queries (2 x [128 x 144] bf16, 72 KB, loaded once per unit) and a 4-stage
+//              ring of database tiles ([128 rows x 144] bf16, 36 KB per stage); columns 0..127 land as two
+//              SWIZZLE_128B slabs, the 16 augmentation columns as one SWIZZLE_32B slab
+//   warp 1     MMA issuer: per database tile 2 x 9 tcgen05.mma (M=128, N=128, K=16, kind::f16, cta_group::1)
 //              into one of two TMEM accumulator buffers (2 x 2 x 128 columns = all 512 columns)
 //   warp 2     TMEM allocator
-//   warps 4-11 epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, key = fma(-2, acc, tn),
-//              min over 8 keys + one compare guards the (rare) top-2 insertion; the running top-2 lives in
-//              registers for the whole database sweep, so there is no reduction anywhere.
+//   warps 4-11 epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, an FMNMX3 tree over the
+//              32 values + one compare guards the (rare) top-2 insertion; the running top-2 lives in registers for
+//              the whole database sweep, so there is no reduction anywhere.
 // A unit is (256 queries) x (one split of the database); a CTA walks units round-robin so all CTAs sweep the
 // database in the same order and every database tile is fetched from HBM once and then served by L2.
 #include <cuda.h>
@@ -36,13 +41,13 @@ constexpr int TC_QB = 256;           // queries per unit (two M=128 MMA tiles)
 constexpr int TC_TN = 128;           // database rows per tile (MMA N)
 constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 384;
+constexpr int TC_KA = 144;                                  // operand row: 128 descriptor columns + 16 augmentation columns
 constexpr int TC_HALF_BYTES = 128 * 128;                    // [128 rows][64 bf16] = 16 KB, one swizzle-128B slab
-constexpr int TC_A_BYTES = 2 * 2 * TC_HALF_BYTES;           // 2 query tiles x 2 k-halves
-constexpr int TC_B_BYTES = 2 * TC_HALF_BYTES;               // per stage
-constexpr int TC_TN_SLOTS = 8;                              // ring of ||t||^2 tiles (>= stages + 2 accumulator buffers + 1)
-constexpr int TC_TN_BYTES = TC_TN * 4;                      // 512 B per tile
-constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + TC_TN_SLOTS * TC_TN_BYTES + 1024 /*alignment slack*/ +
-                              256 /*barriers*/;
+constexpr int TC_AUG_BYTES = 128 * 32;                      // [128 rows][16 bf16] = 4 KB, one swizzle-32B slab
+constexpr int TC_TILE_BYTES = 2 * TC_HALF_BYTES + TC_AUG_BYTES;  // 36 KB: one [128 x 144] operand tile
+constexpr int TC_A_BYTES = 2 * TC_TILE_BYTES;               // two query tiles
+constexpr int TC_B_BYTES = TC_TILE_BYTES;                   // per stage
+constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,13 +77,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float min3(float a, float b, float c) {
+__device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
-  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,40 +113,58 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// Same for the 16 augmentation columns: SWIZZLE_32B, rows 32 B apart, 8-row groups 256 B apart, layout type 6.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
 // Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TN >> 3) << 17) | ((128u >> 4) << 24);
 
 // ---- operand preparation --------------------------------------------------------------------------------
-// One warp per row: float32 -> bf16, ||row||^2 (database side), and the exactness check.  A value passes when
-// it is an integer with |v| <= 256: then bf16 holds it exactly and every partial sum of the contraction is
-// below 2^24.  flag[0] |= 1 otherwise.
+// One warp per row: float32 -> bf16 operand row of 144 columns and the exactness check.  A value passes when it is
+// an integer with |v| <= 256: then bf16 holds v and 2v exactly and every partial sum of the contraction is an
+// integer of magnitude <= 2^24.  flag[0] |= 1 otherwise.
+//   query side    (is_db == 0): [2q | 1 1 1 0 ...]
+//   database side (is_db == 1): [t | -p0 -p1 -p2 0 ...], ||t||^2 = p0 + p1 + p2 (bytes 0, 1, 2 of the integer norm);
+//                               rows n..n_pad are padding that can never be selected (s = -(2^24 - 1)).
 __global__ void __launch_bounds__(256)
-l2_tc_prep_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, __nv_bfloat16* __restrict__ xb,
-                  float* __restrict__ norm2, int* __restrict__ flag) {
+l2_tc_prep_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int is_db, __nv_bfloat16* __restrict__ xb,
+                  int* __restrict__ flag) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_pad) return;
-  if (row >= n) {  // padding rows of the norm array: never selected
-    if (norm2 && lane == 0) norm2[row] = __int_as_float(0x7f800000);
-    return;
-  }
-  const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * TC_D) + lane);
-  const float f[4] = {v.x, v.y, v.z, v.w};
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
   bool bad = false;
   float s = 0.f;
+  if (row < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * TC_D) + lane);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bad |= !(fabsf(f[i]) <= 256.f) || f[i] != rintf(f[i]);
-    s = fmaf(f[i], f[i], s);
+    for (int i = 0; i < 4; ++i) {
+      bad |= !(fabsf(f[i]) <= 256.f) || f[i] != rintf(f[i]);
+      s = fmaf(f[i], f[i], s);
+    }
   }
-  __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+  const float scale = is_db ? 1.f : 2.f;
+  __nv_bfloat162 lo = __floats2bfloat162_rn(scale * f[0], scale * f[1]), hi = __floats2bfloat162_rn(scale * f[2], scale * f[3]);
   uint2 packed;
   packed.x = *reinterpret_cast<uint32_t*>(&lo);
   packed.y = *reinterpret_cast<uint32_t*>(&hi);
-  reinterpret_cast<uint2*>(xb + row * TC_D)[lane] = packed;
-  if (norm2) {
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) norm2[row] = s;
+  __nv_bfloat16* dst = xb + row * TC_KA;
+  reinterpret_cast<uint2*>(dst)[lane] = packed;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane < 2) {  // the 16 augmentation columns, 8 per lane
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (lane == 0) {
+      if (!is_db) { a0 = a1 = a2 = 1.f; }
+      else if (row < n) {
+        const int in = bad ? 0 : (int)s;  // exact: s is an integer below 2^24 whenever the row passed the check
+        a0 = -(float)(in & 0xFF); a1 = -(float)(in & 0xFF00); a2 = -(float)(in & 0xFF0000);
+      } else { a0 = -255.f; a1 = -65280.f; a2 = -16711680.f; }
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a0, a1), p1 = __floats2bfloat162_rn(a2, 0.f);
+    uint4 w = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), 0u, 0u);
+    reinterpret_cast<uint4*>(dst + TC_D)[lane] = w;
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 1);
 }
@@ -157,56 +176,47 @@ struct TcTop2 {
 };
 
 __device__ __forceinline__ void tc_insert(TcTop2& t, float v, int col) {
-  if (v < t.k1) {  // strict: columns reach a thread in increasing index order, so ties keep the lower index
-    if (v < t.k0) { t.k1 = t.k0; t.i1 = t.i0; t.k0 = v; t.i0 = col; }
+  if (v > t.k1) {  // strict: columns reach a thread in increasing index order, so ties keep the lower index
+    if (v > t.k0) { t.k1 = t.k0; t.i1 = t.i0; t.k0 = v; t.i0 = col; }
     else { t.k1 = v; t.i1 = col; }
   }
 }
 
-// 32 accumulator columns of one query row: key = ||t||^2 - 2 q.t, one guard per 32 keys (FMNMX3 tree) in front of
-// the rare insertion.  `tn` points at the 32 norms in shared memory (broadcast LDS.128).
-__device__ __forceinline__ void tc_process32(uint32_t (&acc)[32], const float4* tn, int col, TcTop2& t) {
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 n4 = tn[i];
-    v[4 * i + 0] = fmaf(-2.f, __uint_as_float(acc[4 * i + 0]), n4.x);
-    v[4 * i + 1] = fmaf(-2.f, __uint_as_float(acc[4 * i + 1]), n4.y);
-    v[4 * i + 2] = fmaf(-2.f, __uint_as_float(acc[4 * i + 2]), n4.z);
-    v[4 * i + 3] = fmaf(-2.f, __uint_as_float(acc[4 * i + 3]), n4.w);
-  }
+// 32 accumulator columns of one query row; each holds s = 2 q.t - ||t||^2.  One guard per 32 values (FMNMX3 tree) in
+// front of the rare insertion.
+__device__ __forceinline__ void tc_process32(const uint32_t (&acc)[32], int col, TcTop2& t) {
   float m[11];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) m[i] = min3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-  m[10] = fminf(v[30], v[31]);
-  const float a = min3(m[0], m[1], m[2]), b = min3(m[3], m[4], m[5]), c = min3(m[6], m[7], m[8]);
-  const float lo = fminf(min3(a, b, c), fminf(m[9], m[10]));
-  if (lo < t.k1) {
+  for (int i = 0; i < 10; ++i)
+    m[i] = max3(__uint_as_float(acc[3 * i]), __uint_as_float(acc[3 * i + 1]), __uint_as_float(acc[3 * i + 2]));
+  m[10] = fmaxf(__uint_as_float(acc[30]), __uint_as_float(acc[31]));
+  const float a = max3(m[0], m[1], m[2]), b = max3(m[3], m[4], m[5]), c = max3(m[6], m[7], m[8]);
+  const float hi = fmaxf(max3(a, b, c), fmaxf(m[9], m[10]));
+  if (hi > t.k1) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) tc_insert(t, v[j], col + j);
+    for (int j = 0; j < 32; ++j) tc_insert(t, __uint_as_float(acc[j]), col + j);
   }
 }
 
 // part_idx [splits][nq][2].  `gate` (device int): the kernel does nothing unless *gate == 0.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
-                  const float* __restrict__ tn, int64_t nq, int64_t nt, int q_blocks, int splits, int64_t rows_per_split,
-                  int32_t* __restrict__ part_idx, const int* __restrict__ gate) {
+l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qa,
+                  const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt,
+                  int q_blocks, int splits, int64_t rows_per_split, int32_t* __restrict__ part_idx,
+                  const int* __restrict__ gate) {
   if (*gate != 0) return;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_a = smem;                          // [2 tiles][2 halves][16 KB]
-  uint8_t* smem_b = smem + TC_A_BYTES;             // [stages][2 halves][16 KB]
-  float* smem_tn = reinterpret_cast<float*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);  // [slots][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES + TC_TN_SLOTS * TC_TN_BYTES);
+  uint8_t* smem_a = smem;                          // [2 tiles][16 KB | 16 KB | 4 KB]
+  uint8_t* smem_b = smem + TC_A_BYTES;             // [stages][16 KB | 16 KB | 4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);
   uint64_t* full = bars;                           // [stages]   TMA -> MMA
   uint64_t* empty = bars + TC_STAGES;              // [stages]   MMA -> TMA
   uint64_t* tmem_full = bars + 2 * TC_STAGES;      // [2]        MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2; // [2]        epilogue -> MMA
   uint64_t* a_full = bars + 2 * TC_STAGES + 4;     // query tiles landed
   uint64_t* a_empty = bars + 2 * TC_STAGES + 5;    // all MMAs of the unit retired
-  uint64_t* tn_full = bars + 2 * TC_STAGES + 6;    // [slots]    norms of a database tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6 + TC_TN_SLOTS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -215,7 +225,6 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < TC_TN_SLOTS; ++i) mbar_init(tn_full + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -234,6 +243,8 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_t) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qa) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ta) : "memory");
       uint32_t it = 0, un = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
         const int split = u / q_blocks, qb = u - split * q_blocks;
@@ -243,10 +254,13 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         mbar_wait(a_empty, (un & 1) ^ 1);
         mbar_expect_tx(a_full, TC_A_BYTES);
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d(smem_a + (m * 2 + h) * TC_HALF_BYTES, &map_q, a_full, h * 64, qb * TC_QB + m * 128);
+        for (int m = 0; m < 2; ++m) {
+          uint8_t* dst = smem_a + m * TC_TILE_BYTES;
+          const int row0 = qb * TC_QB + m * 128;
+          tma_load_2d(dst, &map_q, a_full, 0, row0);
+          tma_load_2d(dst + TC_HALF_BYTES, &map_q, a_full, 64, row0);
+          tma_load_2d(dst + 2 * TC_HALF_BYTES, &map_qa, a_full, TC_D, row0);
+        }
         for (int j = 0; j < tiles; ++j, ++it) {
           const int s = it % TC_STAGES;
           mbar_wait(empty + s, ((it / TC_STAGES) & 1) ^ 1);
@@ -254,12 +268,7 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const int row0 = (int)(t_begin + (int64_t)j * TC_TN);
           tma_load_2d(smem_b + s * TC_B_BYTES, &map_t, full + s, 0, row0);
           tma_load_2d(smem_b + s * TC_B_BYTES + TC_HALF_BYTES, &map_t, full + s, 64, row0);
-          // ||t||^2 of the tile for the epilogue.  Slot reuse needs no extra barrier: tile `it` is only issued once the
-          // MMAs of tile it-STAGES retired, those waited for the epilogue of tile it-STAGES-2, and the epilogue reads
-          // its norms before it releases the accumulator -> at most STAGES+2 slots are live.
-          const int ts = it % TC_TN_SLOTS;
-          mbar_expect_tx(tn_full + ts, TC_TN_BYTES);
-          bulk_load_1d(smem_tn + ts * TC_TN, tn + row0, TC_TN_BYTES, tn_full + ts);
+          tma_load_2d(smem_b + s * TC_B_BYTES + 2 * TC_HALF_BYTES, &map_ta, full + s, TC_D, row0);
         }
       }
     }
@@ -285,9 +294,12 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
             for (int k = 0; k < TC_D / 16; ++k) {
               const uint32_t koff = (uint32_t)((k >> 2) * TC_HALF_BYTES + (k & 3) * 32);
-              tc_mma_bf16(d_addr, umma_desc_sw128(a_addr + m * 2 * TC_HALF_BYTES + koff),
+              tc_mma_bf16(d_addr, umma_desc_sw128(a_addr + m * TC_TILE_BYTES + koff),
                           umma_desc_sw128(b_addr + s * TC_B_BYTES + koff), TC_IDESC, k > 0 ? 1u : 0u);
             }
+            // ninth step: the augmentation columns subtract ||t||^2
+            tc_mma_bf16(d_addr, umma_desc_sw32(a_addr + m * TC_TILE_BYTES + 2 * TC_HALF_BYTES),
+                        umma_desc_sw32(b_addr + s * TC_B_BYTES + 2 * TC_HALF_BYTES), TC_IDESC, 1u);
           }
           tc_commit(empty + s);       // the stage may be refilled once these MMAs have read it
           tc_commit(tmem_full + b);   // accumulators ready for the epilogue
@@ -305,37 +317,35 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int64_t t_end = min(nt, t_begin + rows_per_split);
       const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
       TcTop2 top;
-      top.k0 = top.k1 = __int_as_float(0x7f800000);
+      top.k0 = top.k1 = __int_as_float(0xff800000);  // -inf
       top.i0 = top.i1 = -1;
       for (int j = 0; j < tiles; ++j, ++it) {
         const int b = it & 1;
         const int col0 = (int)(t_begin + (int64_t)j * TC_TN);
-        const int ts = it % TC_TN_SLOTS;
-        const float4* tn4 = reinterpret_cast<const float4*>(smem_tn + ts * TC_TN);
         uint32_t acc0[32], acc1[32];
         mbar_wait(tmem_full + b, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + m) * TC_TN);
         tc_ld32(taddr, acc0);
         tc_ld32(taddr + 32, acc1);
-        mbar_wait(tn_full + ts, (it / TC_TN_SLOTS) & 1);
         tc_wait_ld();
-        tc_process32(acc0, tn4, col0, top);
+        tc_process32(acc0, col0, top);
         tc_ld32(taddr + 64, acc0);
-        tc_process32(acc1, tn4 + 8, col0 + 32, top);
+        tc_process32(acc1, col0 + 32, top);
         tc_ld32(taddr + 96, acc1);
         tc_wait_ld();
         // every column of this buffer is in registers: hand the accumulator back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + b);
-        tc_process32(acc0, tn4 + 16, col0 + 64, top);
-        tc_process32(acc1, tn4 + 24, col0 + 96, top);
+        tc_process32(acc0, col0 + 64, top);
+        tc_process32(acc1, col0 + 96, top);
       }
       const int64_t row = (int64_t)qb * TC_QB + m * 128 + quarter * 32 + lane;
       if (row < nq) {
         int32_t* o = part_idx + ((int64_t)split * nq + row) * 2;
-        o[0] = top.i0; o[1] = top.i1;
+        o[0] = top.i0 < nt ? top.i0 : -1;  // a padding row can only surface when the split holds fewer than 2 rows
+        o[1] = top.i1 < nt ? top.i1 : -1;
       }
     }
   }
@@ -365,16 +375,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows][128] bf16 row-major, box = 64 columns x 128 rows, 128-byte swizzle, out-of-range rows read as zero
-static int make_map(CUtensorMap* map, const void* base, int64_t rows) {
+// [rows][144] bf16 row-major; box = `box_cols` columns x 128 rows with the given swizzle; out-of-range rows read as 0
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_cols, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   HPUSM_REQUIRE(fn, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t dims[2] = {(cuuint64_t)TC_D, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)TC_D * sizeof(__nv_bfloat16)};
-  cuuint32_t box[2] = {64, 128};
+  cuuint64_t dims[2] = {(cuuint64_t)TC_KA, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)TC_KA * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HPUSM_REQUIRE(r == CUDA_SUCCESS, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return HPUSM_OK;
@@ -395,7 +405,7 @@ static int tc_splits(int64_t nq, int64_t nt) {
 }
 
 struct TcLayout {
-  size_t qb, tb, tn, flag, part, total;
+  size_t qb, tb, flag, part, total;
   int splits_tc, splits_simt, nparts;
   int64_t nt_pad;
 };
@@ -407,9 +417,8 @@ static TcLayout tc_layout(int64_t nq, int64_t nt, int mode) {
   L.splits_simt = (mode == HPUSM_L2_AUTO) ? l2_simt_splits(nq, nt) : 0;
   L.nparts = L.splits_tc > L.splits_simt ? L.splits_tc : L.splits_simt;
   size_t off = 0;
-  L.qb = off; off += align_up((size_t)nq * TC_D * 2, 1024);
-  L.tb = off; off += align_up((size_t)nt * TC_D * 2, 1024);
-  L.tn = off; off += align_up((size_t)L.nt_pad * sizeof(float), 1024);
+  L.qb = off; off += align_up((size_t)nq * TC_KA * 2, 1024);
+  L.tb = off; off += align_up((size_t)L.nt_pad * TC_KA * 2, 1024);
   L.flag = off; off += 1024;
   L.part = off; off += align_up((size_t)L.nparts * nq * 2 * sizeof(int32_t), 1024);
   L.total = off;
@@ -436,21 +445,21 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   char* base = reinterpret_cast<char*>(ws);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(base + L.qb);
   __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(base + L.tb);
-  float* tn = reinterpret_cast<float*>(base + L.tn);
   int* flag = reinterpret_cast<int*>(base + L.flag);
   int32_t* part = reinterpret_cast<int32_t*>(base + L.part);
 
   HPUSM_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
   HPUSM_CUDA_OK(cudaMemsetAsync(part, 0xff, (size_t)L.nparts * nq * 2 * sizeof(int32_t), st));
-  HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((nq + 7) / 8), 256, 0, st, q, nq, nq, qb, (float*)nullptr, flag);
+  HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((nq + 7) / 8), 256, 0, st, q, nq, nq, 0, qb, flag);
   HPUSM_CHECK_LAUNCH();
-  HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((L.nt_pad + 7) / 8), 256, 0, st, t, nt, L.nt_pad, tb, tn, flag);
+  HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((L.nt_pad + 7) / 8), 256, 0, st, t, nt, L.nt_pad, 1, tb, flag);
   HPUSM_CHECK_LAUNCH();
 
-  CUtensorMap map_q, map_t;
-  int rc = make_map(&map_q, qb, nq);
-  if (rc != HPUSM_OK) return rc;
-  rc = make_map(&map_t, tb, nt);
+  CUtensorMap map_q, map_qa, map_t, map_ta;
+  int rc = make_map(&map_q, qb, nq, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == HPUSM_OK) rc = make_map(&map_qa, qb, nq, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc == HPUSM_OK) rc = make_map(&map_t, tb, L.nt_pad, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == HPUSM_OK) rc = make_map(&map_ta, tb, L.nt_pad, 16, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != HPUSM_OK) return rc;
 
   static bool attr_done[64] = {false};
@@ -465,8 +474,8 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   rows_per_split = (rows_per_split + TC_TN - 1) / TC_TN * TC_TN;
   const int units = q_blocks * L.splits_tc;
   const int grid = units < sm_count() ? units : sm_count();
-  HPUSM_LAUNCH_TIMED(l2_tc_knn2_kernel, grid, TC_THREADS, TC_SMEM_BYTES, st, map_q, map_t, tn, nq, nt, q_blocks, L.splits_tc,
-                     rows_per_split, part, flag);
+  HPUSM_LAUNCH_TIMED(l2_tc_knn2_kernel, grid, TC_THREADS, TC_SMEM_BYTES, st, map_q, map_qa, map_t, map_ta, nq, nt, q_blocks,
+                     L.splits_tc, rows_per_split, part, flag);
   HPUSM_CHECK_LAUNCH();
   if (mode == HPUSM_L2_AUTO) {
     rc = l2_simt_candidates_gated(q, nq, t, nt, d, L.splits_simt, part, flag, st);
