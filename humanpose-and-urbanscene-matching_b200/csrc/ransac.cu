@@ -11,10 +11,12 @@
 //            reject degenerate samples (collinear triples, inconsistent orientation), and solve the
 //            exact 4-point homography in FP64 in closed form (unit square -> quad on both sides,
 //            H = S_dst * adj(S_src)); the FP32 model is parked in shared memory.
-//   phase B  each WARP scores hypotheses (two at a time) against the pair's matches, which are staged in
-//            shared memory as float4 (x, y, x', y') and read with conflict-free LDS.128; the inlier
-//            test is division free, (u - x'w)^2 + (v - y'w)^2 <= thr^2 w^2, and the count is
-//            popc(ballot).
+//   phase B  the surviving hypotheses are compacted; a warp takes 32 of them (one per LANE, model in registers) and
+//            streams a segment of the pair's matches, staged in shared memory as float4 (x, y, x', y') and read as
+//            broadcast LDS.128; the inlier test is division free, (u - x'w)^2 + (v - y'w)^2 <= thr^2 w^2, the count
+//            lives in a register.  (Round-1 first version: one warp per hypothesis + popc(ballot), as north_star
+//            sketches; ncu showed 2.6x the instructions per reprojection -- ballot, POPC on the 16-lane XU pipe, and
+//            half-empty hypothesis pairs -- see profiles/r1_ransac_score_ncu.txt.)
 //   phase C  the sequential early-exit of RANSAC (cv2's adaptive iteration bound) is replayed over the
 //            counts by one thread, so the parallel evaluation returns what the sequential loop would.
 // A second kernel re-derives the winner, writes its inlier mask, and refines: normalised least-squares
@@ -133,21 +135,23 @@ __device__ __forceinline__ bool homography_from_maps(const double* S, const doub
   return ok;
 }
 
-// Whole minimal-sample pipeline for one hypothesis. Points are translated to the first sample point
-// before the closed-form solve (exact in FP64 for pixel-range FP32 input) and the translation is folded
-// back in afterwards.
-__device__ bool hypothesis_model(const float* __restrict__ src, const float* __restrict__ dst, uint32_t K,
-                                 uint64_t seed, uint64_t pair, uint64_t hyp, double* H) {
+// The four sampled correspondences of hypothesis (pair, hyp) as doubles.
+__device__ __forceinline__ void hypothesis_points(const float* __restrict__ src, const float* __restrict__ dst, uint32_t K,
+                                                  uint64_t seed, uint64_t pair, uint64_t hyp, double* sx, double* sy,
+                                                  double* dx, double* dy) {
   uint32_t id[4];
   sample4(seed, pair, hyp, K, id);
-  double sx[4], sy[4], dx[4], dy[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 s = reinterpret_cast<const float2*>(src)[id[j]];
     const float2 d = reinterpret_cast<const float2*>(dst)[id[j]];
     sx[j] = (double)s.x; sy[j] = (double)s.y; dx[j] = (double)d.x; dy[j] = (double)d.y;
   }
-  if (degenerate4(sx, sy, dx, dy)) return false;
+}
+
+// Exact 4-point homography of a non-degenerate sample. Points are translated to the first sample point before the
+// closed-form solve (exact in FP64 for pixel-range FP32 input) and the translation is folded back in afterwards.
+__device__ bool hypothesis_solve(double* sx, double* sy, double* dx, double* dy, double* H) {
   const double osx = sx[0], osy = sy[0], odx = dx[0], ody = dy[0];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -178,6 +182,15 @@ __device__ bool hypothesis_model(const float* __restrict__ src, const float* __r
   return ok;
 }
 
+// Whole minimal-sample pipeline for one hypothesis.
+__device__ bool hypothesis_model(const float* __restrict__ src, const float* __restrict__ dst, uint32_t K,
+                                 uint64_t seed, uint64_t pair, uint64_t hyp, double* H) {
+  double sx[4], sy[4], dx[4], dy[4];
+  hypothesis_points(src, dst, K, seed, pair, hyp, sx, sy, dx, dy);
+  if (degenerate4(sx, sy, dx, dy)) return false;
+  return hypothesis_solve(sx, sy, dx, dy, H);
+}
+
 // Division-free inlier test in FP32 with explicit FMAs (mirrored by the oracle with fmaf()).
 __device__ __forceinline__ bool is_inlier(const float* h, float x, float y, float xp, float yp, float thr2) {
   const float w = __fmaf_rn(h[6], x, __fmaf_rn(h[7], y, h[8]));
@@ -204,7 +217,14 @@ __device__ int update_num_iters(double conf, double outlier_ratio, int max_iters
   return (int)llrint(num / denom);
 }
 
-// grid.x = pairs. dynamic smem: float models[nhyp][9]; int counts[nhyp]; float4 pts[chunk].
+// grid.x = pairs. dynamic smem: float4 pts[chunk]; float models[nhyp][9] (compacted); int counts[nhyp]; int hyp_of[nhyp].
+//   A1  one LANE per hypothesis: sample + degeneracy test; survivors are compacted (ballot + one smem atomic per warp)
+//   A2  one LANE per surviving hypothesis: FP64 closed-form solve, FP32 model parked in shared memory
+//   B   lane = hypothesis (model in 9 registers), the pair's matches stream through as broadcast LDS.128; work items
+//       are (32 hypotheses) x (RS_SEG matches) so all warps stay busy; the count lives in a register
+//   C   sequential replay of RANSAC's early exit over the counts
+constexpr int RS_SEG = 512;
+
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst,
                     const int64_t* __restrict__ pair_offsets, float thresh, int nhyp, double confidence,
@@ -214,6 +234,8 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   float4* pts = reinterpret_cast<float4*>(rs_smem);
   float* models = reinterpret_cast<float*>(rs_smem + (size_t)chunk * sizeof(float4));
   int* counts = reinterpret_cast<int*>(models + (size_t)nhyp * 9);
+  int* hyp_of = counts + nhyp;
+  __shared__ int n_valid;
   const int64_t pair = blockIdx.x;
   const int64_t m0 = pair_offsets[pair];
   const int64_t K64 = pair_offsets[pair + 1] - m0;
@@ -222,18 +244,43 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   const float* d = dst + m0 * 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float thr2 = __fmul_rn(thresh, thresh);
+  if (tid == 0) n_valid = 0;
+  __syncthreads();
 
-  // phase A: one hypothesis per lane
-  for (int h = tid; h < nhyp; h += RS_THREADS) {
-    double H[9];
-    const bool ok = K >= 4 && hypothesis_model(s, d, K, seed, (uint64_t)pair, (uint64_t)h, H);
+  // phase A1
+  const int rounds = (nhyp + RS_THREADS - 1) / RS_THREADS;
+  for (int r = 0; r < rounds; ++r) {
+    const int h = r * RS_THREADS + tid;
+    bool ok = false;
+    if (h < nhyp && K >= 4) {
+      double sx[4], sy[4], dx[4], dy[4];
+      hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+      ok = !degenerate4(sx, sy, dx, dy);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(&n_valid, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) hyp_of[base + __popc(b & ((1u << lane) - 1u))] = h;
+    if (h < nhyp) counts[h] = ok ? 0 : -1;
+  }
+  __syncthreads();
+  const int nv = n_valid;
+
+  // phase A2
+  for (int j = tid; j < nv; j += RS_THREADS) {
+    const int h = hyp_of[j];
+    double sx[4], sy[4], dx[4], dy[4], H[9];
+    hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+    const bool ok = hypothesis_solve(sx, sy, dx, dy, H);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) models[h * 9 + i] = ok ? (float)H[i] : 0.f;
-    counts[h] = ok ? 0 : -1;
+    for (int i = 0; i < 9; ++i) models[j * 9 + i] = ok ? (float)H[i] : 0.f;
+    if (!ok) { counts[h] = -1; hyp_of[j] = -1; }
   }
   __syncthreads();
 
-  // phase B: one warp per hypothesis (two in flight), matches staged chunk by chunk
+  // phase B
+  const int groups = (nv + 31) >> 5;
   for (int64_t c0 = 0; c0 < K64; c0 += chunk) {
     const int cn = (int)min((int64_t)chunk, K64 - c0);
     for (int i = tid; i < cn; i += RS_THREADS) {
@@ -242,31 +289,22 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       pts[i] = make_float4(a.x, a.y, b.x, b.y);
     }
     __syncthreads();
-    for (int h = warp; h < nhyp; h += 2 * RS_WARPS) {
-      const int h2 = h + RS_WARPS;
-      const bool v1 = counts[h] >= 0;
-      const bool v2 = h2 < nhyp && counts[h2] >= 0;
-      if (!v1 && !v2) continue;
-      float ha[9], hb[9];
+    const int segs = (cn + RS_SEG - 1) / RS_SEG;
+    for (int item = warp; item < groups * segs; item += RS_WARPS) {
+      const int g = item / segs, sg = item - g * segs;
+      const int j = g * 32 + lane;
+      const int h = j < nv ? hyp_of[j] : -1;
+      float hm[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        ha[i] = models[h * 9 + i];
-        hb[i] = models[(v2 ? h2 : h) * 9 + i];
+      for (int i = 0; i < 9; ++i) hm[i] = h >= 0 ? models[j * 9 + i] : 0.f;
+      const int p0 = sg * RS_SEG, p1 = min(cn, p0 + RS_SEG);
+      int cnt = 0;
+#pragma unroll 4
+      for (int i = p0; i < p1; ++i) {
+        const float4 p = pts[i];
+        cnt += is_inlier(hm, p.x, p.y, p.z, p.w, thr2) ? 1 : 0;
       }
-      int ca = 0, cb = 0;
-      for (int base = 0; base < cn; base += 32) {  // every lane takes part in the ballot, tail lanes vote 0
-        const int i = base + lane;
-        const bool in = i < cn;
-        const float4 p = pts[in ? i : 0];
-        const bool ia = in && is_inlier(ha, p.x, p.y, p.z, p.w, thr2);
-        const bool ib = in && is_inlier(hb, p.x, p.y, p.z, p.w, thr2);
-        ca += __popc(__ballot_sync(0xffffffffu, ia));
-        cb += __popc(__ballot_sync(0xffffffffu, ib));
-      }
-      if (lane == 0) {
-        if (v1) counts[h] += ca;
-        if (v2) counts[h2] += cb;
-      }
+      if (h >= 0 && cnt) atomicAdd(&counts[h], cnt);
     }
     __syncthreads();
   }
@@ -587,12 +625,12 @@ ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ 
 }
 
 static size_t ransac_smem_bytes(int nhyp, int chunk) {
-  return (size_t)chunk * sizeof(float4) + (size_t)nhyp * (9 * sizeof(float) + sizeof(int));
+  return (size_t)chunk * sizeof(float4) + (size_t)nhyp * (9 * sizeof(float) + 2 * sizeof(int));
 }
 
 static int ransac_pick_chunk(int nhyp) {
   // keep at least two CTAs per SM resident when the hypothesis table allows it
-  const size_t table = (size_t)nhyp * 40;
+  const size_t table = (size_t)nhyp * 44;
   size_t budget = 100 * 1024;
   if (table + 1024 * sizeof(float4) > budget) budget = 220 * 1024;
   if (table + 256 * sizeof(float4) > budget) return -1;
