@@ -65,7 +65,9 @@ __device__ __forceinline__ void lsq_add(LsqSums& m, double x, double y, double X
 
 // Minimum-norm solution via the pseudo-inverse of the 3x3 normal matrix (what an SVD-based lstsq
 // returns when the design matrix has rank < 3: fewer than three detected joints, or collinear joints).
-__device__ __noinline__ void lsq_solve_deficient(const LsqSums& m, double A[9]) {
+// Takes the sums BY VALUE and fills a caller-local scratch array: nothing of the hot path has its address taken, so
+// the moments and the 3x3 result stay in registers for the (overwhelmingly common) full-rank problems.
+__device__ __noinline__ void lsq_solve_deficient(LsqSums m, double* A) {
   double M[3][3] = {{m.sxx, m.sxy, m.sx}, {m.sxy, m.syy, m.sy}, {m.sx, m.sy, m.n}};
   const double R[3][3] = {{m.sxX, m.sxY, m.sx}, {m.syX, m.syY, m.sy}, {m.sX, m.sY, m.n}};  // X^T [X Y 1]
   double V[3][3], w[3];
@@ -100,7 +102,10 @@ __device__ __forceinline__ void lsq_solve(const LsqSums& m, double A[9]) {
     A[3] = a10; A[4] = a11; A[5] = 0.0;
     A[6] = mX - mx * a00 - my * a10; A[7] = mY - mx * a01 - my * a11; A[8] = 1.0;
   } else {
-    lsq_solve_deficient(m, A);
+    double Ad[9];
+    lsq_solve_deficient(m, Ad);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = Ad[i];
   }
 }
 
@@ -207,69 +212,101 @@ __global__ void procrustes_batch_kernel(const double* __restrict__ X, const doub
 }
 
 // ---- match_single, batched ---------------------------------------------------------------------------
-__constant__ int c_torso[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 11};
-__constant__ int c_legs[7] = {1, 8, 9, 10, 11, 12, 13};
-__constant__ int c_face[5] = {0, 14, 15, 16, 17};
+// Body parts (common.py:269-274); constexpr so that every joint index is a compile-time constant after unrolling
+// (the pose lives in registers: a run-time index would push it to local memory).
+struct PartTorso {
+  static constexpr int N = 10;
+  __host__ __device__ static constexpr int at(int k) { return k < 9 ? k : 11; }
+};
+struct PartLegs {
+  static constexpr int N = 7;
+  __host__ __device__ static constexpr int at(int k) { return k == 0 ? 1 : 7 + k; }
+};
+struct PartFace {
+  static constexpr int N = 5;
+  __host__ __device__ static constexpr int at(int k) { return k == 0 ? 0 : 13 + k; }
+};
 
 struct PoseParams {
   double d_torso, tan_torso, rot_torso, d_legs, tan_legs, rot_legs, d_shoulder;
   int torso_use_tan, legs_use_tan;
 };
 
-// min/max scaling parameters of one masked pose (common.feature_scaling, including its quirk that the
-// minimum runs over BOTH coordinates of the rows whose x (resp. y) is non-zero).
+// min/max scaling of one masked pose (common.feature_scaling, including its quirk that each minimum runs over BOTH
+// coordinates of the rows whose x (resp. y) is non-zero).  The extrema are found in the storage type T (comparisons
+// only, exact); a scaled coordinate is  ((double)v - lo) * inv  so that v == lo gives an exact 0, as in the reference
+// (the part gates count exact zeros).  A literal 0 coordinate (undetected joint) scales to max(0, -lo*inv): 0 unless
+// the pose has negative coordinates (`general`).
+__device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float tmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double tmin(double a, double b) { return fmin(a, b); }
+
+template <typename T>
 struct Scale {
-  double xmin, ymin, ix, iy;  // ix = 1/(xmax-xmin)
-  bool valid;
+  T xlo, ylo;
+  double ix, iy, zx, zy;
+  bool valid, general;
 };
 
-template <typename GetX, typename GetY>
-__device__ __forceinline__ Scale make_scale(GetX gx, GetY gy, unsigned undetected) {
-  double xmax = -DBL_MAX, ymax = -DBL_MAX, xmin = DBL_MAX, ymin = DBL_MAX;
+template <typename T, typename Get>
+__device__ __forceinline__ Scale<T> make_scale(Get get, unsigned undetected) {
+  T xmax = -INFINITY, ymax = -INFINITY, xmin = INFINITY, ymin = INFINITY;
   bool anyx = false, anyy = false;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const bool u = (undetected >> j) & 1u;
-    const double x = u ? 0.0 : gx(j), y = u ? 0.0 : gy(j);
-    xmax = fmax(xmax, x); ymax = fmax(ymax, y);
-    const double lo = fmin(x, y);
-    if (x != 0.0) { xmin = fmin(xmin, lo); anyx = true; }
-    if (y != 0.0) { ymin = fmin(ymin, lo); anyy = true; }
+    const T x = u ? T(0) : get(2 * j), y = u ? T(0) : get(2 * j + 1);
+    xmax = tmax(xmax, x); ymax = tmax(ymax, y);
+    const T lo = tmin(x, y);
+    // rows with x == 0 (resp. y == 0) do not take part in the minimum: feed +inf instead of branching
+    xmin = tmin(xmin, x != T(0) ? lo : T(INFINITY));
+    ymin = tmin(ymin, y != T(0) ? lo : T(INFINITY));
+    anyx |= x != T(0); anyy |= y != T(0);
   }
-  Scale s;
+  Scale<T> s;
   // The reference raises here instead of returning: ValueError (np.min of an empty array) when no joint is
   // detected, LinAlgError (NaN/inf into LAPACK) when xmax == xmin or ymax == ymin.  Such poses never match.
   s.valid = anyx && anyy && xmax != xmin && ymax != ymin;
-  s.xmin = xmin; s.ymin = ymin;
-  s.ix = 1.0 / (xmax - xmin); s.iy = 1.0 / (ymax - ymin);
+  s.xlo = xmin; s.ylo = ymin;
+  s.ix = 1.0 / ((double)xmax - (double)xmin); s.iy = 1.0 / ((double)ymax - (double)ymin);
+  const double cx = (0.0 - (double)xmin) * s.ix, cy = (0.0 - (double)ymin) * s.iy;
+  s.zx = cx < 0.0 ? 0.0 : cx; s.zy = cy < 0.0 ? 0.0 : cy;
+  s.general = !(s.zx == 0.0 && s.zy == 0.0);
   return s;
 }
 
-__device__ __forceinline__ double scaled(double v, double lo, double inv, bool undetected) {
-  const double r = ((undetected ? 0.0 : v) - lo) * inv;
-  return r < 0.0 ? 0.0 : r;  // NaN stays NaN, exactly like output[output<0] = 0
+template <typename T, bool GENERAL>
+__device__ __forceinline__ double scale_coord(T raw, bool undetected, T lo, double inv, double z) {
+  const bool is0 = undetected || raw == T(0);
+  const T m = is0 ? lo : raw;                       // (lo - lo) * inv == exact 0
+  double r = ((double)m - (double)lo) * inv;
+  if (GENERAL) r = is0 ? z : (r < 0.0 ? 0.0 : r);   // poses with negative coordinates: the reference's clamp
+  return r;
 }
 
 struct PartResult {
-  double max_dist, shoulder, A[9];
+  double max_d2, shoulder_d2, A[9];  // squared distances: sqrt is monotone, one sqrt per part at the end
   int nz_model, nz_input;
   bool has_A;
 };
 
-// One body part: fit, transform, distances.  `rows` lists the joints of the part.
-template <int NP, typename GetMX, typename GetMY, typename GetIX, typename GetIY>
-__device__ __forceinline__ PartResult eval_part(const int* rows, GetMX mx, GetMY my, GetIX ix, GetIY iy,
-                                                double* transformed /* optional [NP][2] */) {
+// One body part: scale, fit, transform, distances.  model(j, x, y) / input(j, x, y) return SCALED coordinates of
+// joint j; `out` (optional) receives the transformed input rows [NP][2].
+template <typename Rows, typename Model, typename Input>
+__device__ __forceinline__ PartResult eval_part(Model model, Input input, double* out) {
+  constexpr int NP = Rows::N;
   PartResult r;
+  double xm[NP], ym[NP], xi[NP], yi[NP];
   LsqSums m = {};
   r.nz_model = 0; r.nz_input = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const int j = rows[k];
-    const double xi = ix(j), yi = iy(j), xm = mx(j), ym = my(j);
-    r.nz_model += (xm != 0.0) + (ym != 0.0);
-    r.nz_input += (xi != 0.0) + (yi != 0.0);
-    if (!(xi == 0.0 && yi == 0.0)) lsq_add(m, xi, yi, xm, ym);
+    model(Rows::at(k), xm[k], ym[k]);
+    input(Rows::at(k), xi[k], yi[k]);
+    r.nz_model += (xm[k] != 0.0) + (ym[k] != 0.0);
+    r.nz_input += (xi[k] != 0.0) + (yi[k] != 0.0);
+    if (!(xi[k] == 0.0 && yi[k] == 0.0)) lsq_add(m, xi[k], yi[k], xm[k], ym[k]);
   }
   r.has_A = m.n > 0.5;
   if (r.has_A) lsq_solve(m, r.A);
@@ -277,25 +314,22 @@ __device__ __forceinline__ PartResult eval_part(const int* rows, GetMX mx, GetMY
 #pragma unroll
     for (int i = 0; i < 9; ++i) r.A[i] = 0.0;
   }
-  r.max_dist = -1.0; r.shoulder = -1.0;
-  bool nan_seen = false;
+  r.max_d2 = -1.0; r.shoulder_d2 = -1.0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const int j = rows[k];
-    const double xi = ix(j), yi = iy(j), xm = mx(j), ym = my(j);
     double tx, ty;
-    if (!r.has_A) { tx = xi; ty = yi; }
-    else if (xi == 0.0 && yi == 0.0) { tx = 0.0; ty = 0.0; }
-    else { tx = xi * r.A[0] + yi * r.A[3] + r.A[6]; ty = xi * r.A[1] + yi * r.A[4] + r.A[7]; }
-    if (transformed) { transformed[2 * k] = tx; transformed[2 * k + 1] = ty; }
-    const double dx = xm - tx, dy = ym - ty;
-    const double dist = sqrt(dx * dx + dy * dy);
-    // Python's max() over the array keeps the first element unless a later one compares greater:
-    // a NaN in first position poisons the result, later NaNs are skipped.
-    if (k == 0) { r.max_dist = dist; nan_seen = dist != dist; }
-    else if (!nan_seen && dist > r.max_dist) r.max_dist = dist;
-    if (k == 1) r.shoulder = dist;
-    if (k == 4 && !(r.shoulder != r.shoulder) && dist > r.shoulder) r.shoulder = dist;
+    if (!r.has_A) { tx = xi[k]; ty = yi[k]; }
+    else if (xi[k] == 0.0 && yi[k] == 0.0) { tx = 0.0; ty = 0.0; }
+    else { tx = xi[k] * r.A[0] + yi[k] * r.A[3] + r.A[6]; ty = xi[k] * r.A[1] + yi[k] * r.A[4] + r.A[7]; }
+    if (out) { out[2 * k] = tx; out[2 * k + 1] = ty; }
+    const double dx = xm[k] - tx, dy = ym[k] - ty;
+    const double d2 = dx * dx + dy * dy;
+    // Python's max() keeps the first element unless a later one compares greater: a NaN in first position poisons
+    // the result, later NaNs are skipped.  The same holds for these comparisons on the squared values.
+    if (k == 0) r.max_d2 = d2;
+    else if (d2 > r.max_d2) r.max_d2 = d2;
+    if (k == 1) r.shoulder_d2 = d2;
+    if (k == 4 && d2 > r.shoulder_d2) r.shoulder_d2 = d2;
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) r.A[i] = zero_small(r.A[i]);
@@ -314,7 +348,7 @@ __device__ __forceinline__ bool rotation_ok(const PartResult& r, double tan_thr,
   return fmax(r2, r1) <= thr;
 }
 
-__device__ __forceinline__ double rotation_value(const PartResult& r) {
+__device__ __noinline__ double rotation_value(const PartResult& r) {
   if (!r.has_A) return 0.0;
   const double r1 = fabs(atan2(-r.A[1], r.A[0]) * 57.3), r2 = fabs(atan2(r.A[3], r.A[4]) * 57.3);
   return (r1 > r2) ? r1 : r2;  // Python max(rotation_2, rotation_1): the first argument wins unless the second is greater
@@ -341,20 +375,117 @@ __global__ void feature_scaling_batch_kernel(const double* __restrict__ pts, int
   }
 }
 
+// Decision for one pose pair (single_person.py:100-189) given the raw poses, the joint mask and both scalings.
+template <typename T, bool GENERAL, bool DETAIL>
+__device__ __forceinline__ void pose_decide(const T* sq /*shared*/, const T (&pr)[NJ * 2], unsigned und, const Scale<T>& s_q,
+                                            const Scale<T>& s_p, int query_is_model, const PoseParams& prm,
+                                            uint8_t* match, float* score, double* det) {
+  auto q_scaled = [&](int j, double& x, double& y) {
+    const bool u = (und >> j) & 1u;
+    x = scale_coord<T, GENERAL>(sq[2 * j], u, s_q.xlo, s_q.ix, s_q.zx);
+    y = scale_coord<T, GENERAL>(sq[2 * j + 1], u, s_q.ylo, s_q.iy, s_q.zy);
+  };
+  auto p_scaled = [&](int j, double& x, double& y) {
+    const bool u = (und >> j) & 1u;
+    x = scale_coord<T, GENERAL>(pr[2 * j], u, s_p.xlo, s_p.ix, s_p.zx);
+    y = scale_coord<T, GENERAL>(pr[2 * j + 1], u, s_p.ylo, s_p.iy, s_p.zy);
+  };
+  // detail layout: [0..7] scalars, [8..34] A face/torso/legs, [35..78] unsplit (common.py:276) transformed input:
+  // face[0] | torso (10) | legs (7) | face[1:5]
+  PartResult torso, legs;
+  if (query_is_model) {
+    torso = eval_part<PartTorso>(q_scaled, p_scaled, DETAIL ? det + 35 + 2 : nullptr);
+    legs = eval_part<PartLegs>(q_scaled, p_scaled, DETAIL ? det + 35 + 22 : nullptr);
+  } else {
+    torso = eval_part<PartTorso>(p_scaled, q_scaled, DETAIL ? det + 35 + 2 : nullptr);
+    legs = eval_part<PartLegs>(p_scaled, q_scaled, DETAIL ? det + 35 + 22 : nullptr);
+  }
+  const double torso_dist = sqrt(torso.max_d2), legs_dist = sqrt(legs.max_d2), shoulder_dist = sqrt(torso.shoulder_d2);
+
+  // single_person.py:150-178
+  bool ok_torso, ok_legs;
+  if (torso.nz_model > 4) {
+    if (torso.nz_model - torso.nz_input < 2)
+      ok_torso = torso_dist <= prm.d_torso && rotation_ok(torso, prm.tan_torso, prm.rot_torso, prm.torso_use_tan) &&
+                 shoulder_dist <= prm.d_shoulder;
+    else ok_torso = false;
+  } else ok_torso = true;
+  if (legs.nz_model > 8) {
+    if (legs.nz_model - legs.nz_input < 2)
+      ok_legs = legs_dist <= prm.d_legs && rotation_ok(legs, prm.tan_legs, prm.rot_legs, prm.legs_use_tan);
+    else ok_legs = false;
+  } else ok_legs = true;
+  const bool valid = s_q.valid && s_p.valid;
+  const double err = valid ? (torso_dist + legs_dist) * 0.5 : nan("");
+  *match = (valid && ok_torso && ok_legs) ? 1 : 0;
+  *score = (float)err;
+
+  if (DETAIL) {
+    double tf_face[10];
+    PartResult face = query_is_model ? eval_part<PartFace>(q_scaled, p_scaled, tf_face)
+                                     : eval_part<PartFace>(p_scaled, q_scaled, tf_face);
+    det[0] = torso_dist; det[1] = legs_dist; det[2] = sqrt(face.max_d2); det[3] = shoulder_dist;
+    det[4] = rotation_value(torso); det[5] = rotation_value(legs);
+    det[6] = (double)(torso.has_A ? 1 : 0) + 2.0 * (legs.has_A ? 1 : 0) + 4.0 * (face.has_A ? 1 : 0);
+    det[7] = err;
+    for (int i = 0; i < 9; ++i) { det[8 + i] = face.A[i]; det[17 + i] = torso.A[i]; det[26 + i] = legs.A[i]; }
+    double* o = det + 35;
+    o[0] = tf_face[0]; o[1] = tf_face[1];
+    for (int i = 0; i < 8; ++i) o[36 + i] = tf_face[2 + i];
+  }
+}
+
+// Load one pose row into registers (float: 9 x LDG.128; double: 18 x LDG.128).
+template <typename T>
+__device__ __forceinline__ void load_pose(const T* __restrict__ row, T (&pr)[NJ * 2]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4* src = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int v = 0; v < NJ * 2 / 4; ++v) {
+      const float4 x = __ldg(src + v);
+      pr[4 * v] = x.x; pr[4 * v + 1] = x.y; pr[4 * v + 2] = x.z; pr[4 * v + 3] = x.w;
+    }
+  } else {
+    const double2* src = reinterpret_cast<const double2*>(row);
+#pragma unroll
+    for (int v = 0; v < NJ; ++v) {
+      const double2 x = __ldg(src + v);
+      pr[2 * v] = x.x; pr[2 * v + 1] = x.y;
+    }
+  }
+}
+
+// Out-of-line variant for the rare poses with negative coordinates and for callers that want the per-part detail.
+// It re-reads the pose itself so that nothing of the fast path has its address taken (which would push the pose
+// registers of EVERY thread into local memory).
+template <typename T>
+__device__ __noinline__ void pose_decide_slow(const T* sq, const T* __restrict__ row, unsigned und, int query_is_model,
+                                              const PoseParams* prm, uint8_t* match, float* score, double* det) {
+  T pr[NJ * 2];
+  load_pose<T>(row, pr);
+  const Scale<T> s_q = make_scale<T>([&](int i) { return sq[i]; }, und);
+  const Scale<T> s_p = make_scale<T>([&](int i) { return pr[i]; }, und);
+  double scratch[HPUSM_POSE_DETAIL];
+  pose_decide<T, true, true>(sq, pr, und, s_q, s_p, query_is_model, *prm, match, score, det ? det : scratch);
+}
+
 constexpr int PM_THREADS = 128;
 
+#ifndef HPUSM_POSE_MIN_BLOCKS
+#define HPUSM_POSE_MIN_BLOCKS 2
+#endif
 template <typename T>
-__global__ void __launch_bounds__(PM_THREADS)
+__global__ void __launch_bounds__(PM_THREADS, HPUSM_POSE_MIN_BLOCKS)
 pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, int64_t n, int query_is_model,
                         PoseParams prm, uint8_t* __restrict__ match, float* __restrict__ score,
                         double* __restrict__ detail) {
-  __shared__ double sq[NJ * 2];
+  __shared__ T sq[NJ * 2];
   __shared__ unsigned sq_undetected;
-  if (threadIdx.x < NJ * 2) sq[threadIdx.x] = (double)query[threadIdx.x];
+  if (threadIdx.x < NJ * 2) sq[threadIdx.x] = query[threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned u = 0;
-    for (int j = 0; j < NJ; ++j) if (sq[2 * j] == 0.0 && sq[2 * j + 1] == 0.0) u |= 1u << j;
+    for (int j = 0; j < NJ; ++j) if (sq[2 * j] == T(0) && sq[2 * j + 1] == T(0)) u |= 1u << j;
     sq_undetected = u;
   }
   __syncthreads();
@@ -362,83 +493,20 @@ pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, i
   if (p >= n) return;
 
   T pr[NJ * 2];
-  if constexpr (sizeof(T) == 4) {
-    const float4* src = reinterpret_cast<const float4*>(db + p * (NJ * 2));
-#pragma unroll
-    for (int v = 0; v < NJ * 2 / 4; ++v) {
-      const float4 x = __ldg(src + v);
-      pr[4 * v] = x.x; pr[4 * v + 1] = x.y; pr[4 * v + 2] = x.z; pr[4 * v + 3] = x.w;
-    }
-  } else {
-    const double2* src = reinterpret_cast<const double2*>(db + p * (NJ * 2));
-#pragma unroll
-    for (int v = 0; v < NJ; ++v) {
-      const double2 x = __ldg(src + v);
-      pr[2 * v] = x.x; pr[2 * v + 1] = x.y;
-    }
-  }
+  load_pose<T>(db + p * (NJ * 2), pr);
   // common.handle_undetected_points: a joint missing on either side is (0,0) on both
   unsigned und = sq_undetected;
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
     if (pr[2 * j] == T(0) && pr[2 * j + 1] == T(0)) und |= 1u << j;
 
-  auto qx = [&](int j) { return sq[2 * j]; };
-  auto qy = [&](int j) { return sq[2 * j + 1]; };
-  auto px = [&](int j) { return (double)pr[2 * j]; };
-  auto py = [&](int j) { return (double)pr[2 * j + 1]; };
-  const Scale s_q = make_scale(qx, qy, und);
-  const Scale s_p = make_scale(px, py, und);
-
-  auto sqx = [&](int j) { return scaled(sq[2 * j], s_q.xmin, s_q.ix, (und >> j) & 1u); };
-  auto sqy = [&](int j) { return scaled(sq[2 * j + 1], s_q.ymin, s_q.iy, (und >> j) & 1u); };
-  auto spx = [&](int j) { return scaled((double)pr[2 * j], s_p.xmin, s_p.ix, (und >> j) & 1u); };
-  auto spy = [&](int j) { return scaled((double)pr[2 * j + 1], s_p.ymin, s_p.iy, (und >> j) & 1u); };
-
+  const Scale<T> s_q = make_scale<T>([&](int i) { return sq[i]; }, und);
+  const Scale<T> s_p = make_scale<T>([&](int i) { return pr[i]; }, und);
   double* det = detail ? detail + p * HPUSM_POSE_DETAIL : nullptr;
-  double tf_face[10], tf_torso[20], tf_legs[14];
-  PartResult face, torso, legs;
-  if (query_is_model) {
-    torso = eval_part<10>(c_torso, sqx, sqy, spx, spy, det ? tf_torso : nullptr);
-    legs = eval_part<7>(c_legs, sqx, sqy, spx, spy, det ? tf_legs : nullptr);
-    if (det) face = eval_part<5>(c_face, sqx, sqy, spx, spy, tf_face);
-  } else {
-    torso = eval_part<10>(c_torso, spx, spy, sqx, sqy, det ? tf_torso : nullptr);
-    legs = eval_part<7>(c_legs, spx, spy, sqx, sqy, det ? tf_legs : nullptr);
-    if (det) face = eval_part<5>(c_face, spx, spy, sqx, sqy, tf_face);
-  }
-
-  // single_person.py:150-178
-  bool ok_torso, ok_legs;
-  if (torso.nz_model > 4) {
-    if (torso.nz_model - torso.nz_input < 2)
-      ok_torso = torso.max_dist <= prm.d_torso && rotation_ok(torso, prm.tan_torso, prm.rot_torso, prm.torso_use_tan) &&
-                 torso.shoulder <= prm.d_shoulder;
-    else ok_torso = false;
-  } else ok_torso = true;
-  if (legs.nz_model > 8) {
-    if (legs.nz_model - legs.nz_input < 2)
-      ok_legs = legs.max_dist <= prm.d_legs && rotation_ok(legs, prm.tan_legs, prm.rot_legs, prm.legs_use_tan);
-    else ok_legs = false;
-  } else ok_legs = true;
-  const bool valid = s_q.valid && s_p.valid;
-  const double err = valid ? (torso.max_dist + legs.max_dist) * 0.5 : nan("");
-  match[p] = (valid && ok_torso && ok_legs) ? 1 : 0;
-  score[p] = (float)err;
-
-  if (det) {
-    det[0] = torso.max_dist; det[1] = legs.max_dist; det[2] = face.max_dist; det[3] = torso.shoulder;
-    det[4] = rotation_value(torso); det[5] = rotation_value(legs);
-    det[6] = (double)(torso.has_A ? 1 : 0) + 2.0 * (legs.has_A ? 1 : 0) + 4.0 * (face.has_A ? 1 : 0);
-    det[7] = err;
-    for (int i = 0; i < 9; ++i) { det[8 + i] = face.A[i]; det[17 + i] = torso.A[i]; det[26 + i] = legs.A[i]; }
-    // unsplit (common.py:276): face[0], torso (10), legs (7), face[1:5]
-    double* o = det + 35;
-    o[0] = tf_face[0]; o[1] = tf_face[1];
-    for (int i = 0; i < 20; ++i) o[2 + i] = tf_torso[i];
-    for (int i = 0; i < 14; ++i) o[22 + i] = tf_legs[i];
-    for (int i = 0; i < 8; ++i) o[36 + i] = tf_face[2 + i];
-  }
+  if (s_q.general || s_p.general || det)  // negative coordinates / per-part detail requested: the roomy variant
+    pose_decide_slow<T>(sq, db + p * (NJ * 2), und, query_is_model, &prm, match + p, score + p, det);
+  else
+    pose_decide<T, false, false>(sq, pr, und, s_q, s_p, query_is_model, prm, match + p, score + p, nullptr);
 }
 
 // ---- per-rank top-k of the matching poses ---------------------------------------------------------------
@@ -483,28 +551,69 @@ __device__ void block_topk(Get get, int64_t count, int k, float* out_s, int64_t*
   }
 }
 
+// One CTA = TK_TILE database entries held in registers (TK_PER per thread, entry = lo + r*TK_THREADS + tid, so a
+// thread's entries are in increasing index order); k rounds of block-wide lexicographic arg-min over the registers,
+// the winner's owner retires its entry.  One pass over match/score (5 B per pose), no re-reads.
+constexpr int TK_PER = 16;
+constexpr int TK_TILE = TK_THREADS * TK_PER;
+
 __global__ void __launch_bounds__(TK_THREADS)
 pose_topk_partial_kernel(const uint8_t* __restrict__ match, const float* __restrict__ score, int64_t n,
-                         int64_t index_offset, int k, int64_t per_block, float* __restrict__ part_s,
-                         int64_t* __restrict__ part_i, int32_t* __restrict__ match_count) {
+                         int64_t index_offset, int k, float* __restrict__ part_s, int64_t* __restrict__ part_i,
+                         int32_t* __restrict__ match_count) {
   __shared__ float red_s[TK_THREADS / 32];
-  __shared__ int64_t red_i[TK_THREADS / 32];
-  const int64_t lo = (int64_t)blockIdx.x * per_block;
-  const int64_t hi = min(n, lo + per_block);
+  __shared__ int red_r[TK_THREADS / 32];   // winner's slot: r * TK_THREADS + tid, or -1
+  const int64_t lo = (int64_t)blockIdx.x * TK_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float v[TK_PER];
   int cnt = 0;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += TK_THREADS) cnt += match[i] ? 1 : 0;
+#pragma unroll
+  for (int r = 0; r < TK_PER; ++r) {
+    const int64_t g = lo + (int64_t)r * TK_THREADS + tid;
+    float s = INFINITY;
+    if (g < n && match[g]) {
+      ++cnt;
+      const float x = score[g];
+      if (x == x) s = x;  // NaN scores never rank
+    }
+    v[r] = s;
+  }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(match_count, cnt);
-  auto get = [&](int64_t i, float& s, int64_t& id) {
-    const int64_t g = lo + i;
-    if (!match[g]) return false;
-    s = score[g];
-    if (s != s) return false;
-    id = g + index_offset;
-    return true;
-  };
-  block_topk(get, hi > lo ? hi - lo : 0, k, part_s + (int64_t)blockIdx.x * k, part_i + (int64_t)blockIdx.x * k, red_s,
-             red_i);
+  if (lane == 0 && cnt) atomicAdd(match_count, cnt);
+  float* out_s = part_s + (int64_t)blockIdx.x * k;
+  int64_t* out_i = part_i + (int64_t)blockIdx.x * k;
+  for (int round = 0; round < k; ++round) {
+    float bs = INFINITY;
+    int br = -1;
+#pragma unroll
+    for (int r = 0; r < TK_PER; ++r)
+      if (v[r] < bs) { bs = v[r]; br = r * TK_THREADS + tid; }   // strict: lowest index wins inside the thread
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+      if (orr >= 0 && (br < 0 || os < bs || (os == bs && orr < br))) { bs = os; br = orr; }
+    }
+    if (lane == 0) { red_s[warp] = bs; red_r[warp] = br; }
+    __syncthreads();
+    bs = red_s[0]; br = red_r[0];
+#pragma unroll
+    for (int w = 1; w < TK_THREADS / 32; ++w) {
+      const float os = red_s[w];
+      const int orr = red_r[w];
+      if (orr >= 0 && (br < 0 || os < bs || (os == bs && orr < br))) { bs = os; br = orr; }
+    }
+    __syncthreads();
+    if (br < 0) {  // ran out of candidates: pad the rest
+      for (int rr = round + tid; rr < k; rr += TK_THREADS) { out_s[rr] = INFINITY; out_i[rr] = -1; }
+      break;
+    }
+    if (tid == 0) { out_s[round] = bs; out_i[round] = lo + br + index_offset; }
+    if ((br % TK_THREADS) == tid) {
+      const int r = br / TK_THREADS;
+#pragma unroll
+      for (int q = 0; q < TK_PER; ++q) if (q == r) v[q] = INFINITY;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
@@ -522,9 +631,7 @@ pose_topk_final_kernel(const float* __restrict__ part_s, const int64_t* __restri
 }
 
 static int topk_blocks(int64_t n) {
-  int64_t b = (n + 65535) / 65536;
-  const int64_t cap = (int64_t)sm_count() * 4;
-  if (b > cap) b = cap;
+  int64_t b = (n + TK_TILE - 1) / TK_TILE;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -617,6 +724,7 @@ size_t hpusm_pose_topk_workspace_bytes(int64_t n, int k) {
 int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t index_offset, int k, float* top_score,
                     int64_t* top_index, int32_t* match_count, void* ws, size_t ws_bytes, void* stream) {
   HPUSM_REQUIRE(n >= 0 && k > 0 && k <= TK_MAXK, HPUSM_ERR_INVALID, "hpusm_pose_topk: k must be in 1..%d", TK_MAXK);
+  HPUSM_REQUIRE(n < ((int64_t)1 << 31) * TK_TILE, HPUSM_ERR_UNSUPPORTED, "hpusm_pose_topk: too many poses for one call");
   HPUSM_REQUIRE(top_score && top_index && match_count && (n == 0 || (match && score)), HPUSM_ERR_INVALID,
                 "hpusm_pose_topk: null pointer");
   cudaStream_t st = as_stream(stream);
@@ -627,9 +735,7 @@ int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t
   float* ps = reinterpret_cast<float*>(ws);
   int64_t* pi = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(ws) + align_up((size_t)b * k * sizeof(float), 256));
   HPUSM_CUDA_OK(cudaMemsetAsync(match_count, 0, sizeof(int32_t), st));
-  const int64_t per_block = (n + b - 1) / b;
-  HPUSM_LAUNCH(pose_topk_partial_kernel, b, TK_THREADS, 0, st, match, score, n, index_offset, k,
-               per_block > 0 ? per_block : 1, ps, pi, match_count);
+  HPUSM_LAUNCH(pose_topk_partial_kernel, b, TK_THREADS, 0, st, match, score, n, index_offset, k, ps, pi, match_count);
   HPUSM_CHECK_LAUNCH();
   HPUSM_LAUNCH(pose_topk_final_kernel, 1, TK_THREADS, 0, st, ps, pi, (int64_t)b * k, k, top_score, top_index);
   HPUSM_CHECK_LAUNCH();

@@ -223,7 +223,7 @@ __device__ int update_num_iters(double conf, double outlier_ratio, int max_iters
 //   B   lane = hypothesis (model in 9 registers), the pair's matches stream through as broadcast LDS.128; work items
 //       are (32 hypotheses) x (RS_SEG matches) so all warps stay busy; the count lives in a register
 //   C   sequential replay of RANSAC's early exit over the counts
-constexpr int RS_SEG = 512;
+constexpr int RS_SEG = 256;
 
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst,
