@@ -114,6 +114,99 @@ __global__ void perspective_transform_kernel(const float* __restrict__ pts, int6
   reinterpret_cast<float2*>(out)[i] = o;
 }
 
+// ---- per-image match lists for batched RANSAC (query vs image database) ----------------------------------------
+// pair_offsets[s] = sum over s' < s of (count[s'] >= min_count ? count[s'] : 0): single CTA, int64 running carry.
+__global__ void __launch_bounds__(1024)
+seg_offsets_kernel(const int32_t* __restrict__ count, int64_t nseg, int min_count, int64_t* __restrict__ offsets) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nseg; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    long long v = 0;
+    if (i < nseg) { const int c = count[i]; v = c >= min_count ? c : 0; }
+    long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      long long w = wsum[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      wsum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const long long incl = x + ((threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0) + carry;
+    if (i < nseg) offsets[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[nseg] = carry;
+}
+
+// One CTA per database image: order-preserving compaction of the query rows whose ratio test passed against this
+// image (best_idx >= 0) into src = query keypoint, dst = database keypoint.  Images below min_count emit nothing.
+__global__ void __launch_bounds__(256)
+seg_gather_kernel(const int32_t* __restrict__ best_idx, int64_t nq, const float* __restrict__ kp_q,
+                  const float* __restrict__ kp_t, const int64_t* __restrict__ offsets, float* __restrict__ src,
+                  float* __restrict__ dst, int32_t* __restrict__ sel) {
+  __shared__ int wsum[8];
+  __shared__ int carry;
+  const int64_t seg = blockIdx.x;
+  const int64_t o0 = offsets[seg];
+  if (offsets[seg + 1] == o0) return;
+  const int32_t* b = best_idx + seg * nq;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nq; base += 256) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t t = i < nq ? b[i] : -1;
+    const int k = t >= 0 ? 1 : 0;
+    int x = k;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+    const int pos = carry + woff + x - k;
+    if (k) {
+      reinterpret_cast<float2*>(src)[o0 + pos] = reinterpret_cast<const float2*>(kp_q)[i];
+      reinterpret_cast<float2*>(dst)[o0 + pos] = reinterpret_cast<const float2*>(kp_t)[t];
+      if (sel) sel[o0 + pos] = (int32_t)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry = pos + k;
+    __syncthreads();
+  }
+}
+
+// features.validate_homography (features.py:177-211) for a batch of 3x3 matrices; NaN (no model) -> invalid.
+__global__ void validate_homography_kernel(const double* __restrict__ H, int64_t n, uint8_t* __restrict__ valid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* h = H + i * 9;
+  bool ok = h[0] == h[0];
+  const double det = h[0] * h[4] - h[1] * h[3];
+  if (det < 0) ok = false;
+  const double n1 = sqrt(h[0] * h[0] + h[1] * h[1]);
+  if (n1 > 4 || n1 < 0.1) ok = false;
+  const double n2 = sqrt(h[3] * h[3] + h[4] * h[4]);
+  if (n2 > 4 || n2 < 0.1) ok = false;
+  const double n3 = sqrt(h[6] * h[6] + h[7] * h[7]);
+  if (n3 > 0.002) ok = false;
+  valid[i] = ok ? 1 : 0;
+}
+
 }  // namespace hpusm
 
 using namespace hpusm;
@@ -146,6 +239,34 @@ int hpusm_gather_matches(const float* kp_q, const float* kp_t, const int32_t* id
   HPUSM_CHECK_LAUNCH();
   HPUSM_LAUNCH(gm_scatter_kernel, (unsigned)nblocks, GM_THREADS, 0, st, kp_q, kp_t, idx, keep, nq, bc, p_q, p_t,
                sel);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_segment_matches(const int32_t* best_idx, const int32_t* count, int64_t nseg, int64_t nq, const float* kp_q,
+                          const float* kp_t, int min_count, int64_t* pair_offsets, float* src, float* dst, int32_t* sel,
+                          void* stream) {
+  HPUSM_REQUIRE(nseg >= 0 && nq >= 0, HPUSM_ERR_INVALID, "hpusm_segment_matches: negative size");
+  HPUSM_REQUIRE(pair_offsets, HPUSM_ERR_INVALID, "hpusm_segment_matches: null pair_offsets");
+  cudaStream_t st = as_stream(stream);
+  if (nseg == 0) {
+    HPUSM_CUDA_OK(cudaMemsetAsync(pair_offsets, 0, sizeof(int64_t), st));
+    return HPUSM_OK;
+  }
+  HPUSM_REQUIRE(best_idx && count && kp_q && kp_t && src && dst, HPUSM_ERR_INVALID, "hpusm_segment_matches: null pointer");
+  HPUSM_REQUIRE(nseg < 0x7fffffff, HPUSM_ERR_UNSUPPORTED, "hpusm_segment_matches: too many segments");
+  HPUSM_LAUNCH(seg_offsets_kernel, 1, 1024, 0, st, count, nseg, min_count, pair_offsets);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(seg_gather_kernel, (unsigned)nseg, 256, 0, st, best_idx, nq, kp_q, kp_t, pair_offsets, src, dst, sel);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_validate_homography_batch(const double* H, int64_t n, uint8_t* valid, void* stream) {
+  HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_validate_homography_batch: negative size");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(H && valid, HPUSM_ERR_INVALID, "hpusm_validate_homography_batch: null pointer");
+  HPUSM_LAUNCH(validate_homography_kernel, (unsigned)((n + 127) / 128), 128, 0, as_stream(stream), H, n, valid);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

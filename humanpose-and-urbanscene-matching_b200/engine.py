@@ -184,6 +184,36 @@ def gather_matches(kp_q, kp_t, idx, keep):
     return p_q, p_t, sel, count
 
 
+def segment_matches(best_idx, count, kp_q, kp_t, min_count=16):
+    """Per-image match lists after knn2_hamming_segmented(..., want_best_idx=True): (pair_offsets [nseg+1] i64,
+    src [total,2], dst [total,2], sel [total] i32); images below min_count (features.py:64) contribute nothing."""
+    best_idx = _cuda(best_idx, torch.int32, "best_idx")
+    count = _cuda(count, torch.int32, "count")
+    kp_q = _cuda(kp_q, torch.float32, "kp_q")
+    kp_t = _cuda(kp_t, torch.float32, "kp_t")
+    nseg, nq = best_idx.shape
+    dev = best_idx.device
+    with torch.cuda.device(dev):
+        offs = torch.empty((nseg + 1,), dtype=torch.int64, device=dev)
+        cap = int(count[count >= int(min_count)].sum().item())  # sizes the outputs (the only host read of the stage)
+        src = torch.empty((cap, 2), dtype=torch.float32, device=dev)
+        dst = torch.empty((cap, 2), dtype=torch.float32, device=dev)
+        sel = torch.empty((cap,), dtype=torch.int32, device=dev)
+        check(lib.hpusm_segment_matches(_ptr(best_idx), _ptr(count), nseg, nq, _ptr(kp_q), _ptr(kp_t), int(min_count),
+                                        _ptr(offs), _ptr(src), _ptr(dst), _ptr(sel), _stream(dev)))
+    return offs, src, dst, sel
+
+
+def validate_homography_batch(H):
+    """features.validate_homography (features.py:177-211) on [n,3,3] float64: valid [n] u8."""
+    H = _cuda(H, torch.float64, "H")
+    n = H.shape[0]
+    with torch.cuda.device(H.device):
+        valid = torch.empty((n,), dtype=torch.uint8, device=H.device)
+        check(lib.hpusm_validate_homography_batch(_ptr(H), n, _ptr(valid), _stream(H.device)))
+    return valid
+
+
 # ---- K3: RANSAC ----------------------------------------------------------------------------------------
 def ransac_homography_batch(src, dst, pair_offsets, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, refine=True):
     """cv2.findHomography(src, dst, RANSAC, thresh) per pair (features.py:66,:69).

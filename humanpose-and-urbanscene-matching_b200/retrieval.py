@@ -94,3 +94,20 @@ def pose_topk_sharded(query, db_shard, row_offset, k=16, match_fn=None, topk_fn=
     by_idx = torch.argsort(i, stable=True)
     order = by_idx[torch.argsort(s[by_idx], stable=True)][:k]
     return s[order], i[order], gc.sum()
+
+
+def scene_retrieval(query_desc, query_kp, db_desc, db_kp, seg_offsets, ratio=0.8, min_match=16, thresh=5.0, nhyp=2000,
+                    confidence=0.995, seed=0):
+    """One query image against an image database, the whole of features.match_and_draw + validate_homography per
+    database image (features.py:57-105,:177-211) without leaving the device: segmented Hamming kNN-2 + ratio ->
+    per-image match lists -> batched RANSAC in both directions -> homography sanity flags.
+
+    Returns a dict of device tensors, one entry per database image: n_matches, n_inliers, H (model->input, i.e.
+    query->image), H2 (image->query), valid, plus the match lists (pair_offsets, src, dst, mask)."""
+    score, best = engine.knn2_hamming_segmented(query_desc, db_desc, seg_offsets, ratio, want_best_idx=True)
+    offs, src, dst, sel = engine.segment_matches(best, score, query_kp, db_kp, min_match)
+    H, mask, ninl, _ = engine.ransac_homography_batch(src, dst, offs, thresh, nhyp, confidence, seed)
+    H2, _, _, _ = engine.ransac_homography_batch(dst, src, offs, thresh, nhyp, confidence, seed)
+    valid = engine.validate_homography_batch(H)
+    return {"n_matches": score, "n_inliers": ninl, "H": H, "H2": H2, "valid": valid, "pair_offsets": offs, "src": src,
+            "dst": dst, "mask": mask, "sel": sel}

@@ -125,6 +125,20 @@ int hpusm_gather_matches(const float* kp_q, const float* kp_t, const int32_t* id
                          int64_t nq, float* p_q, float* p_t, int32_t* sel, int32_t* count, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* Per-image match lists for batched RANSAC after a segmented retrieval pass (the loop of
+ * dataset/dataset_urbanscene.py:46-84 over features.match_and_draw, features.py:59-64):
+ *   best_idx [nseg][nq] and count [nseg] as written by hpusm_knn2_hamming_segmented; kp_q [nq][2], kp_t [nt][2] keypoints.
+ *   Images with fewer than min_count survivors (thresholds.MIN_MATCH_COUNT = 16, features.py:64) contribute no matches.
+ *   pair_offsets [nseg+1] int64 (device) receives the scan; src/dst must hold sum(count) rows (<= nseg*nq);
+ *   src = query keypoint, dst = database keypoint of each surviving match in increasing query order; sel (optional)
+ *   the query row.  Feeds hpusm_ransac_homography_batch directly. */
+int hpusm_segment_matches(const int32_t* best_idx, const int32_t* count, int64_t nseg, int64_t nq, const float* kp_q,
+                          const float* kp_t, int min_count, int64_t* pair_offsets, float* src, float* dst, int32_t* sel,
+                          void* stream);
+
+/* features.validate_homography (features.py:177-211) on a batch: H [n][9] float64 -> valid [n] uint8 (NaN = no model = 0). */
+int hpusm_validate_homography_batch(const double* H, int64_t n, uint8_t* valid, void* stream);
+
 /* --------------------------------------------------------------------------------------------------
  * K3  Batched RANSAC homography.
  * Replaces cv2.findHomography(src, dst, cv2.RANSAC, thresh) (features.py:66 and :69), batched over

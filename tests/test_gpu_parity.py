@@ -310,3 +310,60 @@ def test_pose_topk(hpusm, cuda_device):
     np.testing.assert_array_equal(ti.cpu().numpy(), order + 1000)
     np.testing.assert_array_equal(ts.cpu().numpy(), score[order])
     assert int(cnt.item()) == int(match.sum())
+
+
+# ---- fused post-match stage ---------------------------------------------------------------------
+def _scene_database(hpusm, nimg=14, per=400, nq=500, seed=21):
+    """A query image (descriptors + keypoints) and a database in which some images show the query scene under a
+    homography (descriptors perturbed by a few bit flips, keypoints moved by H + noise)."""
+    rng = np.random.default_rng(seed)
+    q_desc = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    q_kp = np.stack([rng.uniform(0, 640, nq), rng.uniform(0, 480, nq)], 1).astype(np.float32)
+    sizes = rng.integers(per // 2, per + 1, nimg)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    db_desc = rng.integers(0, 256, (int(offs[-1]), 32), dtype=np.uint8)
+    db_kp = np.stack([rng.uniform(0, 640, offs[-1]), rng.uniform(0, 480, offs[-1])], 1).astype(np.float32)
+    planted = [2, 5, 11]
+    for n_shared, im in zip((120, 40, 10), planted):  # the last one stays below MIN_MATCH_COUNT
+        H = hpusm.synth.random_homography(rng)
+        rows = rng.choice(int(sizes[im]), n_shared, replace=False) + offs[im]
+        src = rng.choice(nq, n_shared, replace=False)
+        bits = np.unpackbits(q_desc[src], axis=1)
+        flip = rng.random(bits.shape) < 0.03
+        db_desc[rows] = np.packbits(bits ^ flip.astype(np.uint8), axis=1)
+        p = np.c_[q_kp[src], np.ones(n_shared)] @ H.T
+        db_kp[rows] = (p[:, :2] / p[:, 2:] + rng.normal(0, 0.5, (n_shared, 2))).astype(np.float32)
+    return q_desc, q_kp, db_desc, db_kp, offs, planted
+
+
+def test_scene_retrieval_fused_stage(hpusm, cuda_device):
+    q_desc, q_kp, db_desc, db_kp, offs, planted = _scene_database(hpusm)
+    out = hpusm.retrieval.scene_retrieval(dev(q_desc, cuda_device), dev(q_kp, cuda_device), dev(db_desc, cuda_device),
+                                          dev(db_kp, cuda_device), dev(offs, cuda_device), nhyp=500, seed=5)
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    # oracle: the reference's per-image loop (match_and_draw + validate_homography) with the shared sample seed
+    nimg = len(offs) - 1
+    srcs, dsts, poffs = [], [], [0]
+    for s in range(nimg):
+        lo, hi = offs[s], offs[s + 1]
+        i2, d2 = knn_oracle.knn2_hamming(q_desc, db_desc[lo:hi])
+        p1, p2, sel = knn_oracle.filter_matches_points(q_kp, db_kp[lo:hi], i2, d2, 0.8)
+        assert got["n_matches"][s] == len(sel)
+        if len(sel) >= 16:
+            srcs.append(p1.reshape(-1, 2)); dsts.append(p2.reshape(-1, 2))
+        poffs.append(poffs[-1] + (len(sel) if len(sel) >= 16 else 0))
+    src, dst = np.concatenate(srcs), np.concatenate(dsts)
+    np.testing.assert_array_equal(got["pair_offsets"], np.array(poffs))
+    np.testing.assert_array_equal(got["src"], src)
+    np.testing.assert_array_equal(got["dst"], dst)
+    rH, rmask, rninl, _ = ransac_oracle.homography_batch(src, dst, poffs, 5.0, 500, 0.995, 5)
+    rH2, _, _, _ = ransac_oracle.homography_batch(dst, src, poffs, 5.0, 500, 0.995, 5)
+    np.testing.assert_array_equal(got["mask"], rmask)
+    np.testing.assert_array_equal(got["n_inliers"], rninl)
+    np.testing.assert_allclose(got["H"], rH, rtol=1e-6, atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(got["H2"], rH2, rtol=1e-6, atol=1e-6, equal_nan=True)
+    # the two well-supported planted images come out as valid homographies, the others (incl. the one below
+    # MIN_MATCH_COUNT) do not
+    assert got["valid"][planted[0]] == 1 and got["valid"][planted[1]] == 1
+    assert got["n_inliers"][planted[0]] >= 100 and got["n_inliers"][planted[2]] == 0
+    assert np.isnan(got["H"][planted[2]]).all()
