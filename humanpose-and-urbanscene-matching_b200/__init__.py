@@ -27,6 +27,7 @@ from .engine import (  # noqa: F401
     affine_lsq_batch,
     procrustes_batch,
     pose_match_batch,
+    pose_match_pairs,
     pose_topk,
     launch_count,
 )
@@ -34,5 +35,5 @@ from .engine import (  # noqa: F401
 __all__ = [
     "knn2_hamming", "knn2_hamming_segmented", "knn2_l2", "ratio_filter", "gather_matches",
     "ransac_homography_batch", "ransac_score_batch", "perspective_transform", "affine_lsq_batch",
-    "procrustes_batch", "pose_match_batch", "pose_topk", "launch_count",
+    "procrustes_batch", "pose_match_batch", "pose_match_pairs", "pose_topk", "launch_count",
 ]

@@ -509,6 +509,33 @@ pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, i
     pose_decide<T, false, false>(sq, pr, und, s_q, s_p, query_is_model, prm, match + p, score + p, nullptr);
 }
 
+// Arbitrary (model, input) pose pairs in one launch: the candidate stage of multi_person.match
+// (multi_person.py:169-207 calls match_single for every model person x input person).
+template <typename T>
+__global__ void __launch_bounds__(PM_THREADS)
+pose_match_pairs_kernel(const T* __restrict__ model, const T* __restrict__ input, int64_t n, PoseParams prm,
+                        uint8_t* __restrict__ match, float* __restrict__ score, double* __restrict__ detail) {
+  const int64_t p = (int64_t)blockIdx.x * PM_THREADS + threadIdx.x;
+  if (p >= n) return;
+  T mo[NJ * 2], pr[NJ * 2];
+  load_pose<T>(model + p * (NJ * 2), mo);
+  load_pose<T>(input + p * (NJ * 2), pr);
+  unsigned und = 0;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+    if ((mo[2 * j] == T(0) && mo[2 * j + 1] == T(0)) || (pr[2 * j] == T(0) && pr[2 * j + 1] == T(0))) und |= 1u << j;
+  const Scale<T> s_q = make_scale<T>([&](int i) { return mo[i]; }, und);
+  const Scale<T> s_p = make_scale<T>([&](int i) { return pr[i]; }, und);
+  double* det = detail ? detail + p * HPUSM_POSE_DETAIL : nullptr;
+  if (s_q.general || s_p.general) {
+    if (det) pose_decide<T, true, true>(mo, pr, und, s_q, s_p, 1, prm, match + p, score + p, det);
+    else pose_decide<T, true, false>(mo, pr, und, s_q, s_p, 1, prm, match + p, score + p, nullptr);
+  } else {
+    if (det) pose_decide<T, false, true>(mo, pr, und, s_q, s_p, 1, prm, match + p, score + p, det);
+    else pose_decide<T, false, false>(mo, pr, und, s_q, s_p, 1, prm, match + p, score + p, nullptr);
+  }
+}
+
 // ---- per-rank top-k of the matching poses ---------------------------------------------------------------
 constexpr int TK_THREADS = 256;
 constexpr int TK_MAXK = 64;
@@ -703,6 +730,26 @@ int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n,
   pose_params(thresholds, prm);
   HPUSM_LAUNCH_TIMED(pose_match_batch_kernel<double>, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
                      as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_pose_match_pairs(const void* model, const void* input, int64_t n, int is_f64, const double* thresholds,
+                           uint8_t* match, float* score, double* detail, void* stream) {
+  HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_pose_match_pairs: negative size");
+  if (n == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(model && input && thresholds && match && score, HPUSM_ERR_INVALID, "hpusm_pose_match_pairs: null pointer");
+  HPUSM_REQUIRE(is_aligned(model, 16) && is_aligned(input, 16), HPUSM_ERR_INVALID,
+                "hpusm_pose_match_pairs: pose arrays must be 16-byte aligned");
+  PoseParams prm;
+  pose_params(thresholds, prm);
+  const unsigned grid = (unsigned)((n + PM_THREADS - 1) / PM_THREADS);
+  if (is_f64)
+    HPUSM_LAUNCH(pose_match_pairs_kernel<double>, grid, PM_THREADS, 0, as_stream(stream), reinterpret_cast<const double*>(model),
+                 reinterpret_cast<const double*>(input), n, prm, match, score, detail);
+  else
+    HPUSM_LAUNCH(pose_match_pairs_kernel<float>, grid, PM_THREADS, 0, as_stream(stream), reinterpret_cast<const float*>(model),
+                 reinterpret_cast<const float*>(input), n, prm, match, score, detail);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

@@ -320,6 +320,27 @@ def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THR
     return (match, score, detail) if want_detail else (match, score)
 
 
+def pose_match_pairs(model, inp, thresholds=DEFAULT_POSE_THRESHOLDS, want_detail=False):
+    """match_single(model[i], input[i]) for n arbitrary pairs in one launch (multi_person.py:169-207 candidate stage).
+    model, inp [n,18,2] float32 or float64.  Returns (match [n] u8, score [n] f32[, detail [n, POSE_DETAIL] f64])."""
+    f64 = inp.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    model = _cuda(model, dt, "model")
+    inp = _cuda(inp, dt, "input")
+    if model.shape != inp.shape or inp.dim() != 3 or inp.shape[1:] != (18, 2):
+        raise ValueError("model and input must both be [n,18,2]")
+    n = inp.shape[0]
+    dev = inp.device
+    thr = (ctypes.c_double * 5)(*[float(x) for x in thresholds])
+    with torch.cuda.device(dev):
+        match = torch.empty((n,), dtype=torch.uint8, device=dev)
+        score = torch.empty((n,), dtype=torch.float32, device=dev)
+        detail = torch.empty((n, POSE_DETAIL), dtype=torch.float64, device=dev) if want_detail else None
+        check(lib.hpusm_pose_match_pairs(_ptr(model), _ptr(inp), n, 1 if f64 else 0, ctypes.cast(thr, ctypes.c_void_p),
+                                         _ptr(match), _ptr(score), _ptr(detail), _stream(dev)))
+    return (match, score, detail) if want_detail else (match, score)
+
+
 def feature_scaling_batch(pts):
     """common.feature_scaling on [n, npts, 2] float64 point sets (common.py:688-708)."""
     pts = _cuda(pts, torch.float64, "pts")

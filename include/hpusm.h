@@ -216,6 +216,12 @@ int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n,
                                const double* thresholds, uint8_t* match, float* score, double* detail,
                                void* stream);
 
+/* Arbitrary pose pairs in one launch: pair i = match_single(model[i], input[i]).  This is the candidate stage of
+ * posematching/multi_person.py:169-207 (every model person x every input person).  model, input [n][18][2] float32
+ * (is_f64 == 0) or float64; outputs as hpusm_pose_match_batch. */
+int hpusm_pose_match_pairs(const void* model, const void* input, int64_t n, int is_f64, const double* thresholds,
+                           uint8_t* match, float* score, double* detail, void* stream);
+
 /* Batched min/max normalisation, replaces common.feature_scaling (common.py:688-708) including its quirk that
  * each minimum runs over BOTH coordinates of the rows whose x (resp. y) is non-zero; negatives clamp to 0.
  *   pts, out [n][npts][2] float64. */

@@ -235,10 +235,47 @@ def record_pose():
     save("pose_decide.npz", rows=np.stack(rows))
 
 
+def record_multi_person():
+    """multi_person.find_ordered_matches (multi_person.py:169) on the multi-person fixtures."""
+    import posematching.multi_person as ref_mp
+    groups = []
+    for f in sorted(glob.glob(os.path.join(REF, "json_data", "*.json"))):
+        try:
+            people = [p for p in ref_common.parse_JSON_multi_person(f) if p.shape == (18, 2)]
+        except Exception:
+            continue
+        if 2 <= len(people) <= 8 and all(((p != 0).any(1)).sum() >= 8 for p in people):
+            groups.append(np.stack(people))
+    rng = np.random.default_rng(40)
+    cases = []
+    for k in range(40):
+        a, b = groups[rng.integers(len(groups))], groups[rng.integers(len(groups))]
+        if k % 3 == 0:
+            b = a + rng.normal(0, 3.0, a.shape) * (a != 0)  # same scene, jittered: guaranteed candidates
+        try:
+            md, mo, ip = ref_mp.find_ordered_matches(list(a), list(b))
+        except Exception:
+            continue
+        cases.append((a, b, md, mo, ip))
+    P = 8
+    A = np.zeros((len(cases), P, 18, 2)); B = np.zeros((len(cases), P, 18, 2))
+    na = np.zeros(len(cases), np.int32); nb = np.zeros(len(cases), np.int32)
+    found = np.zeros(len(cases), np.int8)
+    table = -np.ones((len(cases), P, P), np.int32)   # table[c, model, :] = matching input indices, -1 padded
+    n_model = np.zeros(len(cases), np.int32)
+    for c, (a, b, md, mo, ip) in enumerate(cases):
+        A[c, :len(a)], B[c, :len(b)], na[c], nb[c] = a, b, len(a), len(b)
+        if md is not None:
+            found[c], n_model[c] = 1, len(mo)
+            for m, lst in md.items():
+                table[c, m, :len(lst)] = lst
+    save("pose_multi_person.npz", A=A, B=B, na=na, nb=nb, found=found, table=table, n_model=n_model)
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
-               record_pose):
+               record_pose, record_multi_person):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

@@ -135,3 +135,36 @@ def test_transformation_functions(mods):
     s = tr.affine_multi(model_bg, input_bg, model_pose, input_pose, 480, 640, 480, 640, "x", None, None, None,
                         rng=random.Random(3))
     assert s < 1e-9  # an exact affine relation is recovered exactly
+
+
+def test_multi_person_candidate_stage(cuda_device):
+    """multi_person.find_ordered_matches (multi_person.py:169-207): same candidate lists as the reference, from ONE
+    launch over all (model person, input person) pairs."""
+    mp = importlib.import_module(DROPIN + ".posematching.multi_person")
+    g = load_golden("pose_multi_person.npz")
+    n_found = 0
+    for c in range(len(g["found"])):
+        a = [p for p in g["A"][c][:g["na"][c]]]
+        b = [p for p in g["B"][c][:g["nb"][c]]]
+        md, mo, ip = mp.find_ordered_matches(a, b)
+        if not g["found"][c]:
+            assert md is None
+            continue
+        n_found += 1
+        assert md is not None and len(mo) == g["n_model"][c]
+        for m in range(len(mo)):
+            ref = [int(x) for x in g["table"][c, m] if x >= 0]
+            assert md[m] == ref, (c, m)
+    assert n_found >= 10
+
+
+def test_pose_match_pairs_equals_batch(hpusm, cuda_device):
+    import torch
+    g = load_golden("pose_match_single.npz")
+    M, I = torch.from_numpy(g["model"]).to(cuda_device), torch.from_numpy(g["input"]).to(cuda_device)
+    match, score = hpusm.pose_match_pairs(M, I)
+    match, score = match.cpu().numpy(), score.cpu().numpy()
+    ok = (g["match"] >= 0) & np.isfinite(g["score"])
+    np.testing.assert_array_equal(match[ok].astype(bool), g["match"][ok].astype(bool))
+    np.testing.assert_allclose(score[ok], g["score"][ok], rtol=1e-6, atol=1e-7)
+    assert (match[g["match"] < 0] == 0).all()
