@@ -48,6 +48,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key, {}).get("bytes")
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -298,7 +306,7 @@ def run_ours(args, rank, world, device):
                 "d2h_bytes_per_step": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel())},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%dx%d" % (nq, nt)),
                      "kernel_ms": k_ms, "kernel_launches": int(kernel_n),
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"},
         "clocks": clocks,
@@ -362,15 +370,15 @@ def base_line(args, world, metric, unit, value, ms, dtype, scaling, config):
             "data": "synthetic", "config": config}
 
 
-def popc_peak(hp, device):
-    """Measured POPC.32 issue rate of this GPU (thread-instructions / s): the Hamming roofline denominator."""
+def popc_peak(hp, device, op="popc"):
+    """Measured POPC.32 / LOP3 issue rate of this GPU (thread-instructions / s): the Hamming roofline denominators."""
     eng = hp.engine
     blocks, threads, iters = 148 * 16, 256, 1 << 16
-    eng.microbench_popc(blocks, threads, iters, device)
+    eng.microbench_popc(blocks, threads, iters, device, op)
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    eng.microbench_popc(blocks, threads, iters, device)
+    eng.microbench_popc(blocks, threads, iters, device, op)
     e1.record()
     torch.cuda.synchronize(device)
     return blocks * threads * float(iters) / (e0.elapsed_time(e1) * 1e-3)
@@ -413,10 +421,13 @@ def run_orb(args, rank, world, device, hp):
         return None
     pairs = float(per) * args.images * per
     top = torch.topk(scores, min(len(planted) * world, 16)).indices.tolist()
-    ppeak = popc_peak(hp, device)
+    ppeak, lpeak = popc_peak(hp, device, "popc"), popc_peak(hp, device, "lop3")
     k_ms = r["kernel_ms"] / max(r["kernel_n"], 1)
-    popc_per_launch = 8.0 * per * (b - a) * per * args.steps / max(r["kernel_n"], 1)
-    ach = popc_per_launch / (k_ms * 1e-3)
+    pairs_per_launch = float(per) * (b - a) * per * args.steps / max(r["kernel_n"], 1)
+    # per 256-bit pair the kernel issues 16 LOP3 (8 XOR + 4 carry-save adders) on the ALU pipe and 4 POPC on the XU pipe;
+    # the two pipes run side by side, so the bound is the slower of the two
+    t_bound = max(16.0 * pairs_per_launch / lpeak, 4.0 * pairs_per_launch / ppeak)
+    ach = 16.0 * pairs_per_launch / (k_ms * 1e-3)
     out = base_line(args, world, "descriptor-pairs/sec (kNN+ratio)", "pairs/s", pairs * args.steps / (r["ms"] * 1e-3), r["ms"], "u32 popc",
                     "strong", {"workload": "synthetic ORB 256-bit Hamming, 10k-image database retrieval sharded across 2/4/8 B200",
                                "images": args.images, "descriptors_per_image": per, "query_descriptors": per, "ratio": 0.8,
@@ -425,9 +436,10 @@ def run_orb(args, rank, world, device, hp):
     out["e2e"] = {"value": pairs * args.steps / (e["ms"] * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(hq.numel() + hdb.numel()),
                   "d2h_bytes_per_step": int(hs.numel() * 4)}
     out["gpu_launches"] = int(r["launches"])
-    out["roofline"] = {"bound": "integer pipe (POPC.32, 8 per pair)", "achieved": ach / 1e12, "peak": ppeak / 1e12, "unit": "Tpopc/s",
-                       "frac": ach / ppeak, "traffic": None, "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
-                       "peak_source": "hpusm_microbench_popc measured in this run",
+    out["roofline"] = {"bound": "integer pipes (16 LOP3 + 4 POPC.32 per pair)", "achieved": ach / 1e12, "peak": lpeak / 1e12, "unit": "Tlop3/s",
+                       "frac": t_bound / (k_ms * 1e-3), "traffic": None, "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
+                       "peak_source": "hpusm_microbench_lop3 / hpusm_microbench_popc measured in this run",
+                       "popc_peak_Tpopc": ppeak / 1e12, "naive_popc_bound_ms": 8.0 * pairs_per_launch / ppeak * 1e3,
                        "hbm_GBps_algorithmic": (db.numel() + query.numel()) / (k_ms * 1e-3) / 1e9}
     out["clocks"] = r["clocks"]
     if not args.no_cpu_baseline and world == 1:

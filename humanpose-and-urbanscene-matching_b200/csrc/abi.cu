@@ -65,6 +65,25 @@ __global__ void popc_microbench_kernel(int64_t iters, uint32_t* sink) {
   if (r == 0xffffffffu) sink[0] = r;  // never true in practice; keeps the chains alive
 }
 
+// Same for LOP3 (ALU pipe): 8 independent chains of majority/xor3 operations.
+__global__ void lop3_microbench_kernel(int64_t iters, uint32_t* sink) {
+  uint32_t a0 = threadIdx.x * 2654435761u + blockIdx.x, a1 = a0 ^ 0x9e3779b9u, a2 = a0 + 0x7f4a7c15u, a3 = ~a0,
+           a4 = a0 * 3u, a5 = a1 * 5u, a6 = a2 * 7u, a7 = a3 * 11u;
+  const uint32_t k0 = a0 * 13u + 1u, k1 = a1 * 17u + 3u;
+  for (int64_t i = 0; i < iters; i += 8) {
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a0) : "r"(k0), "r"(k1));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a1) : "r"(k0), "r"(k1));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a2) : "r"(k1), "r"(k0));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a3) : "r"(k1), "r"(k0));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a4) : "r"(k0), "r"(k1));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a5) : "r"(k0), "r"(k1));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a6) : "r"(k1), "r"(k0));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a7) : "r"(k1), "r"(k0));
+  }
+  const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  if (r == 0xffffffffu && k0 == 7u) sink[0] = r;
+}
+
 }  // namespace hpusm
 
 using namespace hpusm;
@@ -121,6 +140,14 @@ int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* 
   HPUSM_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,
                 "hpusm_microbench_popc: bad arguments");
   HPUSM_LAUNCH(popc_microbench_kernel, (unsigned)blocks, threads, 0, as_stream(stream), iters, sink);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream) {
+  HPUSM_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,
+                "hpusm_microbench_lop3: bad arguments");
+  HPUSM_LAUNCH(lop3_microbench_kernel, (unsigned)blocks, threads, 0, as_stream(stream), iters, sink);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

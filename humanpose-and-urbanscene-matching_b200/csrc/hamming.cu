@@ -32,11 +32,26 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // sum + carry, one LOP3 each) fold the eight XOR words into ones {o3, x7}, twos {tw} and fours {f}.  POPC issues at
 // 16 lanes/clk/SM, LOP3 at 64: 8 XOR + 8 LOP3 + 4 POPC balances the two pipes (0.25 cycles per pair on each) where the
 // plain form is POPC-bound at 0.5.  Exact: d = popc(o3) + popc(x7) + 2 popc(tw) + 4 popc(f).
-__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
+// (inline PTX: left to itself ptxas folds the XORs into the adders and rematerialises them, ~25 LOP3 per pair
+// instead of 16, which makes the ALU pipe the new bound)
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t xor2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ int hamming256(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {
-  const uint32_t x0 = a[0] ^ b[0], x1 = a[1] ^ b[1], x2 = a[2] ^ b[2], x3 = a[3] ^ b[3];
-  const uint32_t x4 = a[4] ^ b[4], x5 = a[5] ^ b[5], x6 = a[6] ^ b[6], x7 = a[7] ^ b[7];
+  const uint32_t x0 = xor2(a[0], b[0]), x1 = xor2(a[1], b[1]), x2 = xor2(a[2], b[2]), x3 = xor2(a[3], b[3]);
+  const uint32_t x4 = xor2(a[4], b[4]), x5 = xor2(a[5], b[5]), x6 = xor2(a[6], b[6]), x7 = xor2(a[7], b[7]);
   const uint32_t o1 = xor3(x0, x1, x2), t1 = maj3(x0, x1, x2);
   const uint32_t o2 = xor3(x3, x4, x5), t2 = maj3(x3, x4, x5);
   const uint32_t o3 = xor3(o1, o2, x6), t3 = maj3(o1, o2, x6);

@@ -367,7 +367,8 @@ def pose_topk(match, score, k=16, index_offset=0):
     return ts, ti, cnt
 
 
-def microbench_popc(blocks, threads, iters, device):
+def microbench_popc(blocks, threads, iters, device, op="popc"):
     sink = torch.zeros((1,), dtype=torch.int32, device=device)
+    fn = lib.hpusm_microbench_popc if op == "popc" else lib.hpusm_microbench_lop3
     with torch.cuda.device(device):
-        check(lib.hpusm_microbench_popc(int(blocks), int(threads), int(iters), _ptr(sink), _stream(device)))
+        check(fn(int(blocks), int(threads), int(iters), _ptr(sink), _stream(device)))

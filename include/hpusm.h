@@ -235,9 +235,11 @@ int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t
                     float* top_score, int64_t* top_index, int32_t* match_count, void* ws,
                     size_t ws_bytes, void* stream);
 
-/* Integer-pipe micro-benchmark: every thread issues `iters` dependent-free POPC.32; returns nothing
- * useful in `sink`.  bench.py uses it as the measured denominator of the Hamming roofline. */
+/* Integer-pipe micro-benchmarks: every thread issues `iters` POPC.32 (resp. LOP3) in 8 independent chains; returns
+ * nothing useful in `sink`.  bench.py uses them as the measured denominators of the Hamming roofline. */
 int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
+/* Same for LOP3 on the ALU pipe (the Hamming kernel issues 16 LOP3 + 4 POPC per 256-bit pair). */
+int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
 
 #ifdef __cplusplus
 }
