@@ -235,6 +235,24 @@ def record_pose():
     save("pose_decide.npz", rows=np.stack(rows))
 
 
+def record_json_parser():
+    """common.parse_JSON_multi_person (common.py:215-239) on a few fixture files: raw keypoint triples in, poses out."""
+    raws, outs, counts = [], [], []
+    for name in ("duo1.json", "trio1.json", "foto3.json", "1027.json", "emma1.json", "taj3.json"):
+        f = os.path.join(REF, "json_data", name)
+        if not os.path.exists(f):
+            continue
+        people = json.load(open(f))["people"]
+        ref = ref_common.parse_JSON_multi_person(f)
+        raw = np.zeros((8, 54)); out = np.zeros((8, 18, 2))
+        n = min(len(people), 8)
+        for k in range(n):
+            raw[k] = people[k]["pose_keypoints"]
+            out[k] = ref[k]
+        raws.append(raw); outs.append(out); counts.append(n)
+    save("pose_json_parser.npz", raw=np.stack(raws), poses=np.stack(outs), n=np.array(counts))
+
+
 def record_multi_person():
     """multi_person.find_ordered_matches (multi_person.py:169) on the multi-person fixtures."""
     import posematching.multi_person as ref_mp
@@ -275,7 +293,7 @@ def record_multi_person():
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
-               record_pose, record_multi_person):
+               record_pose, record_multi_person, record_json_parser):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

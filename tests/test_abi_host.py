@@ -73,3 +73,27 @@ def test_synth_generators_are_seeded(hpusm):
     assert offs[0] == 0 and offs[-1] == len(db) and len(offs) == 21
     P = hpusm.synth.pose_database(hpusm.synth.CANONICAL_POSE, 100, seed=2)
     assert P.shape == (100, 18, 2) and P.dtype == np.float32
+
+
+def test_openpose_json_parser_and_packed_db(hpusm, tmp_path):
+    """posedb.parse_openpose_json == common.parse_JSON_multi_person (common.py:215-239) on keypoint triples recorded
+    from the reference's fixtures; pack() / PoseDB round trip."""
+    import json
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pose_json_parser.npz"))
+    paths = []
+    for fi in range(len(g["n"])):
+        n = int(g["n"][fi])
+        doc = {"version": 1.0, "people": [{"pose_keypoints": g["raw"][fi, k].tolist(), "face_keypoints": []} for k in range(n)]}
+        p = tmp_path / ("img%d_keypoints.json" % fi)
+        p.write_text(json.dumps(doc))
+        paths.append(str(p))
+        got = hpusm.posedb.parse_openpose_json(str(p))
+        assert len(got) == n
+        for k in range(n):
+            np.testing.assert_array_equal(got[k], g["poses"][fi, k])
+    out = str(tmp_path / "db.hpusm")
+    total = hpusm.posedb.pack(paths, out)
+    db = hpusm.posedb.PoseDB(out)
+    assert len(db) == total == int(g["n"].sum()) and db.n_files == len(paths) and db.names[0] == "img0_keypoints.json"
+    np.testing.assert_array_equal(db.poses[0], g["poses"][0, 0].astype(np.float32))
+    assert db.file_index[-1] == len(paths) - 1 and db.person_index[0] == 0

@@ -367,3 +367,18 @@ def test_scene_retrieval_fused_stage(hpusm, cuda_device):
     assert got["valid"][planted[0]] == 1 and got["valid"][planted[1]] == 1
     assert got["n_inliers"][planted[0]] >= 100 and got["n_inliers"][planted[2]] == 0
     assert np.isnan(got["H"][planted[2]]).all()
+
+
+def test_posedb_streaming_search(hpusm, cuda_device, tmp_path):
+    """Packed pose database streamed from disk in chunks (copy stream + two pinned buffers) == one resident pass."""
+    db = hpusm.synth.pose_database(hpusm.synth.CANONICAL_POSE, 50000, seed=9)
+    path = str(tmp_path / "poses.hpusm")
+    assert hpusm.posedb.pack_array(db, path) == len(db)
+    pdb = hpusm.posedb.PoseDB(path)
+    q = hpusm.synth.CANONICAL_POSE.astype(np.float32)
+    s, i, total = pdb.search(q, k=16, device=cuda_device, chunk=7001)  # 8 ragged chunks
+    match, score = hpusm.pose_match_batch(dev(q, cuda_device), dev(db, cuda_device))
+    ts, ti, cnt = hpusm.pose_topk(match, score, k=16)
+    np.testing.assert_array_equal(i, ti.cpu().numpy())
+    np.testing.assert_array_equal(s, ts.cpu().numpy())
+    assert total == int(cnt.item()) == int(match.sum().item())
