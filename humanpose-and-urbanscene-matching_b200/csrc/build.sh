@@ -10,7 +10,7 @@ OBJS=()
 for f in *.cu; do
   o="build/${f%.cu}.o"
   mkdir -p build
-  if [[ ! -f "$o" || "$f" -nt "$o" || common.cuh -nt "$o" || ../../include/hpusm.h -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$f" -nt "$o" || common.cuh -nt "$o" || tc_ptx.cuh -nt "$o" || l2_internal.cuh -nt "$o" || ../../include/hpusm.h -nt "$o" ]]; then
     echo "nvcc $f"
     "$NVCC" "${FLAGS[@]}" ${HPUSM_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
   fi

@@ -19,4 +19,9 @@ size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode);
 int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist,
                void* ws, size_t ws_bytes, cudaStream_t st, int* resolved_mode, int64_t* fallback_rows);
 
+// l2_tc_split.cu (tcgen05 engine for general float descriptors: hi/lo bf16 split, top-4 candidates, verified re-rank)
+size_t l2_tc_split_workspace_bytes(int64_t nq, int64_t nt);
+int l2_tc_split_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_t* idx, float* dist, void* ws,
+                     size_t ws_bytes, cudaStream_t st, int64_t* fallback_rows);
+
 }  // namespace hpusm

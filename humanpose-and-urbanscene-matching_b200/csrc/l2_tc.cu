@@ -11,10 +11,10 @@
 // OpenCV SIFT descriptors are integer valued (0..255) stored as float32, so bf16 operands are exact and
 // the FP32 accumulation (every partial sum is an integer of magnitude <= 2^24) is exact: s is the exact integer, the
 // fused top-2 on (s, index) is the exact answer, and ties fall to the lower index exactly as OpenCV resolves them.  The
-// prep kernel verifies that property for every value; when it does not hold the kernel is skipped on the
-// device (no host round trip) and the FP32 CUDA-core engine produces the candidates instead.  Either way the
-// candidates go through l2_rerank_finalize (l2_simt.cu): exact FP32 distances from the ORIGINAL float32
-// rows, lexicographic (d2, index) top-2, sqrtf -- the numbers DMatch.distance carries.
+// prep kernel verifies that property for every value; when it does not hold HPUSM_L2_AUTO hands the call to the
+// split-operand engine (l2_tc_split.cu) after one 4-byte host read.  The candidates go through l2_rerank_finalize
+// (l2_simt.cu): exact FP32 distances from the ORIGINAL float32 rows, lexicographic (d2, index) top-2, sqrtf -- the
+// numbers DMatch.distance carries.
 //
 // Kernel shape (one persistent CTA per SM, 384 threads, warp specialised):
 //   warp 0     TMA producer: the unit's 256 queries (2 x [128 x 144] bf16, 72 KB, loaded once per unit) and a 4-stage
@@ -33,6 +33,7 @@
 #include <float.h>
 #include "common.cuh"
 #include "l2_internal.cuh"
+#include "tc_ptx.cuh"
 
 namespace hpusm {
 
@@ -49,74 +50,6 @@ constexpr int TC_A_BYTES = 2 * TC_TILE_BYTES;               // two query tiles
 constexpr int TC_B_BYTES = TC_TILE_BYTES;                   // per stage
 constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows 128 B apart inside an 8-row group,
-// 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1 (Blackwell), layout type 2.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// Same for the 16 augmentation columns: SWIZZLE_32B, rows 32 B apart, 8-row groups 256 B apart, layout type 6.
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
-}
 // Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TN >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -375,12 +308,12 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows][144] bf16 row-major; box = `box_cols` columns x 128 rows with the given swizzle; out-of-range rows read as 0
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int box_cols, CUtensorMapSwizzle swizzle) {
+// [rows][cols] bf16 row-major; box = `box_cols` columns x 128 rows with the given swizzle; out-of-range rows read as 0
+int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_cols, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   HPUSM_REQUIRE(fn, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t dims[2] = {(cuuint64_t)TC_KA, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)TC_KA * sizeof(__nv_bfloat16)};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__nv_bfloat16)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -414,7 +347,7 @@ static TcLayout tc_layout(int64_t nq, int64_t nt, int mode) {
   TcLayout L;
   L.nt_pad = (nt + TC_TN - 1) / TC_TN * TC_TN;
   L.splits_tc = tc_splits(nq, nt);
-  L.splits_simt = (mode == HPUSM_L2_AUTO) ? l2_simt_splits(nq, nt) : 0;
+  L.splits_simt = 0;  // (the FP32 engine no longer shares this buffer: general floats go to the split engine)
   L.nparts = L.splits_tc > L.splits_simt ? L.splits_tc : L.splits_simt;
   size_t off = 0;
   L.qb = off; off += align_up((size_t)nq * TC_KA * 2, 1024);
@@ -427,7 +360,9 @@ static TcLayout tc_layout(int64_t nq, int64_t nt, int mode) {
 
 size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode) {
   if (d != TC_D || nq <= 0 || nt <= 0) return 256;
-  return tc_layout(nq, nt, mode).total;
+  const size_t a = mode == HPUSM_L2_TC_SPLIT ? 0 : tc_layout(nq, nt, mode).total;
+  const size_t b = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_SPLIT) ? l2_tc_split_workspace_bytes(nq, nt) : 0;
+  return a > b ? a : b;
 }
 
 // Defined in l2_simt.cu: the FP32 engine, launched only when *gate != 0.
@@ -437,8 +372,10 @@ int l2_simt_candidates_gated(const float* q, int64_t nq, const float* t, int64_t
 int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist, void* ws,
                size_t ws_bytes, cudaStream_t st, int* resolved_mode, int64_t* fallback_rows) {
   HPUSM_REQUIRE(d == TC_D, HPUSM_ERR_UNSUPPORTED, "tensor-core L2 engine is built for d == %d, got %d", TC_D, d);
-  HPUSM_REQUIRE(mode != HPUSM_L2_TC_SPLIT, HPUSM_ERR_UNSUPPORTED,
-                "HPUSM_L2_TC_SPLIT is not built yet: use HPUSM_L2_AUTO (general floats take the FP32 engine)");
+  if (mode == HPUSM_L2_TC_SPLIT) {
+    *resolved_mode = HPUSM_L2_TC_SPLIT;
+    return l2_tc_split_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
+  }
   const TcLayout L = tc_layout(nq, nt, mode);
   HPUSM_REQUIRE(ws_bytes >= L.total, HPUSM_ERR_WORKSPACE, "l2 tensor engine: workspace needs %zu bytes, got %zu", L.total,
                 ws_bytes);
@@ -455,11 +392,21 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   HPUSM_LAUNCH(l2_tc_prep_kernel, (unsigned)((L.nt_pad + 7) / 8), 256, 0, st, t, nt, L.nt_pad, 1, tb, flag);
   HPUSM_CHECK_LAUNCH();
 
+  if (mode == HPUSM_L2_AUTO) {
+    // one host read: are the descriptors integer valued (exact single-pass engine) or general floats (split engine)?
+    int h_flag = 0;
+    HPUSM_CUDA_OK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HPUSM_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_flag != 0) {
+      *resolved_mode = HPUSM_L2_TC_SPLIT;
+      return l2_tc_split_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
+    }
+  }
   CUtensorMap map_q, map_qa, map_t, map_ta;
-  int rc = make_map(&map_q, qb, nq, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc == HPUSM_OK) rc = make_map(&map_qa, qb, nq, 16, CU_TENSOR_MAP_SWIZZLE_32B);
-  if (rc == HPUSM_OK) rc = make_map(&map_t, tb, L.nt_pad, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc == HPUSM_OK) rc = make_map(&map_ta, tb, L.nt_pad, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+  int rc = tc_make_map(&map_q, qb, nq, TC_KA, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == HPUSM_OK) rc = tc_make_map(&map_qa, qb, nq, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc == HPUSM_OK) rc = tc_make_map(&map_t, tb, L.nt_pad, TC_KA, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != HPUSM_OK) return rc;
 
   static bool attr_done[64] = {false};
@@ -477,10 +424,6 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   HPUSM_LAUNCH_TIMED(l2_tc_knn2_kernel, grid, TC_THREADS, TC_SMEM_BYTES, st, map_q, map_qa, map_t, map_ta, nq, nt, q_blocks,
                      L.splits_tc, rows_per_split, part, flag);
   HPUSM_CHECK_LAUNCH();
-  if (mode == HPUSM_L2_AUTO) {
-    rc = l2_simt_candidates_gated(q, nq, t, nt, d, L.splits_simt, part, flag, st);
-    if (rc != HPUSM_OK) return rc;
-  }
   *resolved_mode = HPUSM_L2_TC_INT;
   *fallback_rows = 0;
   return l2_rerank_finalize(q, nq, t, d, part, L.nparts, 2, nullptr, 0, idx, dist, st);

@@ -37,10 +37,12 @@ extern "C" {
 #define HPUSM_ERR_UNSUPPORTED (-4) /* shape outside what the sm_100a kernels were built for         */
 
 /* L2 kNN engine selection (hpusm_knn2_l2 `mode`). */
-#define HPUSM_L2_AUTO 0   /* tensor-core path; operand split chosen from the data (exact-int or 3-way) */
+#define HPUSM_L2_AUTO 0   /* tensor-core path; engine chosen from the data (exact-int, else hi/lo split); reads one
+                             4-byte flag back, i.e. synchronises the stream once per call                          */
 #define HPUSM_L2_SIMT 1   /* exact FP32 CUDA-core brute force (cross-check / tiny inputs)             */
 #define HPUSM_L2_TC_INT 2 /* tcgen05, bf16 operands, caller asserts integer values in [0,256]         */
-#define HPUSM_L2_TC_SPLIT 3 /* tcgen05, hi/lo bf16 split (general float) + top-m FP32 re-rank         */
+#define HPUSM_L2_TC_SPLIT 3 /* tcgen05, hi/lo bf16 split (general float), top-4 + verified FP32 re-rank; synchronises
+                               the stream once (count of rows sent to the exact fallback)                          */
 
 int hpusm_version(void);
 const char* hpusm_last_error(void);

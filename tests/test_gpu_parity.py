@@ -382,3 +382,47 @@ def test_posedb_streaming_search(hpusm, cuda_device, tmp_path):
     np.testing.assert_array_equal(i, ti.cpu().numpy())
     np.testing.assert_array_equal(s, ts.cpu().numpy())
     assert total == int(cnt.item()) == int(match.sum().item())
+
+
+# ---- K1 split-operand tensor engine (general float descriptors) ---------------------------------------------------
+def test_l2_split_engine_general_floats(hpusm, cuda_device):
+    """HPUSM_L2_TC_SPLIT / AUTO on non-integer descriptors: indices equal the float64 brute force (ties within the
+    stated 1e-5 relative tolerance aside), distances to 2e-6; units, database splits and ragged tails included."""
+    rng = np.random.default_rng(77)
+    for nq, nt in [(300, 900), (1, 5), (129, 3), (4000, 70001), (20000, 1085)]:
+        q = rng.standard_normal((nq, 128)).astype(np.float32)
+        t = rng.standard_normal((nt, 128)).astype(np.float32)
+        k = min(nq, nt) // 3
+        if k:
+            t[:k] = q[:k] + 0.05 * rng.standard_normal((k, 128)).astype(np.float32)  # planted near neighbours
+        for mode in (hpusm.engine.L2_TC_SPLIT, hpusm.engine.L2_AUTO):
+            idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=mode)
+            assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_SPLIT
+            ri, rd = knn_oracle.knn2_l2(q, t)
+            assert_l2_parity(idx, dist, ri, rd, q, t)
+
+
+def test_l2_split_engine_sift_like_unnormalised(hpusm, cuda_device):
+    """Real-valued SIFT-like rows (norm ~ 512, non-integer): large norms stress the error bound of the proof."""
+    q, t = hpusm.synth.sift_like(3000, 20000, seed=5, planted=0.3)
+    q = (q * np.float32(1.0137)).astype(np.float32)
+    t = (t * np.float32(1.0137)).astype(np.float32)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_AUTO)
+    assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_SPLIT
+    ri, rd = knn_oracle.knn2_l2(q, t)
+    assert_l2_parity(idx, dist, ri, rd, q, t)
+
+
+def test_l2_split_engine_near_ties_take_the_exact_fallback(hpusm, cuda_device):
+    """Database rows packed so tightly around the queries that the top-4 lists cannot be proven complete: those
+    rows must be redone by the exact FP32 engine, and the answer must still be the exact one."""
+    rng = np.random.default_rng(78)
+    nq, nt = 257, 6000
+    q = rng.standard_normal((nq, 128)).astype(np.float32)
+    t = rng.standard_normal((nt, 128)).astype(np.float32)
+    for r in range(40):  # 20 database rows within 1e-4 of query r
+        t[100 * r:100 * r + 20] = q[r] + 1e-4 * rng.standard_normal((20, 128)).astype(np.float32)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_TC_SPLIT)
+    assert hpusm.engine.knn2_l2_last_fallback_rows() >= 30
+    sidx, sdist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_SIMT)
+    assert torch.equal(idx, sidx) and torch.equal(dist, sdist)  # both end in the same exact FP32 re-rank
