@@ -83,13 +83,17 @@ def knn2_l2(q, t, chunk=512, tchunk=65536):
         best_d = np.full((qa.shape[0], 2), np.inf)
         for b in range(0, nt, tchunk):
             tb = t64[b:b + tchunk]
-            if exact_int:
-                d = (qa * qa).sum(1)[:, None] + tn[None, b:b + tchunk] - 2.0 * (qa @ tb.T)
-            else:
-                d = np.empty((qa.shape[0], tb.shape[0]))
-                for r in range(qa.shape[0]):
-                    diff = tb - qa[r]
-                    d[r] = np.einsum("ij,ij->i", diff, diff)
+            d = (qa * qa).sum(1)[:, None] + tn[None, b:b + tchunk] - 2.0 * (qa @ tb.T)
+            if not exact_int:
+                # float64 GEMM form (error ~1e-13 |q||t|) to find the few smallest entries, then the exact
+                # sum((a-b)^2) in float64 for those, so near-ties are ordered by the true distances
+                m = min(4, d.shape[1])
+                cols = np.argpartition(d, m - 1, axis=1)[:, :m]
+                rows = np.arange(d.shape[0])[:, None]
+                diff = tb[cols] - qa[:, None, :]
+                exact = np.einsum("ijk,ijk->ij", diff, diff)
+                d = np.full_like(d, np.inf)
+                d[rows, cols] = exact
             i2, d2 = _top2_from_matrix(d)
             i2 = np.where(i2 >= 0, i2 + b, -1)
             best_i, best_d = _merge_top2(best_i, best_d, i2, d2)
