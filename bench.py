@@ -313,7 +313,7 @@ def run_ours(args, rank, world, device):
                 "d2h_bytes_per_step": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel())},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%dx%d" % (nq, nt)),
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%dx%d" % (nq, nt)) if args.descriptors == "int" else None,
                      "kernel_ms": k_ms, "kernel_launches": int(kernel_n),
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"},
         "clocks": clocks,
