@@ -14,7 +14,7 @@ module at the repository root.
 """
 from . import _lib  # noqa: F401
 from . import synth  # noqa: F401
-from . import engine, retrieval, posedb  # noqa: F401
+from . import engine, retrieval, posedb, dropin  # noqa: F401
 from .engine import (  # noqa: F401
     knn2_hamming,
     knn2_hamming_segmented,

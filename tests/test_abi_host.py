@@ -97,3 +97,29 @@ def test_openpose_json_parser_and_packed_db(hpusm, tmp_path):
     assert len(db) == total == int(g["n"].sum()) and db.n_files == len(paths) and db.names[0] == "img0_keypoints.json"
     np.testing.assert_array_equal(db.poses[0], g["poses"][0, 0].astype(np.float32))
     assert db.file_index[-1] == len(paths) - 1 and db.person_index[0] == 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_dropin_install_over_reference_checkout():
+    """dropin.install(reference_root): the reference's own pipeline modules import, see OUR hot-path functions, and
+    still reach the reference's non-hot-path helpers through the fall-through.  (No compute here: no GPU.)"""
+    import subprocess
+    import sys
+    code = r'''
+import sys, math
+import numpy as np
+np.math = math
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle/refshim")
+import hpusm
+hpusm.dropin.install(reference_root="/root/reference")
+import matching, urbanscene.urban_scene as us, posematching.multi_person as mp, common, urbanscene.features as ft
+assert ft.match_and_draw.__module__.endswith("dropin.urbanscene.features")
+assert us.features is ft and mp.find_transformation.__module__.endswith("dropin.common")
+assert common.parse_JSON_multi_person.__module__.startswith("_hpusm_reference")      # fall-through
+poses = common.parse_JSON_multi_person("/root/reference/json_data/duo1.json")
+assert poses[0].shape == (18, 2)
+assert hasattr(ft, "explore_match")                                                   # GUI helper of the reference
+print("OK")
+''' % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
