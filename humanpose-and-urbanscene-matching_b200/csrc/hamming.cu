@@ -56,7 +56,11 @@ __device__ __forceinline__ int hamming256(const uint32_t* __restrict__ a, const 
   const uint32_t o2 = xor3(x3, x4, x5), t2 = maj3(x3, x4, x5);
   const uint32_t o3 = xor3(o1, o2, x6), t3 = maj3(o1, o2, x6);
   const uint32_t tw = xor3(t1, t2, t3), f = maj3(t1, t2, t3);
-  return __popc(o3) + __popc(x7) + 2 * __popc(tw) + 4 * __popc(f);
+  // combine with IMAD (FMA pipe, idle here) rather than LEA/IADD3 (ALU pipe, the bound)
+  int d = __popc(o3) + __popc(x7), p2 = __popc(tw), p4 = __popc(f);
+  asm("mad.lo.s32 %0, %1, 2, %0;" : "+r"(d) : "r"(p2));
+  asm("mad.lo.s32 %0, %1, 4, %0;" : "+r"(d) : "r"(p4));
+  return d;
 }
 
 struct HamTop2 {
@@ -123,16 +127,26 @@ __device__ __forceinline__ void hamming_sweep(const uint8_t* __restrict__ q, int
         uint4 x = sp[j * V + v];
         w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
       }
+      int d[HAM_QPT];
+      bool hit = false;
 #pragma unroll
       for (int r = 0; r < HAM_QPT; ++r) {
-        int d = 0;
+        d[r] = 0;
 #pragma unroll
-        for (int k = 0; k < NW; k += 8) d += hamming256(&qr[r][k], &w[k]);
-        if (d < top[r].d1) {  // rare after the first few rows; strict '<' keeps the lower index on ties
-          if (d < top[r].d0) {
-            top[r].d1 = top[r].d0; top[r].i1 = top[r].i0; top[r].d0 = d; top[r].i0 = idx0 + j;
-          } else {
-            top[r].d1 = d; top[r].i1 = idx0 + j;
+        for (int k = 0; k < NW; k += 8) d[r] += hamming256(&qr[r][k], &w[k]);
+        hit |= d[r] < top[r].d1;
+      }
+      // One warp-uniform branch per database row guards the (rare, after the first rows) top-2 update; left to
+      // itself the compiler predicates the update and spends ~8 ALU-pipe selects per pair on it.
+      if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+        for (int r = 0; r < HAM_QPT; ++r) {
+          if (d[r] < top[r].d1) {  // strict '<' keeps the lower index on ties
+            if (d[r] < top[r].d0) {
+              top[r].d1 = top[r].d0; top[r].i1 = top[r].i0; top[r].d0 = d[r]; top[r].i0 = idx0 + j;
+            } else {
+              top[r].d1 = d[r]; top[r].i1 = idx0 + j;
+            }
           }
         }
       }

@@ -203,6 +203,18 @@ __device__ __forceinline__ bool is_inlier(const float* h, float x, float y, floa
   return e <= lim;
 }
 
+// Same test, accumulating into `cnt` with one predicated add (the compiler's select + add costs an extra issue slot).
+__device__ __forceinline__ void inlier_count(const float* h, float x, float y, float xp, float yp, float thr2, int& cnt) {
+  const float w = __fmaf_rn(h[6], x, __fmaf_rn(h[7], y, h[8]));
+  const float u = __fmaf_rn(h[0], x, __fmaf_rn(h[1], y, h[2]));
+  const float v = __fmaf_rn(h[3], x, __fmaf_rn(h[4], y, h[5]));
+  const float du = __fmaf_rn(-xp, w, u);
+  const float dv = __fmaf_rn(-yp, w, v);
+  const float e = __fmaf_rn(du, du, __fmul_rn(dv, dv));
+  const float lim = __fmul_rn(__fmul_rn(thr2, w), w);
+  asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(e), "f"(lim));
+}
+
 // cv2's adaptive bound on the number of iterations (RANSACUpdateNumIters restated).
 __device__ int update_num_iters(double conf, double outlier_ratio, int max_iters) {
   double p = fmin(fmax(conf, 0.0), 1.0);
@@ -302,7 +314,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
 #pragma unroll 4
       for (int i = p0; i < p1; ++i) {
         const float4 p = pts[i];
-        cnt += is_inlier(hm, p.x, p.y, p.z, p.w, thr2) ? 1 : 0;
+        inlier_count(hm, p.x, p.y, p.z, p.w, thr2, cnt);
       }
       if (h >= 0 && cnt) atomicAdd(&counts[h], cnt);
     }
