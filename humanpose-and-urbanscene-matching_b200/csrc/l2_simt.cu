@@ -5,8 +5,7 @@
 // l2_simt_knn2_kernel is the exact brute force: d2 = sum_k fma(a_k-b_k, a_k-b_k, d2) in increasing k,
 // FP32, i.e. the same number the re-rank produces.  It is the cross-check for the tcgen05 engine at
 // sizes no CPU oracle reaches, the engine for shapes the tensor path does not take (d not a multiple of
-// 16, d > 128), and the fallback for query rows whose tensor-core candidate list could not be proven
-// complete.  64x64 register-tiled, query tile resident in shared memory for the whole sweep, database
+// 128), and the fallback for query rows whose split-engine candidate list could not be proven complete.  64x64 register-tiled, query tile resident in shared memory for the whole sweep, database
 // chunks double-buffered with cp.async, per-thread running top-2 (no reduction in the hot loop) and one
 // lexicographic warp-shuffle merge at the end.
 //
@@ -40,8 +39,7 @@ struct F32Top2 {
 __global__ void __launch_bounds__(SIMT_THREADS)
 l2_simt_knn2_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ t, int64_t nt, int d,
                     int64_t rows_per_split, const int32_t* __restrict__ row_list, int64_t n_list,
-                    int32_t* __restrict__ part_idx, const int* __restrict__ gate) {
-  if (gate && *gate == 0) return;  // the tensor-core engine took this call (l2_tc.cu)
+                    int32_t* __restrict__ part_idx) {
   extern __shared__ __align__(16) float smem_f[];
   float* As = smem_f;                                   // [d][SIMT_LD]   As[k][query]
   float* Braw = As + (size_t)d * SIMT_LD;               // 2 x [SIMT_TT][SIMT_KCP] row-major staging
@@ -253,8 +251,8 @@ size_t l2_simt_smem_bytes(int d) {
 }
 
 // Brute-force top-2 candidate indices for nq rows (or for row_list) -> part_idx [splits][rows][2].
-static int simt_launch(const float* q, int64_t nq, const float* t, int64_t nt, int d, const int32_t* row_list,
-                       int64_t n_list, int splits, int32_t* part_idx, const int* gate, cudaStream_t st) {
+int l2_simt_candidates(const float* q, int64_t nq, const float* t, int64_t nt, int d, const int32_t* row_list,
+                       int64_t n_list, int splits, int32_t* part_idx, cudaStream_t st) {
   const int64_t rows = row_list ? n_list : nq;
   if (rows == 0) return HPUSM_OK;
   const size_t smem = l2_simt_smem_bytes(d);
@@ -269,23 +267,13 @@ static int simt_launch(const float* q, int64_t nq, const float* t, int64_t nt, i
   const int64_t tiles = (rows + SIMT_TQ - 1) / SIMT_TQ;
   const int64_t rows_per_split = nt == 0 ? 1 : (nt + splits - 1) / splits;
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  if (gate) HPUSM_LAUNCH(l2_simt_knn2_kernel, grid, SIMT_THREADS, smem, st, q, nq, t, nt, d, rows_per_split, row_list,
-                         n_list, part_idx, gate);
+  // bracketed for the roofline only when it is the whole sweep (as a fallback of the split engine it is a side show)
+  if (row_list) HPUSM_LAUNCH(l2_simt_knn2_kernel, grid, SIMT_THREADS, smem, st, q, nq, t, nt, d, rows_per_split, row_list,
+                             n_list, part_idx);
   else HPUSM_LAUNCH_TIMED(l2_simt_knn2_kernel, grid, SIMT_THREADS, smem, st, q, nq, t, nt, d, rows_per_split, row_list,
-                          n_list, part_idx, gate);
+                          n_list, part_idx);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
-}
-
-int l2_simt_candidates(const float* q, int64_t nq, const float* t, int64_t nt, int d, const int32_t* row_list,
-                       int64_t n_list, int splits, int32_t* part_idx, cudaStream_t st) {
-  return simt_launch(q, nq, t, nt, d, row_list, n_list, splits, part_idx, nullptr, st);
-}
-
-// Same sweep, but a no-op on the device unless *gate != 0 (set by the tensor engine's operand check).
-int l2_simt_candidates_gated(const float* q, int64_t nq, const float* t, int64_t nt, int d, int splits, int32_t* part_idx,
-                             const int* gate, cudaStream_t st) {
-  return simt_launch(q, nq, t, nt, d, nullptr, 0, splits, part_idx, gate, st);
 }
 
 int l2_rerank_finalize(const float* q, int64_t nq, const float* t, int d, const int32_t* cand, int nparts,

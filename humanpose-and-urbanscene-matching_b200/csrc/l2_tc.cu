@@ -365,10 +365,6 @@ size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode) {
   return a > b ? a : b;
 }
 
-// Defined in l2_simt.cu: the FP32 engine, launched only when *gate != 0.
-int l2_simt_candidates_gated(const float* q, int64_t nq, const float* t, int64_t nt, int d, int splits, int32_t* part_idx,
-                             const int* gate, cudaStream_t st);
-
 int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist, void* ws,
                size_t ws_bytes, cudaStream_t st, int* resolved_mode, int64_t* fallback_rows) {
   HPUSM_REQUIRE(d == TC_D, HPUSM_ERR_UNSUPPORTED, "tensor-core L2 engine is built for d == %d, got %d", TC_D, d);
