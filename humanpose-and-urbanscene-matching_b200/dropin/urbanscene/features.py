@@ -103,9 +103,31 @@ def find_homography_ransac(src, dst, thresh=5.0, maxIters=2000, confidence=0.995
     return down(H)[0], down(mask).reshape(-1, 1)
 
 
+def _kp_array(kps):
+    if isinstance(kps, np.ndarray):
+        return np.ascontiguousarray(kps, dtype=np.float32).reshape(-1, 2)
+    return np.float32([_pt(kp) for kp in kps]).reshape(-1, 2)
+
+
+def _match_and_filter_on_device(matcher, desc_model, desc_input, kp_model, kp_input, ratio):
+    """knnMatch + filter_matches without materialising 2 x Nq DMatch objects: kNN-2, ratio test, compaction and
+    keypoint gather stay on the GPU; only the K surviving point pairs come back."""
+    idx, dist = matcher.knn2(desc_model, desc_input)
+    keep, count = engine.ratio_filter(idx, dist, ratio)
+    p_q, p_t, sel, cnt = engine.gather_matches(up(_kp_array(kp_model), np.float32), up(_kp_array(kp_input), np.float32), idx, keep)
+    n = int(cnt.item())
+    return down(p_q[:n]).reshape(-1, 1, 2), down(p_t[:n]).reshape(-1, 1, 2)
+
+
 def match_and_draw(win, matcher, desc_model, desc_input, kp_model, kp_input, model_img, input_img, show_win):
-    raw_matches = matcher.knnMatch(desc_model, trainDescriptors=desc_input, k=2)
-    p_model, p_input, kp_pairs = filter_matches(kp_model, kp_input, raw_matches)
+    if isinstance(matcher, BFMatcher):
+        if desc_model is None or desc_input is None:
+            raise ValueError("knnMatch: descriptors are None (image without keypoints)")
+        p_model, p_input = _match_and_filter_on_device(matcher, desc_model, desc_input, kp_model, kp_input,
+                                                       thresholds.FILTER_RATIO)
+    else:  # any other object with cv2's knnMatch contract
+        raw_matches = matcher.knnMatch(desc_model, trainDescriptors=desc_input, k=2)
+        p_model, p_input, kp_pairs = filter_matches(kp_model, kp_input, raw_matches)
     if len(p_model) >= thresholds.MIN_MATCH_COUNT:
         H, mask = find_homography_ransac(p_model, p_input, 5.0)
         H2, mask2 = find_homography_ransac(p_input, p_model, 5.0)
