@@ -17,11 +17,15 @@
 // numbers DMatch.distance carries.
 //
 // Kernel shape (one persistent CTA per SM, 384 threads, warp specialised):
-//   warp 0     TMA producer: the unit's 256 queries (2 x [128 x 144] bf16, 72 KB, loaded once per unit) and a 4-stage
-//              ring of database tiles ([128 rows x 144] bf16, 36 KB per stage); columns 0..127 land as two
+//   warp 0     TMA producer: the unit's 256 queries (2 x [128 x 144] bf16, 72 KB, loaded once per unit) and a 2-stage
+//              ring of database tiles ([256 rows x 144] bf16, 72 KB per stage); columns 0..127 land as two
 //              SWIZZLE_128B slabs, the 16 augmentation columns as one SWIZZLE_32B slab
-//   warp 1     MMA issuer: per database tile 2 x 9 tcgen05.mma (M=128, N=128, K=16, kind::f16, cta_group::1)
-//              into one of two TMEM accumulator buffers (2 x 2 x 128 columns = all 512 columns)
+//   warp 1     MMA issuer: per database tile 2 x 9 tcgen05.mma (M=128, N=256, K=16, kind::f16, cta_group::1), one
+//              block of 9 per query tile, each into its own 256-column TMEM accumulator (2 x 256 = all 512 columns).
+//              The two query tiles ping-pong: while the tensor pipe works on tile 1's accumulator the epilogue drains
+//              tile 0's, and vice versa.  N=256 matters: with operands in shared memory every MMA re-reads its A
+//              slice, and at N=128 shared-memory bandwidth (MMA operand reads + TMA writes = 156 B/clk against 128 B/clk)
+//              capped the tensor pipe at 80 %; at N=256 the A re-reads halve (125 B/clk).
 //   warp 2     TMEM allocator
 //   warps 4-11 epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, an FMNMX3 tree over the
 //              32 values + one compare guards the (rare) top-2 insertion; the running top-2 lives in registers for
@@ -39,15 +43,17 @@ namespace hpusm {
 
 constexpr int TC_D = 128;            // descriptor length the engine is built for
 constexpr int TC_QB = 256;           // queries per unit (two M=128 MMA tiles)
-constexpr int TC_TN = 128;           // database rows per tile (MMA N)
-constexpr int TC_STAGES = 4;
+constexpr int TC_TN = 256;           // database rows per tile (MMA N)
+constexpr int TC_STAGES = 2;
 constexpr int TC_THREADS = 384;
 constexpr int TC_KA = 144;                                  // operand row: 128 descriptor columns + 16 augmentation columns
-constexpr int TC_HALF_BYTES = 128 * 128;                    // [128 rows][64 bf16] = 16 KB, one swizzle-128B slab
-constexpr int TC_AUG_BYTES = 128 * 32;                      // [128 rows][16 bf16] = 4 KB, one swizzle-32B slab
-constexpr int TC_TILE_BYTES = 2 * TC_HALF_BYTES + TC_AUG_BYTES;  // 36 KB: one [128 x 144] operand tile
+constexpr int TC_HALF_BYTES = 128 * 128;                    // query side: [128 rows][64 bf16] = 16 KB swizzle-128B slab
+constexpr int TC_AUG_BYTES = 128 * 32;                      // query side: [128 rows][16 bf16] = 4 KB swizzle-32B slab
+constexpr int TC_TILE_BYTES = 2 * TC_HALF_BYTES + TC_AUG_BYTES;  // 36 KB: one [128 x 144] query tile
 constexpr int TC_A_BYTES = 2 * TC_TILE_BYTES;               // two query tiles
-constexpr int TC_B_BYTES = TC_TILE_BYTES;                   // per stage
+constexpr int TC_BHALF_BYTES = TC_TN * 128;                 // database side: [256 rows][64 bf16] = 32 KB slab
+constexpr int TC_BAUG_BYTES = TC_TN * 32;                   // database side: [256 rows][16 bf16] = 8 KB slab
+constexpr int TC_B_BYTES = 2 * TC_BHALF_BYTES + TC_BAUG_BYTES;   // 72 KB per stage
 constexpr int TC_SMEM_BYTES = TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128.
@@ -141,12 +147,12 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                          // [2 tiles][16 KB | 16 KB | 4 KB]
-  uint8_t* smem_b = smem + TC_A_BYTES;             // [stages][16 KB | 16 KB | 4 KB]
+  uint8_t* smem_b = smem + TC_A_BYTES;             // [stages][32 KB | 32 KB | 8 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);
   uint64_t* full = bars;                           // [stages]   TMA -> MMA
   uint64_t* empty = bars + TC_STAGES;              // [stages]   MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * TC_STAGES;      // [2]        MMA -> epilogue
-  uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2; // [2]        epilogue -> MMA
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;      // [2 query tiles] MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2; // [2 query tiles] epilogue -> MMA
   uint64_t* a_full = bars + 2 * TC_STAGES + 4;     // query tiles landed
   uint64_t* a_empty = bars + 2 * TC_STAGES + 5;    // all MMAs of the unit retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
@@ -155,7 +161,7 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 4); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -200,8 +206,8 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           mbar_expect_tx(full + s, TC_B_BYTES);
           const int row0 = (int)(t_begin + (int64_t)j * TC_TN);
           tma_load_2d(smem_b + s * TC_B_BYTES, &map_t, full + s, 0, row0);
-          tma_load_2d(smem_b + s * TC_B_BYTES + TC_HALF_BYTES, &map_t, full + s, 64, row0);
-          tma_load_2d(smem_b + s * TC_B_BYTES + 2 * TC_HALF_BYTES, &map_ta, full + s, TC_D, row0);
+          tma_load_2d(smem_b + s * TC_B_BYTES + TC_BHALF_BYTES, &map_t, full + s, 64, row0);
+          tma_load_2d(smem_b + s * TC_B_BYTES + 2 * TC_BHALF_BYTES, &map_ta, full + s, TC_D, row0);
         }
       }
     }
@@ -217,25 +223,26 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
         mbar_wait(a_full, un & 1);
         for (int j = 0; j < tiles; ++j, ++it) {
-          const int s = it % TC_STAGES, b = it & 1;
+          const int s = it % TC_STAGES;
           mbar_wait(full + s, (it / TC_STAGES) & 1);
-          mbar_wait(tmem_empty + b, ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
-            const uint32_t d_addr = tmem_base + (uint32_t)((b * 2 + m) * TC_TN);
+            mbar_wait(tmem_empty + m, (it & 1) ^ 1);   // the epilogue has drained this query tile's accumulator
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + (uint32_t)(m * TC_TN);
 #pragma unroll
             for (int k = 0; k < TC_D / 16; ++k) {
-              const uint32_t koff = (uint32_t)((k >> 2) * TC_HALF_BYTES + (k & 3) * 32);
-              tc_mma_bf16(d_addr, umma_desc_sw128(a_addr + m * TC_TILE_BYTES + koff),
-                          umma_desc_sw128(b_addr + s * TC_B_BYTES + koff), TC_IDESC, k > 0 ? 1u : 0u);
+              const uint32_t koff_a = (uint32_t)((k >> 2) * TC_HALF_BYTES + (k & 3) * 32);
+              const uint32_t koff_b = (uint32_t)((k >> 2) * TC_BHALF_BYTES + (k & 3) * 32);
+              tc_mma_bf16(d_addr, umma_desc_sw128(a_addr + m * TC_TILE_BYTES + koff_a),
+                          umma_desc_sw128(b_addr + s * TC_B_BYTES + koff_b), TC_IDESC, k > 0 ? 1u : 0u);
             }
             // ninth step: the augmentation columns subtract ||t||^2
             tc_mma_bf16(d_addr, umma_desc_sw32(a_addr + m * TC_TILE_BYTES + 2 * TC_HALF_BYTES),
-                        umma_desc_sw32(b_addr + s * TC_B_BYTES + 2 * TC_HALF_BYTES), TC_IDESC, 1u);
+                        umma_desc_sw32(b_addr + s * TC_B_BYTES + 2 * TC_BHALF_BYTES), TC_IDESC, 1u);
+            tc_commit(tmem_full + m);   // this query tile's accumulator is ready for its epilogue warps
           }
-          tc_commit(empty + s);       // the stage may be refilled once these MMAs have read it
-          tc_commit(tmem_full + b);   // accumulators ready for the epilogue
+          tc_commit(empty + s);         // the stage may be refilled once both blocks have read it
         }
         tc_commit(a_empty);           // the query tiles may be replaced
       }
@@ -253,26 +260,28 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       top.k0 = top.k1 = __int_as_float(0xff800000);  // -inf
       top.i0 = top.i1 = -1;
       for (int j = 0; j < tiles; ++j, ++it) {
-        const int b = it & 1;
         const int col0 = (int)(t_begin + (int64_t)j * TC_TN);
         uint32_t acc0[32], acc1[32];
-        mbar_wait(tmem_full + b, (it >> 1) & 1);
+        mbar_wait(tmem_full + m, it & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + m) * TC_TN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * TC_TN);
         tc_ld32(taddr, acc0);
         tc_ld32(taddr + 32, acc1);
         tc_wait_ld();
-        tc_process32(acc0, col0, top);
-        tc_ld32(taddr + 64, acc0);
-        tc_process32(acc1, col0 + 32, top);
-        tc_ld32(taddr + 96, acc1);
-        tc_wait_ld();
-        // every column of this buffer is in registers: hand the accumulator back to the MMA warp
+#pragma unroll
+        for (int c = 0; c < TC_TN / 64 - 1; ++c) {  // 64 columns per round, the next 64 in flight meanwhile
+          tc_process32(acc0, col0 + 64 * c, top);
+          tc_ld32(taddr + 64 * (c + 1), acc0);
+          tc_process32(acc1, col0 + 64 * c + 32, top);
+          tc_ld32(taddr + 64 * (c + 1) + 32, acc1);
+          tc_wait_ld();
+        }
+        // every column of this accumulator is in registers: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + b);
-        tc_process32(acc0, col0 + 64, top);
-        tc_process32(acc1, col0 + 96, top);
+        if (lane == 0) mbar_arrive(tmem_empty + m);
+        tc_process32(acc0, col0 + TC_TN - 64, top);
+        tc_process32(acc1, col0 + TC_TN - 32, top);
       }
       const int64_t row = (int64_t)qb * TC_QB + m * 128 + quarter * 32 + lane;
       if (row < nq) {
@@ -308,13 +317,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows][cols] bf16 row-major; box = `box_cols` columns x 128 rows with the given swizzle; out-of-range rows read as 0
-int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_cols, CUtensorMapSwizzle swizzle) {
+// [rows][cols] bf16 row-major; box = `box_cols` columns x `box_rows` rows with the given swizzle; out-of-range rows read 0
+int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_cols, CUtensorMapSwizzle swizzle,
+                int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   HPUSM_REQUIRE(fn, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__nv_bfloat16)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, 128};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -401,8 +411,8 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   CUtensorMap map_q, map_qa, map_t, map_ta;
   int rc = tc_make_map(&map_q, qb, nq, TC_KA, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc == HPUSM_OK) rc = tc_make_map(&map_qa, qb, nq, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B);
-  if (rc == HPUSM_OK) rc = tc_make_map(&map_t, tb, L.nt_pad, TC_KA, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc == HPUSM_OK) rc = tc_make_map(&map_t, tb, L.nt_pad, TC_KA, 64, CU_TENSOR_MAP_SWIZZLE_128B, TC_TN);
+  if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B, TC_TN);
   if (rc != HPUSM_OK) return rc;
 
   static bool attr_done[64] = {false};
