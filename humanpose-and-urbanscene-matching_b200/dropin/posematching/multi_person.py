@@ -8,29 +8,37 @@ from .. import thresholds
 from .._dev import engine, up, down
 
 
+def _leftmost_x(pose):
+    xs = pose[:, 0]
+    xs = xs[xs != 0]
+    return xs.min() if xs.size else None
+
+
 def order_poses(poses):
-    """Verbatim control flow of the reference (sorting people left to right by their smallest non-zero x)."""
+    """The reference's left-to-right ordering (multi_person.py:225-253), restated.  Poses with at most 8 non-zero
+    coordinates are dropped.  Pose i walks back over its predecessors in the ORIGINAL list while it lies left of
+    them; running off the front puts it first, otherwise it is inserted at position 1 (sic: the reference inserts at
+    index 1, not behind the predecessor it stopped at); a predecessor or pose without any detected x ends the walk
+    without inserting the pose at all."""
     ordered = []
-    for i in range(0, len(poses)):
-        if np.count_nonzero(poses[i]) > 8:
-            pose = poses[i][:, 0]
-            placed = False
-            place_counter = 1
-            while not placed:
-                place = i - place_counter
-                if place > -1:
-                    prev_pose = poses[place][:, 0]
-                    try:
-                        if np.min(pose[np.nonzero(pose)]) < np.min(prev_pose[np.nonzero(prev_pose)]):
-                            place_counter = place_counter + 1
-                        else:
-                            ordered.insert(1, poses[i])
-                            placed = True
-                    except ValueError:
-                        placed = True
-                else:
-                    ordered.insert(0, poses[i])
-                    placed = True
+    for i, pose in enumerate(poses):
+        if np.count_nonzero(pose) <= 8:
+            continue
+        mine = _leftmost_x(pose)
+        back = 1
+        while True:
+            j = i - back
+            if j < 0:
+                ordered.insert(0, pose)
+                break
+            theirs = _leftmost_x(poses[j])
+            if mine is None or theirs is None:  # np.min of an empty selection raises in the reference: pose is skipped
+                break
+            if mine < theirs:
+                back += 1
+                continue
+            ordered.insert(1, pose)
+            break
     return ordered
 
 
