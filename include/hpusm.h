@@ -88,8 +88,12 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
 /* --------------------------------------------------------------------------------------------------
  * K1  Float-descriptor kNN, k=2, L2 norm.
  * Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) (features.py:42,:59).
- *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512
- *   (tensor-core modes: d a multiple of 16 and d <= 128).
+ *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512.
+ *   The tensor-core engines are built for d == 128 (SIFT); HPUSM_L2_AUTO takes the exact FP32 engine for other
+ *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT return HPUSM_ERR_UNSUPPORTED there.
+ *   HPUSM_L2_TC_INT trusts the caller that every value is an integer with |v| <= 256 (what OpenCV SIFT emits);
+ *   HPUSM_L2_AUTO checks that on the device and otherwise uses the split engine, whose answer is the exact FP32 one
+ *   as well (candidate lists are proven complete or the row is redone by the FP32 engine).
  *   idx  [nq][2] int32 as above.
  *   dist [nq][2] float32 = sqrtf( sum_k (q_k - t_k)^2 ), the sum taken in FP32 in increasing k with
  *   fused multiply-add (the "exact FP32 re-rank"); this is what DMatch.distance holds in the reference.
