@@ -215,6 +215,44 @@ __device__ __forceinline__ void inlier_count(const float* h, float x, float y, f
   asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(e), "f"(lim));
 }
 
+// ---- packed FP32 (sm_100 FFMA2 / FMUL2): two matches per instruction, each half rounded exactly like the scalar op ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// The inlier test of is_inlier() on TWO matches at once.  xy = (x0, x1, y0, y1), nq = (-x'0, -x'1, -y'0, -y'1);
+// h2[i] holds model coefficient i in both halves.  Same operations in the same order as the scalar test, so the
+// counts stay bit-identical to oracle/ransac_oracle.c.
+__device__ __forceinline__ void inlier_count2(const f32x2* h2, f32x2 thr2, float4 xy, float4 nq, int& cnt) {
+  const f32x2 X = pack2(xy.x, xy.y), Y = pack2(xy.z, xy.w), NXP = pack2(nq.x, nq.y), NYP = pack2(nq.z, nq.w);
+  const f32x2 w = fma2(h2[6], X, fma2(h2[7], Y, h2[8]));
+  const f32x2 u = fma2(h2[0], X, fma2(h2[1], Y, h2[2]));
+  const f32x2 v = fma2(h2[3], X, fma2(h2[4], Y, h2[5]));
+  const f32x2 du = fma2(NXP, w, u);
+  const f32x2 dv = fma2(NYP, w, v);
+  const f32x2 e = fma2(du, du, mul2(dv, dv));
+  const f32x2 lim = mul2(mul2(thr2, w), w);
+  float e0, e1, l0, l1;
+  unpack2(e, e0, e1);
+  unpack2(lim, l0, l1);
+  asm("{\n\t.reg .pred p, q;\n\tsetp.le.f32 p, %1, %2;\n\tsetp.le.f32 q, %3, %4;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t}"
+      : "+r"(cnt) : "f"(e0), "f"(l0), "f"(e1), "f"(l1));
+}
+
 // cv2's adaptive bound on the number of iterations (RANSACUpdateNumIters restated).
 __device__ int update_num_iters(double conf, double outlier_ratio, int max_iters) {
   double p = fmin(fmax(conf, 0.0), 1.0);
@@ -295,27 +333,38 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   const int groups = (nv + 31) >> 5;
   for (int64_t c0 = 0; c0 < K64; c0 += chunk) {
     const int cn = (int)min((int64_t)chunk, K64 - c0);
-    for (int i = tid; i < cn; i += RS_THREADS) {
-      const float2 a = reinterpret_cast<const float2*>(s)[c0 + i];
-      const float2 b = reinterpret_cast<const float2*>(d)[c0 + i];
-      pts[i] = make_float4(a.x, a.y, b.x, b.y);
+    // staged two matches per entry pair: pts[2j] = (x0, x1, y0, y1), pts[2j+1] = (-x'0, -x'1, -y'0, -y'1); an odd tail is
+    // padded with a match that no model can explain
+    const int npair = (cn + 1) >> 1;
+    for (int j = tid; j < npair; j += RS_THREADS) {
+      const int i0 = 2 * j, i1 = 2 * j + 1;
+      const float2 a0 = reinterpret_cast<const float2*>(s)[c0 + i0];
+      const float2 b0 = reinterpret_cast<const float2*>(d)[c0 + i0];
+      float2 a1 = make_float2(0.f, 0.f), b1 = make_float2(1e30f, 1e30f);
+      if (i1 < cn) {
+        a1 = reinterpret_cast<const float2*>(s)[c0 + i1];
+        b1 = reinterpret_cast<const float2*>(d)[c0 + i1];
+      }
+      pts[2 * j] = make_float4(a0.x, a1.x, a0.y, a1.y);
+      pts[2 * j + 1] = make_float4(-b0.x, -b1.x, -b0.y, -b1.y);
     }
     __syncthreads();
-    const int segs = (cn + RS_SEG - 1) / RS_SEG;
+    const int segs = (npair + RS_SEG / 2 - 1) / (RS_SEG / 2);
+    const f32x2 thr2x2 = pack2(thr2, thr2);
     for (int item = warp; item < groups * segs; item += RS_WARPS) {
       const int g = item / segs, sg = item - g * segs;
       const int j = g * 32 + lane;
       const int h = j < nv ? hyp_of[j] : -1;
-      float hm[9];
+      f32x2 h2[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) hm[i] = h >= 0 ? models[j * 9 + i] : 0.f;
-      const int p0 = sg * RS_SEG, p1 = min(cn, p0 + RS_SEG);
+      for (int i = 0; i < 9; ++i) {
+        const float c = h >= 0 ? models[j * 9 + i] : 0.f;
+        h2[i] = pack2(c, c);
+      }
+      const int p0 = sg * (RS_SEG / 2), p1 = min(npair, p0 + RS_SEG / 2);
       int cnt = 0;
 #pragma unroll 4
-      for (int i = p0; i < p1; ++i) {
-        const float4 p = pts[i];
-        inlier_count(hm, p.x, p.y, p.z, p.w, thr2, cnt);
-      }
+      for (int i = p0; i < p1; ++i) inlier_count2(h2, thr2x2, pts[2 * i], pts[2 * i + 1], cnt);
       if (h >= 0 && cnt) atomicAdd(&counts[h], cnt);
     }
     __syncthreads();
