@@ -149,6 +149,21 @@ __device__ __forceinline__ void hypothesis_points(const float* __restrict__ src,
   }
 }
 
+// Same, reading the matches from the pair-packed shared-memory staging of the scoring kernel:
+// pts[2j] = (x0, x1, y0, y1), pts[2j+1] = (-x'0, -x'1, -y'0, -y'1) for matches 2j, 2j+1 (negation is exact).
+__device__ __forceinline__ void hypothesis_points_smem(const float4* pts, uint32_t K, uint64_t seed, uint64_t pair,
+                                                       uint64_t hyp, double* sx, double* sy, double* dx, double* dy) {
+  uint32_t id[4];
+  sample4(seed, pair, hyp, K, id);
+  const float* f = reinterpret_cast<const float*>(pts);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t base = (id[j] >> 1) * 8 + (id[j] & 1);
+    sx[j] = (double)f[base]; sy[j] = (double)f[base + 2];
+    dx[j] = (double)(-f[base + 4]); dy[j] = (double)(-f[base + 6]);
+  }
+}
+
 // Exact 4-point homography of a non-degenerate sample. Points are translated to the first sample point before the
 // closed-form solve (exact in FP64 for pixel-range FP32 input) and the translation is folded back in afterwards.
 __device__ bool hypothesis_solve(double* sx, double* sy, double* dx, double* dy, double* H) {
@@ -295,6 +310,27 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float thr2 = __fmul_rn(thresh, thresh);
   if (tid == 0) n_valid = 0;
+
+  // Stage `cn` matches starting at c0, two per entry pair; an odd tail is padded with a match no model can explain.
+  auto stage = [&](int64_t c0, int cn) {
+    const int npair = (cn + 1) >> 1;
+    for (int j = tid; j < npair; j += RS_THREADS) {
+      const int i0 = 2 * j, i1 = 2 * j + 1;
+      const float2 a0 = reinterpret_cast<const float2*>(s)[c0 + i0];
+      const float2 b0 = reinterpret_cast<const float2*>(d)[c0 + i0];
+      float2 a1 = make_float2(0.f, 0.f), b1 = make_float2(1e30f, 1e30f);
+      if (i1 < cn) {
+        a1 = reinterpret_cast<const float2*>(s)[c0 + i1];
+        b1 = reinterpret_cast<const float2*>(d)[c0 + i1];
+      }
+      pts[2 * j] = make_float4(a0.x, a1.x, a0.y, a1.y);
+      pts[2 * j + 1] = make_float4(-b0.x, -b1.x, -b0.y, -b1.y);
+    }
+  };
+  // When the whole pair fits (the common case) it is staged ONCE, before hypothesis generation, so the 8 scattered
+  // sample reads per hypothesis hit shared memory instead of L2.
+  const bool resident = K64 <= chunk;
+  if (resident) stage(0, (int)K64);
   __syncthreads();
 
   // phase A1
@@ -304,7 +340,8 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
     bool ok = false;
     if (h < nhyp && K >= 4) {
       double sx[4], sy[4], dx[4], dy[4];
-      hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+      if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+      else hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
       ok = !degenerate4(sx, sy, dx, dy);
     }
     const unsigned b = __ballot_sync(0xffffffffu, ok);
@@ -321,7 +358,8 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   for (int j = tid; j < nv; j += RS_THREADS) {
     const int h = hyp_of[j];
     double sx[4], sy[4], dx[4], dy[4], H[9];
-    hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+    if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+    else hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
     const bool ok = hypothesis_solve(sx, sy, dx, dy, H);
 #pragma unroll
     for (int i = 0; i < 9; ++i) models[j * 9 + i] = ok ? (float)H[i] : 0.f;
@@ -331,26 +369,15 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
 
   // phase B
   const int groups = (nv + 31) >> 5;
+  const f32x2 thr2x2 = pack2(thr2, thr2);
   for (int64_t c0 = 0; c0 < K64; c0 += chunk) {
     const int cn = (int)min((int64_t)chunk, K64 - c0);
-    // staged two matches per entry pair: pts[2j] = (x0, x1, y0, y1), pts[2j+1] = (-x'0, -x'1, -y'0, -y'1); an odd tail is
-    // padded with a match that no model can explain
-    const int npair = (cn + 1) >> 1;
-    for (int j = tid; j < npair; j += RS_THREADS) {
-      const int i0 = 2 * j, i1 = 2 * j + 1;
-      const float2 a0 = reinterpret_cast<const float2*>(s)[c0 + i0];
-      const float2 b0 = reinterpret_cast<const float2*>(d)[c0 + i0];
-      float2 a1 = make_float2(0.f, 0.f), b1 = make_float2(1e30f, 1e30f);
-      if (i1 < cn) {
-        a1 = reinterpret_cast<const float2*>(s)[c0 + i1];
-        b1 = reinterpret_cast<const float2*>(d)[c0 + i1];
-      }
-      pts[2 * j] = make_float4(a0.x, a1.x, a0.y, a1.y);
-      pts[2 * j + 1] = make_float4(-b0.x, -b1.x, -b0.y, -b1.y);
+    if (!resident) {
+      stage(c0, cn);
+      __syncthreads();
     }
-    __syncthreads();
+    const int npair = (cn + 1) >> 1;
     const int segs = (npair + RS_SEG / 2 - 1) / (RS_SEG / 2);
-    const f32x2 thr2x2 = pack2(thr2, thr2);
     for (int item = warp; item < groups * segs; item += RS_WARPS) {
       const int g = item / segs, sg = item - g * segs;
       const int j = g * 32 + lane;

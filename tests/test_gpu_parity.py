@@ -191,6 +191,19 @@ def test_ransac_counts_identical_to_oracle(hpusm, cuda_device):
     np.testing.assert_array_equal(counts.cpu().numpy(), ref)
 
 
+def test_ransac_large_pair_streams_in_chunks(hpusm, cuda_device):
+    """A pair with more matches than fit in shared memory (staged chunk by chunk, samples read from global memory)."""
+    src, dst, _ = hpusm.synth.ransac_pair(9001, inlier_ratio=0.4, seed=12)
+    offs = np.array([0, 9001], np.int64)
+    counts = hpusm.ransac_score_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device), 5.0, 300, seed=3)
+    np.testing.assert_array_equal(counts.cpu().numpy(), ransac_oracle.score_batch(src, dst, offs, 5.0, 300, 3))
+    H, mask, ninl, best = hpusm.ransac_homography_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device),
+                                                        5.0, 300, 0.995, seed=3)
+    rH, rmask, rninl, rbest = ransac_oracle.homography_batch(src, dst, offs, 5.0, 300, 0.995, 3)
+    np.testing.assert_array_equal(mask.cpu().numpy(), rmask)
+    np.testing.assert_allclose(H.cpu().numpy(), rH, rtol=1e-7, atol=1e-7)
+
+
 @pytest.mark.parametrize("confidence", [0.995, 0.0])
 def test_ransac_homography_identical_inlier_sets(hpusm, cuda_device, confidence):
     g = load_golden("ransac_cv2.npz")
