@@ -72,6 +72,7 @@ SIGNATURES = {
     "hpusm_pose_match_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "hpusm_pose_match_batch_f64": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "hpusm_pose_match_pairs": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "hpusm_scene_score_batch": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _f64, _f64, _u64, _p, _p, _p, _p]),
     "hpusm_feature_scaling_batch": (_i32, [_p, _i64, _i32, _p, _p]),
     "hpusm_pose_topk_workspace_bytes": (_sz, [_i64, _i32]),
     "hpusm_pose_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),

@@ -536,6 +536,118 @@ pose_match_pairs_kernel(const T* __restrict__ model, const T* __restrict__ input
   }
 }
 
+// ---- scene score: perspective correction + affine fit of pose and random background matches -------------------
+// Batched urban_scene.match_scene_multi steps 3.1-5 (urban_scene.py:80-145): transformation.perspective_correction
+// (transformation.py:22-53: cv2.perspectiveTransform of the inlier matches and the input pose with H2) followed by
+// transformation.affine_multi (transformation.py:101-173,:413: affine least squares over the pose and
+// AMOUNT_BACKGROUND_FEATURES = 5 randomly chosen inlier matches, normalisation by the model image size, maximum
+// distance).  The reference draws the 5 matches with Python's unseeded random.sample; here they come from a
+// counter-based table keyed on (seed, pair) -- or from the caller (`picks`).
+__device__ __forceinline__ uint64_t scene_mix64(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// cv2.perspectiveTransform on a CV_32FC2 point with a CV_64F matrix: double accumulate, float32 result
+__device__ __forceinline__ void persp32(const double* H, double x, double y, double& ox, double& oy) {
+  double w = x * H[6] + y * H[7] + H[8];
+  if (fabs(w) > 2.220446049250313e-16) {
+    w = 1.0 / w;
+    ox = (double)(float)((x * H[0] + y * H[1] + H[2]) * w);
+    oy = (double)(float)((x * H[3] + y * H[4] + H[5]) * w);
+  } else { ox = 0.0; oy = 0.0; }
+}
+
+constexpr int SCENE_BG = 5;  // thresholds.AMOUNT_BACKGROUND_FEATURES
+
+// One thread per image pair.
+__global__ void scene_score_batch_kernel(const float* __restrict__ src, const float* __restrict__ dst,
+                                         const int64_t* __restrict__ pair_offsets, const uint8_t* __restrict__ mask,
+                                         const double* __restrict__ H2, const double* __restrict__ model_pose,
+                                         const double* __restrict__ input_pose, int64_t npairs, int model_pose_stride,
+                                         int njoints, double model_w, double model_h, uint64_t seed,
+                                         const int32_t* __restrict__ picks, double* __restrict__ score,
+                                         int32_t* __restrict__ picks_out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const int64_t m0 = pair_offsets[p], K = pair_offsets[p + 1] - m0;
+  const double* H = H2 + p * 9;
+  int n_in = 0;
+  for (int64_t i = 0; i < K; ++i) n_in += mask[m0 + i] ? 1 : 0;
+  if (!(H[0] == H[0])) { score[p] = INFINITY; return; }             // no homography (urban_scene.py:45-47)
+  if (n_in < SCENE_BG) { score[p] = 1.0; return; }                  // transformation.py:107-108
+  // the five background matches: ordinals among the inliers
+  int pick[SCENE_BG];
+  if (picks) {
+#pragma unroll
+    for (int j = 0; j < SCENE_BG; ++j) pick[j] = picks[p * SCENE_BG + j];
+  } else {
+    uint64_t st = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(p + 1));
+    (void)scene_mix64(st);
+    int taken[SCENE_BG];
+    for (int j = 0; j < SCENE_BG; ++j) {
+      const uint64_t r = scene_mix64(st);
+      int v = (int)(((r >> 32) * (uint64_t)(n_in - j)) >> 32);
+      int pos = 0;
+      for (int c = 0; c < j; ++c)
+        if (v >= taken[c]) { ++v; pos = c + 1; }
+      for (int c = j; c > pos; --c) taken[c] = taken[c - 1];
+      taken[pos] = v;
+      pick[j] = v;
+    }
+  }
+  if (picks_out)
+    for (int j = 0; j < SCENE_BG; ++j) picks_out[p * SCENE_BG + j] = pick[j];
+  // coordinates of the picked matches (model side as is, input side perspective corrected)
+  double bmx[SCENE_BG], bmy[SCENE_BG], bix[SCENE_BG], biy[SCENE_BG];
+  {
+    int ord = 0;
+    for (int64_t i = 0; i < K; ++i) {
+      if (!mask[m0 + i]) continue;
+#pragma unroll
+      for (int j = 0; j < SCENE_BG; ++j)
+        if (pick[j] == ord) {
+          bmx[j] = (double)src[2 * (m0 + i)]; bmy[j] = (double)src[2 * (m0 + i) + 1];
+          persp32(H, (double)dst[2 * (m0 + i)], (double)dst[2 * (m0 + i) + 1], bix[j], biy[j]);
+        }
+      ++ord;
+    }
+  }
+  const double* mp = model_pose + p * model_pose_stride;
+  const double* ip = input_pose + p * njoints * 2;
+  // find_transformation(model = pose + picks, input = corrected pose + corrected picks) (transformation.py:129)
+  LsqSums m = {};
+  for (int j = 0; j < njoints; ++j) {
+    double x, y;
+    persp32(H, (double)(float)ip[2 * j], (double)(float)ip[2 * j + 1], x, y);
+    if (!(x == 0.0 && y == 0.0)) lsq_add(m, x, y, mp[2 * j], mp[2 * j + 1]);
+  }
+#pragma unroll
+  for (int j = 0; j < SCENE_BG; ++j)
+    if (!(bix[j] == 0.0 && biy[j] == 0.0)) lsq_add(m, bix[j], biy[j], bmx[j], bmy[j]);
+  if (m.n < 0.5) { score[p] = NAN; return; }
+  double A[9];
+  lsq_solve(m, A);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = zero_small(A[i]);  // find_transformation returns M with |a| < 1e-10 zeroed (common.py:99)
+  // np.dot(pad(input_pose), M) for every row (zero rows included), scaled by the model image size, max distance
+  double best = -1.0;
+  for (int j = 0; j < njoints + SCENE_BG; ++j) {
+    double x, y, X, Y;
+    if (j < njoints) { persp32(H, (double)(float)ip[2 * j], (double)(float)ip[2 * j + 1], x, y); X = mp[2 * j]; Y = mp[2 * j + 1]; }
+    else { x = bix[j - njoints]; y = biy[j - njoints]; X = bmx[j - njoints]; Y = bmy[j - njoints]; }
+    const double tx = x * A[0] + y * A[3] + A[6], ty = x * A[1] + y * A[4] + A[7];
+    const double dx = fabs(X / model_w - tx / model_w), dy = fabs(Y / model_h - ty / model_h);
+    const double dist = sqrt(dx * dx + dy * dy);
+    if (j == 0) best = dist;
+    else if (dist > best) best = dist;
+  }
+  score[p] = best;
+}
+
 // ---- per-rank top-k of the matching poses ---------------------------------------------------------------
 constexpr int TK_THREADS = 256;
 constexpr int TK_MAXK = 64;
@@ -750,6 +862,21 @@ int hpusm_pose_match_pairs(const void* model, const void* input, int64_t n, int 
   else
     HPUSM_LAUNCH(pose_match_pairs_kernel<float>, grid, PM_THREADS, 0, as_stream(stream), reinterpret_cast<const float*>(model),
                  reinterpret_cast<const float*>(input), n, prm, match, score, detail);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_scene_score_batch(const float* src, const float* dst, const int64_t* pair_offsets, const uint8_t* mask,
+                            const double* H2, const double* model_pose, int model_pose_shared, const double* input_pose,
+                            int64_t npairs, int njoints, double model_w, double model_h, uint64_t seed,
+                            const int32_t* picks, double* score, int32_t* picks_out, void* stream) {
+  HPUSM_REQUIRE(npairs >= 0 && njoints > 0 && model_w > 0 && model_h > 0, HPUSM_ERR_INVALID, "hpusm_scene_score_batch: bad sizes");
+  if (npairs == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(src && dst && pair_offsets && mask && H2 && model_pose && input_pose && score, HPUSM_ERR_INVALID,
+                "hpusm_scene_score_batch: null pointer");
+  HPUSM_LAUNCH(scene_score_batch_kernel, (unsigned)((npairs + 63) / 64), 64, 0, as_stream(stream), src, dst, pair_offsets, mask,
+               H2, model_pose, input_pose, npairs, model_pose_shared ? 0 : njoints * 2, njoints, model_w, model_h, seed, picks,
+               score, picks_out);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

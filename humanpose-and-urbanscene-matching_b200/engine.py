@@ -341,6 +341,31 @@ def pose_match_pairs(model, inp, thresholds=DEFAULT_POSE_THRESHOLDS, want_detail
     return (match, score, detail) if want_detail else (match, score)
 
 
+def scene_score_batch(src, dst, pair_offsets, mask, H2, model_pose, input_pose, model_w, model_h, seed=0, picks=None):
+    """Perspective correction + affine_multi score per image pair (urban_scene.py:80-145).  model_pose [18,2] (shared)
+    or [npairs,18,2]; input_pose [npairs,18,2]; float64.  Returns (score [npairs] f64, picks [npairs,5] i32)."""
+    src = _cuda(src, torch.float32, "src")
+    dst = _cuda(dst, torch.float32, "dst")
+    pair_offsets = _cuda(pair_offsets, torch.int64, "pair_offsets")
+    mask = _cuda(mask, torch.uint8, "mask")
+    H2 = _cuda(H2, torch.float64, "H2")
+    model_pose = _cuda(model_pose, torch.float64, "model_pose")
+    input_pose = _cuda(input_pose, torch.float64, "input_pose")
+    npairs = pair_offsets.numel() - 1
+    nj = input_pose.shape[-2]
+    shared = model_pose.dim() == 2
+    dev = src.device
+    if picks is not None:
+        picks = _cuda(picks, torch.int32, "picks")
+    with torch.cuda.device(dev):
+        score = torch.empty((npairs,), dtype=torch.float64, device=dev)
+        used = torch.full((npairs, 5), -1, dtype=torch.int32, device=dev)
+        check(lib.hpusm_scene_score_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), _ptr(mask), _ptr(H2), _ptr(model_pose),
+                                          1 if shared else 0, _ptr(input_pose), npairs, nj, float(model_w), float(model_h),
+                                          int(seed), _ptr(picks), _ptr(score), _ptr(used), _stream(dev)))
+    return score, used
+
+
 def feature_scaling_batch(pts):
     """common.feature_scaling on [n, npts, 2] float64 point sets (common.py:688-708)."""
     pts = _cuda(pts, torch.float64, "pts")

@@ -228,6 +228,21 @@ int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n,
 int hpusm_pose_match_pairs(const void* model, const void* input, int64_t n, int is_f64, const double* thresholds,
                            uint8_t* match, float* score, double* detail, void* stream);
 
+/* Scene score of image pairs after RANSAC: urban_scene.match_scene_multi steps 3.1-5 (urban_scene.py:80-145) =
+ * transformation.perspective_correction (transformation.py:22-53) + transformation.affine_multi (:101-173,:413).
+ *   src/dst/pair_offsets/mask as produced by hpusm_segment_matches + hpusm_ransac_homography_batch (src = model side);
+ *   H2 [npairs][9] float64 maps input -> model (NaN = no homography -> score +inf, as urban_scene.py:45-47);
+ *   model_pose [18][2] float64 shared by all pairs (model_pose_shared != 0) or [npairs][njoints][2];
+ *   input_pose [npairs][njoints][2] float64 (undetected joints (0,0)).
+ *   The 5 background matches (thresholds.AMOUNT_BACKGROUND_FEATURES) are ordinals among each pair's inliers: taken from
+ *   picks [npairs][5] if given, else from a counter-based table keyed on (seed, pair) -- the reference uses Python's
+ *   unseeded random.sample (transformation.py:111).  picks_out (optional) receives the ordinals used.
+ *   score [npairs] float64: max normalised distance; 1 when a pair has fewer than 5 inliers (transformation.py:107). */
+int hpusm_scene_score_batch(const float* src, const float* dst, const int64_t* pair_offsets, const uint8_t* mask,
+                            const double* H2, const double* model_pose, int model_pose_shared, const double* input_pose,
+                            int64_t npairs, int njoints, double model_w, double model_h, uint64_t seed,
+                            const int32_t* picks, double* score, int32_t* picks_out, void* stream);
+
 /* Batched min/max normalisation, replaces common.feature_scaling (common.py:688-708) including its quirk that
  * each minimum runs over BOTH coordinates of the rows whose x (resp. y) is non-zero; negatives clamp to 0.
  *   pts, out [n][npts][2] float64. */

@@ -224,3 +224,31 @@ def superimpose_old(inp, model):
     foot = 10 if inp[10][1] >= inp[13][1] else 13
     Z[:, 1] += inp[foot][1] - Z[foot][1]
     return Z, model
+
+
+def perspective_transform32(pts, H):
+    """cv2.perspectiveTransform on float32 points with a float64 3x3 (features.py:77, transformation.py:38)."""
+    p = np.asarray(pts, dtype=np.float32).astype(np.float64).reshape(-1, 2)
+    w = p[:, 0] * H[2, 0] + p[:, 1] * H[2, 1] + H[2, 2]
+    ok = np.abs(w) > np.finfo(np.float64).eps
+    w = np.where(ok, 1.0 / np.where(ok, w, 1.0), 0.0)
+    x = (p[:, 0] * H[0, 0] + p[:, 1] * H[0, 1] + H[0, 2]) * w
+    y = (p[:, 0] * H[1, 0] + p[:, 1] * H[1, 1] + H[1, 2]) * w
+    return np.stack([x, y], 1).astype(np.float32)
+
+
+def scene_score(p_model_good, p_input_good, H2, model_pose, input_pose, model_w, model_h, picks):
+    """urban_scene.match_scene_multi steps 3.1-5 (urban_scene.py:80-145) = transformation.perspective_correction
+    (transformation.py:22-53) + transformation.affine_multi (:101-173,:413) for the given background picks."""
+    p_model_good = np.asarray(p_model_good)
+    if len(p_model_good) < 5:
+        return 1
+    bg_in = perspective_transform32(p_input_good, H2).astype(np.float64)
+    pose_in = perspective_transform32(input_pose, H2).astype(np.float64)
+    model_pts = np.vstack([np.asarray(model_pose, np.float64)] + [p_model_good[i][None].astype(np.float64) for i in picks])
+    input_pts = np.vstack([pose_in] + [bg_in[i][None] for i in picks])
+    _, M = find_transformation(model_pts, input_pts)
+    trans = (np.hstack([input_pts, np.ones((len(input_pts), 1))]) @ M)[:, :2]
+    a = np.stack([model_pts[:, 0] / model_w, model_pts[:, 1] / model_h], 1)
+    b = np.stack([trans[:, 0] / model_w, trans[:, 1] / model_h], 1)
+    return _py_max(euclidean_distances(a, b))

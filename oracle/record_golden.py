@@ -253,6 +253,49 @@ def record_json_parser():
     save("pose_json_parser.npz", raw=np.stack(raws), poses=np.stack(outs), n=np.array(counts))
 
 
+def record_scene_score():
+    """urban_scene.match_scene_multi steps 3.1-5 (urban_scene.py:80-145): transformation.perspective_correction +
+    transformation.affine_multi with random.sample pinned to recorded picks."""
+    import random
+    import urbanscene.transformation as ref_tr
+    import plot_vars
+    poses, _ = load_fixture_poses()
+    full = poses[((poses != 0).any(2)).sum(1) == 18]
+    rng = np.random.default_rng(50)
+    out = {k: [] for k in ("src", "dst", "H2", "model_pose", "input_pose", "picks", "score", "n")}
+    model_img = np.zeros((480, 640), np.uint8)
+    for case in range(16):
+        src, dst, Ht = synth.ransac_pair(120, inlier_ratio=1.0, seed=60 + case, noise=0.7)
+        H2, _ = cv2.findHomography(dst.reshape(-1, 1, 2), src.reshape(-1, 1, 2), cv2.RANSAC, 5.0)
+        model_pose = full[rng.integers(len(full))] * 0.5 + 20.0
+        if case % 4 == 3:
+            model_pose = model_pose.copy(); model_pose[[3, 9]] = 0       # undetected joints
+        pp = np.c_[model_pose, np.ones(18)] @ Ht.T
+        input_pose = pp[:, :2] / pp[:, 2:] + rng.normal(0, 1.5, (18, 2))
+        input_pose[(model_pose == 0).all(1)] = 0
+        p_model_good, p_input_good = src, dst
+        picks = sorted(rng.choice(len(src), 5, replace=False).tolist())
+        (p_trans, pose_trans, _img) = ref_tr.perspective_correction(H2, np.vstack((p_model_good, model_pose)),
+                                                                    np.vstack((p_input_good, input_pose)), model_pose,
+                                                                    input_pose, model_img, model_img, False)
+        only_buildings = p_trans[0:len(p_trans) - 18]
+        plot_vars.input_background_no_correction = p_input_good
+        orig = random.sample
+        random.sample = lambda population, k: list(picks)
+        try:
+            score = ref_tr.affine_multi(p_model_good, only_buildings, model_pose, pose_trans, 480, 640, 480, 640, "g",
+                                        model_img, model_img, input_pose, False)
+        finally:
+            random.sample = orig
+        for k, v in (("src", src), ("dst", dst), ("H2", H2), ("model_pose", model_pose), ("input_pose", input_pose),
+                     ("picks", np.array(picks, np.int32)), ("score", score), ("n", len(src))):
+            out[k].append(v)
+    save("scene_score.npz", src=np.concatenate(out["src"]), dst=np.concatenate(out["dst"]), H2=np.stack(out["H2"]),
+         model_pose=np.stack(out["model_pose"]), input_pose=np.stack(out["input_pose"]), picks=np.stack(out["picks"]),
+         score=np.array(out["score"]), pair_offsets=np.concatenate([[0], np.cumsum(out["n"])]).astype(np.int64),
+         model_wh=np.array([640.0, 480.0]))
+
+
 def record_multi_person():
     """multi_person.find_ordered_matches (multi_person.py:169) on the multi-person fixtures."""
     import posematching.multi_person as ref_mp
@@ -293,7 +336,7 @@ def record_multi_person():
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
-               record_pose, record_multi_person, record_json_parser):
+               record_pose, record_multi_person, record_json_parser, record_scene_score):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

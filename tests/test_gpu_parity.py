@@ -439,3 +439,59 @@ def test_l2_split_engine_near_ties_take_the_exact_fallback(hpusm, cuda_device):
     assert hpusm.engine.knn2_l2_last_fallback_rows() >= 30
     sidx, sdist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_SIMT)
     assert torch.equal(idx, sidx) and torch.equal(dist, sdist)  # both end in the same exact FP32 re-rank
+
+
+def test_scene_score_batch_reference(hpusm, cuda_device):
+    """Batched scene score vs the reference's perspective_correction + affine_multi (recorded, picks pinned), and the
+    seeded picks vs the oracle."""
+    g = load_golden("scene_score.npz")
+    offs = g["pair_offsets"]
+    n = len(g["score"])
+    mask = np.ones(offs[-1], np.uint8)
+    args = (dev(g["src"], cuda_device), dev(g["dst"], cuda_device), dev(offs, cuda_device), dev(mask, cuda_device),
+            dev(g["H2"], cuda_device), dev(g["model_pose"], cuda_device), dev(g["input_pose"], cuda_device), 640.0, 480.0)
+    score, used = hpusm.engine.scene_score_batch(*args, picks=dev(g["picks"], cuda_device))
+    np.testing.assert_allclose(score.cpu().numpy(), g["score"], rtol=1e-6)
+    np.testing.assert_array_equal(used.cpu().numpy(), g["picks"])
+    # seeded picks: distinct ordinals; the score equals the oracle evaluated on those picks; masks are honoured
+    mask2 = mask.copy()
+    mask2[offs[0]:offs[0] + 40] = 0
+    args2 = args[:3] + (dev(mask2, cuda_device),) + args[4:]
+    score, used = hpusm.engine.scene_score_batch(*args2, seed=11)
+    used = used.cpu().numpy()
+    for p in range(n):
+        lo, hi = offs[p], offs[p + 1]
+        keep = mask2[lo:hi].astype(bool)
+        assert len(set(used[p].tolist())) == 5 and used[p].min() >= 0 and used[p].max() < keep.sum()
+        ref = pose_oracle.scene_score(g["src"][lo:hi][keep], g["dst"][lo:hi][keep], g["H2"][p], g["model_pose"][p],
+                                      g["input_pose"][p], 640.0, 480.0, used[p])
+        np.testing.assert_allclose(score[p].item(), ref, rtol=1e-6)
+    # sentinels: no homography -> inf, fewer than 5 inliers -> 1
+    H2 = g["H2"].copy(); H2[1] = np.nan
+    mask3 = mask.copy(); mask3[offs[2]:offs[3]] = 0; mask3[offs[2]:offs[2] + 4] = 1
+    score, _ = hpusm.engine.scene_score_batch(args[0], args[1], args[2], dev(mask3, cuda_device), dev(H2, cuda_device), args[5],
+                                              args[6], 640.0, 480.0)
+    assert np.isinf(score[1].item()) and score[2].item() == 1.0
+
+
+def test_scene_retrieval_with_scores(hpusm, cuda_device):
+    """The whole scene stage for one query against an image database, scores included: planted views score low."""
+    q_desc, q_kp, db_desc, db_kp, offs, planted = _scene_database(hpusm)
+    nimg = len(offs) - 1
+    rng = np.random.default_rng(3)
+    qpose = hpusm.synth.CANONICAL_POSE * 0.8 + 30.0
+    db_poses = rng.uniform(50, 400, (nimg, 18, 2))
+    out = hpusm.retrieval.scene_retrieval(dev(q_desc, cuda_device), dev(q_kp, cuda_device), dev(db_desc, cuda_device),
+                                          dev(db_kp, cuda_device), dev(offs, cuda_device), nhyp=500, seed=5,
+                                          query_pose=dev(qpose, cuda_device), db_poses=dev(db_poses, cuda_device),
+                                          query_size=(640.0, 480.0))
+    score, valid = out["score"].cpu().numpy(), out["valid"].cpu().numpy().astype(bool)
+    assert np.isinf(score[~valid]).all() and np.isfinite(score[valid]).all() and valid[planted[0]] and valid[planted[1]]
+    # oracle on the same picks
+    H2, picks = out["H2"].cpu().numpy(), out["picks"].cpu().numpy()
+    po, src, dst, mask = (out[k].cpu().numpy() for k in ("pair_offsets", "src", "dst", "mask"))
+    for p in (planted[0], planted[1]):
+        keep = mask[po[p]:po[p + 1]].astype(bool)
+        ref = pose_oracle.scene_score(src[po[p]:po[p + 1]][keep], dst[po[p]:po[p + 1]][keep], H2[p], qpose, db_poses[p],
+                                      640.0, 480.0, picks[p])
+        np.testing.assert_allclose(score[p], ref, rtol=1e-6)

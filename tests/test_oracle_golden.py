@@ -164,3 +164,14 @@ def test_pose_decide_matches_reference():
         A, d, sh = r[:9].reshape(3, 3), r[9], r[10]
         assert pose_oracle.decide_torso_shoulders_incl(d, A, 0.236, 19.8, sh, 0.125) == bool(r[11])
         assert pose_oracle.decide_legs(d, A, 0.082, 24) == bool(r[12])
+
+
+def test_scene_score_matches_reference():
+    """perspective_correction + affine_multi (urban_scene.py:80-145) with the recorded background picks."""
+    g = load_golden("scene_score.npz")
+    offs = g["pair_offsets"]
+    for p in range(len(g["score"])):
+        lo, hi = offs[p], offs[p + 1]
+        s = pose_oracle.scene_score(g["src"][lo:hi], g["dst"][lo:hi], g["H2"][p], g["model_pose"][p], g["input_pose"][p],
+                                    g["model_wh"][0], g["model_wh"][1], g["picks"][p])
+        np.testing.assert_allclose(s, g["score"][p], rtol=1e-8)
