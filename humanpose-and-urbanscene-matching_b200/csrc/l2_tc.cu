@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "l2_internal.cuh"
 #include "tc_ptx.cuh"
@@ -138,6 +139,10 @@ __device__ __forceinline__ void tc_process32(const uint32_t (&acc)[32], int col,
 }
 
 // part_idx [splits][nq][2].  `gate` (device int): the kernel does nothing unless *gate == 0.
+// PAIR = true: launched as clusters of two CTAs that sweep the same database tiles in lock-step on two different query
+// blocks; each CTA fetches HALF of every database tile and TMA-multicasts it into both CTAs' shared memory, so the
+// L2 -> SM traffic of the sweep halves.  A stage is released by the MMA commits of BOTH CTAs (multicast arrive).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qa,
                   const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt,
@@ -160,7 +165,7 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, PAIR ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 4); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -172,10 +177,18 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_units = q_blocks * splits;
+  // Work assignment.  Single: unit u = (split, query block), CTA b takes u = b, b + grid, ...  Pair: a cluster takes a
+  // PAIR of query blocks (2 qp + rank) of one split; an odd tail gives the second CTA a block beyond the queries (its
+  // TMA reads zeros, its rows are never written) so that it still serves its half of the database tiles.
+  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;
+  const int q_groups = PAIR ? (q_blocks + 1) / 2 : q_blocks;
+  const int total_units = q_groups * splits;
+  const int u_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int u_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -185,8 +198,8 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qa) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ta) : "memory");
       uint32_t it = 0, un = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
-        const int split = u / q_blocks, qb = u - split * q_blocks;
+      for (int u = u_first; u < total_units; u += u_step, ++un) {
+        const int split = u / q_groups, qb = PAIR ? 2 * (u - split * q_groups) + rank : u - split * q_groups;
         const int64_t t_begin = (int64_t)split * rows_per_split;
         const int64_t t_end = min(nt, t_begin + rows_per_split);
         const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
@@ -205,9 +218,17 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           mbar_wait(empty + s, ((it / TC_STAGES) & 1) ^ 1);
           mbar_expect_tx(full + s, TC_B_BYTES);
           const int row0 = (int)(t_begin + (int64_t)j * TC_TN);
-          tma_load_2d(smem_b + s * TC_B_BYTES, &map_t, full + s, 0, row0);
-          tma_load_2d(smem_b + s * TC_B_BYTES + TC_BHALF_BYTES, &map_t, full + s, 64, row0);
-          tma_load_2d(smem_b + s * TC_B_BYTES + 2 * TC_BHALF_BYTES, &map_ta, full + s, TC_D, row0);
+          uint8_t* bs = smem_b + s * TC_B_BYTES;
+          if (PAIR) {  // my 128 of the tile's 256 rows, into both CTAs (the maps carry 128-row boxes here)
+            const int r0 = row0 + rank * 128;
+            tma_load_2d_mc(bs + rank * (TC_BHALF_BYTES / 2), &map_t, full + s, 0, r0, 3);
+            tma_load_2d_mc(bs + TC_BHALF_BYTES + rank * (TC_BHALF_BYTES / 2), &map_t, full + s, 64, r0, 3);
+            tma_load_2d_mc(bs + 2 * TC_BHALF_BYTES + rank * (TC_BAUG_BYTES / 2), &map_ta, full + s, TC_D, r0, 3);
+          } else {
+            tma_load_2d(bs, &map_t, full + s, 0, row0);
+            tma_load_2d(bs + TC_BHALF_BYTES, &map_t, full + s, 64, row0);
+            tma_load_2d(bs + 2 * TC_BHALF_BYTES, &map_ta, full + s, TC_D, row0);
+          }
         }
       }
     }
@@ -216,8 +237,8 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (lane == 0) {
       uint32_t it = 0, un = 0;
       const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
-        const int split = u / q_blocks;
+      for (int u = u_first; u < total_units; u += u_step, ++un) {
+        const int split = u / q_groups;
         const int64_t t_begin = (int64_t)split * rows_per_split;
         const int64_t t_end = min(nt, t_begin + rows_per_split);
         const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
@@ -242,7 +263,8 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         umma_desc_sw32(b_addr + s * TC_B_BYTES + 2 * TC_BHALF_BYTES), TC_IDESC, 1u);
             tc_commit(tmem_full + m);   // this query tile's accumulator is ready for its epilogue warps
           }
-          tc_commit(empty + s);         // the stage may be refilled once both blocks have read it
+          if (PAIR) tc_commit_mc(empty + s, 3);  // ... in BOTH CTAs: either producer may overwrite either copy
+          else tc_commit(empty + s);    // the stage may be refilled once both blocks have read it
         }
         tc_commit(a_empty);           // the query tiles may be replaced
       }
@@ -251,8 +273,8 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ===== epilogue: fused top-2 =====
     const int ew = warp - 4, quarter = ew & 3, m = ew >> 2;
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int split = u / q_blocks, qb = u - split * q_blocks;
+    for (int u = u_first; u < total_units; u += u_step) {
+      const int split = u / q_groups, qb = PAIR ? 2 * (u - split * q_groups) + rank : u - split * q_groups;
       const int64_t t_begin = (int64_t)split * rows_per_split;
       const int64_t t_end = min(nt, t_begin + rows_per_split);
       const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
@@ -294,6 +316,7 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // nobody leaves while the peer can still multicast into this CTA
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
@@ -415,20 +438,51 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B, TC_TN);
   if (rc != HPUSM_OK) return rc;
 
+  // HPUSM_L2_PAIR=1 selects the 2-CTA cluster variant (database tiles multicast to both CTAs); default: single CTAs.
+  static const bool use_pair = []() { const char* e = getenv("HPUSM_L2_PAIR"); return e && e[0] == '1'; }();
+  if (use_pair) {
+    rc = tc_make_map(&map_t, tb, L.nt_pad, TC_KA, 64, CU_TENSOR_MAP_SWIZZLE_128B, 128);
+    if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B, 128);
+    if (rc != HPUSM_OK) return rc;
+  }
   static bool attr_done[64] = {false};
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_done[dev] = true;
   }
   const int q_blocks = (int)((nq + TC_QB - 1) / TC_QB);
   int64_t rows_per_split = (nt + L.splits_tc - 1) / L.splits_tc;
   rows_per_split = (rows_per_split + TC_TN - 1) / TC_TN * TC_TN;
-  const int units = q_blocks * L.splits_tc;
-  const int grid = units < sm_count() ? units : sm_count();
-  HPUSM_LAUNCH_TIMED(l2_tc_knn2_kernel, grid, TC_THREADS, TC_SMEM_BYTES, st, map_q, map_qa, map_t, map_ta, nq, nt, q_blocks,
-                     L.splits_tc, rows_per_split, part, flag);
+  if (use_pair) {
+    const int units = ((q_blocks + 1) / 2) * L.splits_tc;
+    int clusters = sm_count() / 2;
+    if (units < clusters) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int splits_i = L.splits_tc;
+    const int* gate = flag;
+    profile_mark(st, true);
+    HPUSM_CUDA_OK(cudaLaunchKernelEx(&cfg, l2_tc_knn2_kernel<true>, map_q, map_qa, map_t, map_ta, nq, nt, q_blocks, splits_i,
+                                     rows_per_split, part, gate));
+    profile_mark(st, false);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    const int units = q_blocks * L.splits_tc;
+    const int grid = units < sm_count() ? units : sm_count();
+    HPUSM_LAUNCH_TIMED(l2_tc_knn2_kernel<false>, grid, TC_THREADS, TC_SMEM_BYTES, st, map_q, map_qa, map_t, map_ta, nq, nt, q_blocks,
+                       L.splits_tc, rows_per_split, part, flag);
+  }
   HPUSM_CHECK_LAUNCH();
   *resolved_mode = HPUSM_L2_TC_INT;
   *fallback_rows = 0;
