@@ -296,7 +296,8 @@ def run_ours(args, rank, world, device):
     k_ms = kernel_ms / max(kernel_n, 1)
     flops_per_launch = FLOP_PER_PAIR * float(nq) * float(nt) * args.steps / max(kernel_n, 1)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    mode = {0: "auto", 1: "simt-fp32", 2: "tcgen05-bf16-exact-int", 3: "tcgen05-bf16-split"}.get(eng.knn2_l2_last_mode(), "?")
+    mode = {0: "auto", 1: "simt-fp32", 2: "tcgen05-bf16-exact-int", 3: "tcgen05-bf16-split",
+            4: "tcgen05-i8-exact-int"}.get(eng.knn2_l2_last_mode(), "?")
     if mode == "tcgen05-bf16-split":
         pass  # roofline still counts the algorithmic 256 FLOP per pair; the engine executes 25/8 of that on the tensor pipe
     out = {

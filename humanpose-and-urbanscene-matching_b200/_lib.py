@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libhpusm.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = -1, -2, -3, -4
-L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT = 0, 1, 2, 3
+L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT, L2_TC_I8 = 0, 1, 2, 3, 4
 POSE_DETAIL = 8 + 27 + 44
 
 
@@ -78,6 +78,7 @@ SIGNATURES = {
     "hpusm_pose_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "hpusm_microbench_popc": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_lop3": (_i32, [_i64, _i32, _i64, _p, _p]),
+    "hpusm_microbench_minmax": (_i32, [_i32, _i64, _i32, _i64, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

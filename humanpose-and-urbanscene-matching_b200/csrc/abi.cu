@@ -84,6 +84,30 @@ __global__ void lop3_microbench_kernel(int64_t iters, uint32_t* sink) {
   if (r == 0xffffffffu && k0 == 7u) sink[0] = r;
 }
 
+// Min/max issue rates (the fused top-2 epilogues are max-scans): 8 independent chains of one of
+//   OP 0: 3-input s32 max (VIMNMX3)   1: 3-input f32 max (FMNMX3)   2: 2-input s32 max   3: 2-input f32 max
+template <int OP>
+__global__ void minmax_microbench_kernel(int64_t iters, uint32_t* sink) {
+  uint32_t a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (threadIdx.x * 2654435761u + blockIdx.x * 40503u + i * 977u) & 0x3fffffffu;
+  const uint32_t k1 = a[1] * 17u & 0x3fffffffu;
+  for (int64_t it = 0; it < iters; it += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // each value is refreshed from its neighbours: nothing for the compiler to fold
+      const uint32_t x = a[(i + 1) & 7], y = a[(i + 2) & 7];
+      if (OP == 0) asm volatile("max.s32 %0, %0, %1;\n\tmax.s32 %0, %0, %2;" : "+r"(a[i]) : "r"(x), "r"(y));  // ptxas fuses: VIMNMX3
+      if (OP == 1) asm volatile("max.f32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(x), "r"(y));
+      if (OP == 2) asm volatile("max.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(x));
+      if (OP == 3) asm volatile("max.f32 %0, %0, %1;" : "+r"(a[i]) : "r"(x));
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r ^= a[i];
+  if (r == 0xffffffffu && k1 == 7u) sink[0] = r;
+}
+
 }  // namespace hpusm
 
 using namespace hpusm;
@@ -148,6 +172,18 @@ int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* 
   HPUSM_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,
                 "hpusm_microbench_lop3: bad arguments");
   HPUSM_LAUNCH(lop3_microbench_kernel, (unsigned)blocks, threads, 0, as_stream(stream), iters, sink);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_microbench_minmax(int op, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream) {
+  HPUSM_REQUIRE(op >= 0 && op <= 3 && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,
+                "hpusm_microbench_minmax: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (op == 0) { HPUSM_LAUNCH(minmax_microbench_kernel<0>, (unsigned)blocks, threads, 0, st, iters, sink); }
+  else if (op == 1) { HPUSM_LAUNCH(minmax_microbench_kernel<1>, (unsigned)blocks, threads, 0, st, iters, sink); }
+  else if (op == 2) { HPUSM_LAUNCH(minmax_microbench_kernel<2>, (unsigned)blocks, threads, 0, st, iters, sink); }
+  else { HPUSM_LAUNCH(minmax_microbench_kernel<3>, (unsigned)blocks, threads, 0, st, iters, sink); }
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

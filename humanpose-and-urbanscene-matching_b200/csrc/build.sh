@@ -7,15 +7,19 @@ OUT=../libhpusm.so
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
        --expt-relaxed-constexpr -cudart static)
 OBJS=()
+PIDS=()
 for f in *.cu; do
   o="build/${f%.cu}.o"
   mkdir -p build
   if [[ ! -f "$o" || "$f" -nt "$o" || common.cuh -nt "$o" || tc_ptx.cuh -nt "$o" || l2_internal.cuh -nt "$o" || ../../include/hpusm.h -nt "$o" ]]; then
     echo "nvcc $f"
     "$NVCC" "${FLAGS[@]}" ${HPUSM_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
+    PIDS+=($!)
   fi
   OBJS+=("$o")
 done
-wait
+for p in "${PIDS[@]:-}"; do   # a failed compile must fail the build, not link a stale object
+  if [[ -n "$p" ]] && ! wait "$p"; then echo "build.sh: a compile failed" >&2; rm -f "$OUT"; exit 1; fi
+done
 "$NVCC" -shared -cudart static "${OBJS[@]}" -o "$OUT" -lpthread -ldl
 echo "built $(readlink -f $OUT)"

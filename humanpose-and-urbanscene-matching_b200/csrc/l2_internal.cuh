@@ -24,4 +24,9 @@ size_t l2_tc_split_workspace_bytes(int64_t nq, int64_t nt);
 int l2_tc_split_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_t* idx, float* dist, void* ws,
                      size_t ws_bytes, cudaStream_t st, int64_t* fallback_rows);
 
+// l2_tc_i8.cu (tcgen05 kind::i8 engine for integer descriptors in [0,255]; *eligible = 0 when the data does not fit)
+size_t l2_tc_i8_workspace_bytes(int64_t nq, int64_t nt);
+int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_t* idx, float* dist, void* ws,
+                  size_t ws_bytes, cudaStream_t st, bool require, int* eligible);
+
 }  // namespace hpusm

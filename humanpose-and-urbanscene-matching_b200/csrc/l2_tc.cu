@@ -340,16 +340,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows][cols] bf16 row-major; box = `box_cols` columns x `box_rows` rows with the given swizzle; out-of-range rows read 0
+// [rows][cols] bf16 or u8 row-major; box = `box_cols` columns x `box_rows` rows with the given swizzle; out-of-range
+// rows read 0
 int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_cols, CUtensorMapSwizzle swizzle,
-                int box_rows) {
+                int box_rows, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   HPUSM_REQUIRE(fn, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__nv_bfloat16)};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (cuuint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HPUSM_REQUIRE(r == CUDA_SUCCESS, HPUSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -393,9 +395,11 @@ static TcLayout tc_layout(int64_t nq, int64_t nt, int mode) {
 
 size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode) {
   if (d != TC_D || nq <= 0 || nt <= 0) return 256;
-  const size_t a = mode == HPUSM_L2_TC_SPLIT ? 0 : tc_layout(nq, nt, mode).total;
+  const size_t a = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_INT) ? tc_layout(nq, nt, mode).total : 0;
   const size_t b = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_SPLIT) ? l2_tc_split_workspace_bytes(nq, nt) : 0;
-  return a > b ? a : b;
+  const size_t c = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_I8) ? l2_tc_i8_workspace_bytes(nq, nt) : 0;
+  const size_t ab = a > b ? a : b;
+  return ab > c ? ab : c;
 }
 
 int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist, void* ws,
@@ -404,6 +408,17 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   if (mode == HPUSM_L2_TC_SPLIT) {
     *resolved_mode = HPUSM_L2_TC_SPLIT;
     return l2_tc_split_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
+  }
+  if (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_I8) {
+    // u8 operands on the integer tensor pipe when every value is an integer in [0,255] (what cv2 SIFT produces)
+    int eligible = 0;
+    const int rc8 = l2_tc_i8_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, mode == HPUSM_L2_TC_I8, &eligible);
+    if (rc8 != HPUSM_OK) return rc8;
+    if (eligible) {
+      *resolved_mode = HPUSM_L2_TC_I8;
+      *fallback_rows = 0;
+      return HPUSM_OK;
+    }
   }
   const TcLayout L = tc_layout(nq, nt, mode);
   HPUSM_REQUIRE(ws_bytes >= L.total, HPUSM_ERR_WORKSPACE, "l2 tensor engine: workspace needs %zu bytes, got %zu", L.total,

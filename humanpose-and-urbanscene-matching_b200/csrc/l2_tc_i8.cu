@@ -1,0 +1,497 @@
+// K1 (integer tensor-core engine): brute-force L2 kNN (k=2) on tcgen05 kind::i8, sm_100a only.
+//
+// Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) at reference urbanscene/features.py:59 for what SIFT actually
+// produces: descriptors whose 128 values are integers 0..255 (cv2 stores them as float32).  Such rows fit the u8
+// operands of the integer MMA, whose s32 accumulation is exact and which retires K=32 per instruction at twice the
+// bf16 rate; a database row costs 160 bytes of operand instead of 288.
+//
+//   ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t      ->  per query, order the database by  K = 2 q.t - ||t||^2  (largest first)
+//
+// u8 operands cannot carry the factor 2, so the accumulator holds  s = q.t + (HB - (||t||^2 >> 1))  (the bracket is
+// folded into the contraction through 32 augmentation columns: A = [q | 1 128 128 ...], B = [t | d0 d1 d2 ...] with
+// HB - h = d0 + 128 (d1 + ... + d31)) and  K + 2 HB = 2 s - (||t||^2 & 1).  The epilogue max-scans s; only a column
+// with 2 s > K1 (the running second best) can matter, and for those few the comparison is made on the exact K with the
+// parity bit taken from a bit array (each epilogue warp keeps the 64 bits of its columns in registers).  The result is the exact top-2 on (K, index), ties to the lower index
+// as OpenCV resolves them; the candidates then go through l2_rerank_finalize (exact FP32 distances from the ORIGINAL
+// float32 rows).
+//
+// The prep kernel verifies the value range for every row (integers in [0,255], ||t||^2 < 2 HB); HPUSM_L2_AUTO falls
+// through to the bf16 engines (l2_tc.cu, l2_tc_split.cu) when it does not hold.
+//
+// Kernel shape: as l2_tc.cu (persistent CTA per SM, TMA producer warp, MMA issuer warp, two 128-query tiles
+// ping-ponging on two 256-column TMEM accumulators), with a 4-stage ring of [256 x 160] u8 tiles and 16 epilogue warps
+// (the integer MMA block of a tile lasts only 640 cycles, so the accumulator read-out has to be twice as parallel).
+#include <cuda.h>
+#include <limits.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include "common.cuh"
+#include "l2_internal.cuh"
+#include "tc_ptx.cuh"
+
+namespace hpusm {
+
+constexpr int I8_D = 128;
+constexpr int I8_QB = 256;            // queries per unit (two M=128 query tiles)
+constexpr int I8_TN = 128;            // database rows per tile (MMA N)
+constexpr int I8_STAGES = 8;
+constexpr int I8_THREADS = 640;       // 4 service warps + 16 epilogue warps
+constexpr int I8_CGS = 4;             // column groups of 32 per 128-column accumulator (one per epilogue warp and lane quarter)
+constexpr int I8_NBUF = 3;            // accumulators in rotation
+constexpr int I8_KA = 160;            // operand row: 128 descriptor bytes + 32 augmentation bytes
+constexpr int I8_A_COLS = 40;         // a query tile in tensor memory: 160 bytes per row = 40 32-bit columns
+constexpr int I8_ACC_COL0 = 128;      // tensor memory: query tiles in columns [0, 80), accumulators at 128, 256, 384
+constexpr int I8_BMAIN_BYTES = I8_TN * 128;             // [128 rows][128 u8] swizzle-128B slab, 16 KB
+constexpr int I8_BAUG_BYTES = I8_TN * 32;               // [128 rows][32 u8] swizzle-32B slab, 4 KB
+constexpr int I8_B_BYTES = I8_BMAIN_BYTES + I8_BAUG_BYTES;      // 20 KB per stage
+constexpr int I8_SMEM_BYTES = I8_STAGES * I8_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                              I8_QB * 4 /*shared thresholds*/;
+constexpr int I8_HB = 1000000;        // bias of the folded half-norm; ||t||^2 < 2 HB is required
+
+// Instruction descriptor: D = S32, A = B = U8, both K-major, N = 128, M = 128.
+constexpr uint32_t I8_IDESC = (2u << 4) | ((uint32_t)(I8_TN >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// ---- operand preparation --------------------------------------------------------------------------------
+// One warp per row: float32 -> u8 operand row of 160 bytes and the range check (flag[0] |= 1 when a value is not an
+// integer in [0,255] or a database norm exceeds 2 HB).
+//   query side    (is_db == 0): [q | 1 128 128 ... 128]
+//   database side (is_db == 1): [t | d0 d1 ... d31] with HB - (||t||^2 >> 1) = d0 + 128 (d1 + ... + d31), d0 < 128;
+//                               bit `row` of par = ||t||^2 & 1.  Rows n..n_pad are zero: s = 0, below or tied with every real
+//                               row, and their index is the highest.
+__global__ void __launch_bounds__(256)
+l2_i8_prep_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int is_db, uint8_t* __restrict__ xb,
+                  uint32_t* __restrict__ par, int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  bool bad = false;
+  float s = 0.f;
+  if (row < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * I8_D) + lane);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bad |= !(f[i] >= 0.f && f[i] <= 255.f) || f[i] != rintf(f[i]);
+      s = fmaf(f[i], f[i], s);
+    }
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int tn = bad ? 0 : (int)s;  // exact: an integer below 2^24 whenever the row passed the check
+  const int h = tn >> 1;
+  if (is_db && h >= I8_HB) bad = true;  // strict: HB - h >= 1 keeps every real row above the zero padding
+  uint32_t packed = 0;
+  if (!bad) packed = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
+  uint8_t* dst = xb + row * I8_KA;
+  reinterpret_cast<uint32_t*>(dst)[lane] = packed;
+  // augmentation byte `lane`
+  uint32_t a;
+  if (!is_db) a = lane == 0 ? 1u : 128u;
+  else if (row >= n || bad) a = 0u;
+  else {
+    const int rem = I8_HB - h;
+    if (lane == 0) a = (uint32_t)(rem & 127);
+    else {
+      int m = (rem >> 7) - 255 * (lane - 1);
+      a = (uint32_t)(m < 0 ? 0 : (m > 255 ? 255 : m));
+    }
+  }
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w |= __shfl_sync(0xffffffffu, a, (4 * lane + i) & 31) << (8 * i);
+  if (lane < 8) reinterpret_cast<uint32_t*>(dst + I8_D)[lane] = w;
+  if (lane == 0) {
+    if (is_db && row < n && !bad && (tn & 1)) atomicOr(par + (row >> 5), 1u << (row & 31));  // par is zeroed by the host
+    if (bad) atomicOr(flag, 1);
+  }
+}
+
+// ---- the contraction + fused top-2 ------------------------------------------------------------------------
+struct I8Top2 {
+  int k0, k1;  // exact keys 2 s - parity of the best and second best so far
+  int thr;     // k1 >> 1: a column can only matter when its s exceeds this
+  int i0, i1;
+};
+
+__device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
+
+// `sh`: this row's threshold shared by the four warps that scan different column groups of the same row.
+__device__ __forceinline__ void i8_insert(I8Top2& t, int s, int col, int parity, int* sh) {
+  const int k = 2 * s - parity;
+  if (k > t.k1) {  // strict: candidates reach a thread in increasing index order within equal keys
+    if (k > t.k0) { t.k1 = t.k0; t.i1 = t.i0; t.k0 = k; t.i0 = col; }
+    else { t.k1 = k; t.i1 = col; }
+    t.thr = max(t.thr, t.k1 >> 1);
+    atomicMax(sh, t.k1 >> 1);
+  }
+}
+
+// 32 accumulator columns of one query row.  Fast path: a 3-input max tree and one compare.  When some column beats the
+// threshold (rare once the sweep is under way) the candidates are pulled out one at a time, largest s first and the
+// lower column first among equals, by a max tree over (s << 5 | 31 - j): a short loop instead of 32 unrolled
+// insertions, because rarely executed straight-line code runs at instruction-fetch speed and every warp of the CTA
+// waits for the slowest one at the next accumulator hand-over.
+// `pbits`: parity bits of these 32 columns (bit j = column col + j).
+__device__ __forceinline__ void i8_process32(const uint32_t (&acc)[32], int col, I8Top2& t, uint32_t pbits, int* sh) {
+  int m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = imax3((int)acc[3 * i], (int)acc[3 * i + 1], (int)acc[3 * i + 2]);
+  m[10] = max((int)acc[30], (int)acc[31]);
+  const int a = imax3(m[0], m[1], m[2]), b = imax3(m[3], m[4], m[5]), c = imax3(m[6], m[7], m[8]);
+  const int hi = max(imax3(a, b, c), max(m[9], m[10]));
+  if (hi > t.thr) {
+    int last = INT_MAX;
+#pragma unroll 1
+    for (;;) {
+      int pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int v = ((int)acc[j] << 5) + (31 - j);
+        pk[j] = v < last ? v : INT_MIN;
+      }
+      int r[11];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) r[i] = imax3(pk[3 * i], pk[3 * i + 1], pk[3 * i + 2]);
+      r[10] = max(pk[30], pk[31]);
+      const int best = max(imax3(imax3(r[0], r[1], r[2]), imax3(r[3], r[4], r[5]), imax3(r[6], r[7], r[8])), max(r[9], r[10]));
+      const int sb = best >> 5;
+      if (sb <= t.thr) break;
+      const int j = 31 - (best & 31);
+      i8_insert(t, sb, col + j, (int)((pbits >> j) & 1u), sh);
+      last = best;
+    }
+  }
+}
+
+// tcgen05.st: 8 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One lane of the (converged) warp, chosen by the hardware.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (query rows) is read from tensor memory
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// part_idx [splits * I8_CGS][nq][2];  qu [nq][160] u8 operand rows of the queries
+__global__ void __launch_bounds__(I8_THREADS, 1)
+l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtensorMap map_t,
+                  const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt, int q_blocks, int splits,
+                  int64_t rows_per_split, const uint32_t* __restrict__ par, int32_t* __restrict__ part_idx) {
+  extern __shared__ uint8_t i8_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem;                          // [stages][16 KB | 4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + I8_STAGES * I8_B_BYTES);
+  uint64_t* full = bars;                                     // [stages]  TMA -> MMA
+  uint64_t* empty = bars + I8_STAGES;                        // [stages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * I8_STAGES;                // [NBUF]    MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * I8_STAGES + I8_NBUF;     // [NBUF]    epilogue -> MMA
+  uint64_t* a_ready = bars + 2 * I8_STAGES + 2 * I8_NBUF;    // the unit's query rows are in tensor memory
+  uint64_t* a_free = bars + 2 * I8_STAGES + 2 * I8_NBUF + 1; // all MMAs of the unit retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 2 * I8_NBUF + 2);
+  int* thr_sh = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 query tiles][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int b = 0; b < I8_NBUF; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 16); }
+    mbar_init(a_ready, 16);
+    mbar_init(a_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_units = q_blocks * splits;
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring of database tiles =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_t) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ta) : "memory");
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u / q_blocks;
+        const int64_t t_begin = (int64_t)split * rows_per_split;
+        const int64_t t_end = min(nt, t_begin + rows_per_split);
+        const int tiles = (int)((t_end - t_begin + I8_TN - 1) / I8_TN);
+        for (int j = 0; j < tiles; ++j, ++it) {
+          const int s = it % I8_STAGES;
+          mbar_wait(empty + s, ((it / I8_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full + s, I8_B_BYTES);
+          const int row0 = (int)(t_begin + (int64_t)j * I8_TN);
+          uint8_t* bs = smem_b + s * I8_B_BYTES;
+          tma_load_2d(bs, &map_t, full + s, 0, row0);
+          tma_load_2d(bs + I8_BMAIN_BYTES, &map_ta, full + s, I8_D, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // The whole warp walks the loop and one ELECTED lane issues: with `elect.sync` ptxas knows a single lane is active
+    // and emits the tcgen05 instructions directly; behind a plain `lane == 0` test it wraps every one of them in a
+    // serialising loop, and at N = 128 (64 tensor cycles per instruction) that loop was the bottleneck.
+    uint32_t it = 0, un = 0, buf = 0, buf_phase = 0;
+    const uint32_t b_addr = smem_u32(smem_b);
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
+      const int split = u / q_blocks;
+      const int64_t t_begin = (int64_t)split * rows_per_split;
+      const int64_t t_end = min(nt, t_begin + rows_per_split);
+      const int tiles = (int)((t_end - t_begin + I8_TN - 1) / I8_TN);
+      mbar_wait(a_ready, un & 1);
+      tc_fence_after();
+      for (int j = 0; j < tiles; ++j, ++it) {
+        const int s = it % I8_STAGES;
+        mbar_wait(full + s, (it / I8_STAGES) & 1);
+        const uint64_t bdesc = umma_desc_sw128(b_addr + s * I8_B_BYTES);
+        const uint64_t bdesc_aug = umma_desc_sw32(b_addr + s * I8_B_BYTES + I8_BMAIN_BYTES);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mbar_wait(tmem_empty + buf, buf_phase ^ 1);   // the epilogue has read this accumulator out
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + (uint32_t)(I8_ACC_COL0 + buf * I8_TN);
+          const uint32_t a_col = tmem_base + (uint32_t)(m * I8_A_COLS);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < I8_D / 32; ++k)   // +2 in the descriptor's address field = 32 bytes along K
+              tc_mma_i8_ts(d_addr, a_col + k * 8, bdesc + (uint64_t)(2 * k), I8_IDESC, k > 0 ? 1u : 0u);
+            // fifth step: the augmentation columns add HB - (||t||^2 >> 1)
+            tc_mma_i8_ts(d_addr, a_col + 32, bdesc_aug, I8_IDESC, 1u);
+            tc_commit(tmem_full + buf);
+          }
+          __syncwarp();
+          if (++buf == I8_NBUF) { buf = 0; buf_phase ^= 1; }
+        }
+        if (elect_one()) tc_commit(empty + s);
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(a_free);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: fused top-2 =====
+    // An accumulator (one 128-query tile x 128 database rows) is only free for its next MMA block once it has been
+    // read out, tcgen05.ld has a long latency and tensor memory reads run at 64 B/clk per SM sub-partition.  So ALL
+    // 16 warps serve EVERY accumulator: warp -> (TMEM lane quarter = warp % 4, column group cg = 32 of the 128
+    // columns); when an accumulator is ready every warp pulls its 32 columns, releases it, and only then scans.
+    // Three accumulators rotate, so the tensor pipe always has one to fill while another is being read out.
+    // A thread carries two running top-2 states (its row in query tile 0 and in tile 1) over its column group; the
+    // groups are separate candidate parts.
+    const int ew = warp - 4, quarter = ew & 3, cg = ew >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t un = 0, buf = 0, buf_phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
+      const int split = u / q_blocks, qb = u - split * q_blocks;
+      const int64_t t_begin = (int64_t)split * rows_per_split;
+      const int64_t t_end = min(nt, t_begin + rows_per_split);
+      const int tiles = (int)((t_end - t_begin + I8_TN - 1) / I8_TN);
+      // -- the unit's query rows go into tensor memory: thread = row, 40 words = [q | augmentation] (MMA operand A) --
+      {
+        const int am = cg & 1, ahalf = cg >> 1;  // warp (quarter, cg) stores words [20 ahalf, 20 ahalf + 20) of tile am's rows
+        const int64_t row = (int64_t)qb * I8_QB + am * 128 + quarter * 32 + lane;
+        uint32_t w[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) w[i] = 0u;
+        if (row < nq) {
+          const uint4* src = reinterpret_cast<const uint4*>(qu + row * I8_KA) + ahalf * 5;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const uint4 v = __ldg(src + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+          }
+        }
+        mbar_wait(a_free, (un & 1) ^ 1);   // the previous unit's MMAs no longer read the old rows
+        tc_fence_after();
+        const uint32_t a_addr = lane_base + (uint32_t)(am * I8_A_COLS + ahalf * 20);
+        uint32_t g0[8], g1[8], g2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { g0[i] = w[i]; g1[i] = w[8 + i]; g2[i] = w[16 + i]; }
+        tc_st8(a_addr, g0);
+        tc_st8(a_addr + 8, g1);
+        // words 16..19 of this half: a 4-column store
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_addr + 16), "r"(g2[0]), "r"(g2[1]),
+                     "r"(g2[2]), "r"(g2[3])
+                     : "memory");
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+      I8Top2 top[2];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        top[m].k0 = top[m].k1 = INT_MIN;
+        top[m].thr = INT_MIN >> 1;
+        top[m].i0 = top[m].i1 = -1;
+      }
+      // The four column-group warps of a row share their thresholds: each keeps its own top-2, but a column is only
+      // looked at when it could beat the best second-best key any of them holds (minus one, so that equal keys still
+      // reach their own list and the final re-rank settles the index order).
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // everybody is done with the previous unit's thresholds
+      if (cg == 0) { thr_sh[quarter * 32 + lane] = INT_MIN >> 1; thr_sh[128 + quarter * 32 + lane] = INT_MIN >> 1; }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // parity bits of this warp's 32 columns, fetched one tile ahead so that an insertion never waits on memory
+      uint32_t pb_next = __ldg(par + (((int)t_begin + cg * 32) >> 5));
+      for (int j = 0; j < tiles; ++j) {
+        const int col0 = (int)(t_begin + (int64_t)j * I8_TN) + cg * 32;
+        const uint32_t pb = pb_next;
+        if (j + 1 < tiles) pb_next = __ldg(par + ((col0 + I8_TN) >> 5));
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          uint32_t acc[32];
+          int* sh = thr_sh + m * 128 + quarter * 32 + lane;
+          const int shared_thr = *reinterpret_cast<volatile int*>(sh);
+          mbar_wait(tmem_full + buf, buf_phase);
+          tc_fence_after();
+          tc_ld32(lane_base + (uint32_t)(I8_ACC_COL0 + buf * I8_TN + cg * 32), acc);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + buf);
+          if (++buf == I8_NBUF) { buf = 0; buf_phase ^= 1; }
+          top[m].thr = max(top[m].thr, shared_thr - 1);
+          i8_process32(acc, col0, top[m], pb, sh);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int64_t row = (int64_t)qb * I8_QB + m * 128 + quarter * 32 + lane;
+        if (row < nq) {
+          int32_t* o = part_idx + ((int64_t)(split * I8_CGS + cg) * nq + row) * 2;
+          o[0] = top[m].i0 < nt ? top[m].i0 : -1;  // a padding row can only surface when the share holds fewer than 2 rows
+          o[1] = top[m].i1 < nt ? top[m].i1 : -1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static int i8_splits(int64_t nq, int64_t nt) {
+  const int64_t qbs = (nq + I8_QB - 1) / I8_QB;
+  const int64_t sms = sm_count();
+  if (qbs >= 2 * sms) return 1;
+  int64_t s = (2 * sms + qbs - 1) / qbs;
+  const int64_t max_s = (nt + 2047) / 2048;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 24) s = 24;  // the re-rank holds splits * I8_CGS * 2 <= 192 candidates per query
+  return (int)s;
+}
+
+struct I8Layout {
+  size_t qb, tb, par, flag, part, total;
+  int splits;
+  int64_t nt_pad;
+};
+
+static I8Layout i8_layout(int64_t nq, int64_t nt) {
+  I8Layout L;
+  L.nt_pad = (nt + I8_TN - 1) / I8_TN * I8_TN;
+  L.splits = i8_splits(nq, nt);
+  size_t off = 0;
+  L.qb = off; off += align_up((size_t)nq * I8_KA, 1024);
+  L.tb = off; off += align_up((size_t)L.nt_pad * I8_KA, 1024);
+  L.par = off; off += align_up((size_t)L.nt_pad / 8, 1024);
+  L.flag = off; off += 1024;
+  L.part = off; off += align_up((size_t)L.splits * I8_CGS * nq * 2 * sizeof(int32_t), 1024);
+  L.total = off;
+  return L;
+}
+
+size_t l2_tc_i8_workspace_bytes(int64_t nq, int64_t nt) {
+  if (nq <= 0 || nt <= 0) return 256;
+  return i8_layout(nq, nt).total;
+}
+
+// *eligible = 0: the descriptors do not fit the u8 engine and nothing was computed (AUTO falls through); with
+// `require` set that is an error instead.
+int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_t* idx, float* dist, void* ws, size_t ws_bytes,
+                  cudaStream_t st, bool require, int* eligible) {
+  const I8Layout L = i8_layout(nq, nt);
+  HPUSM_REQUIRE(ws_bytes >= L.total, HPUSM_ERR_WORKSPACE, "l2 i8 engine: workspace needs %zu bytes, got %zu", L.total, ws_bytes);
+  char* base = reinterpret_cast<char*>(ws);
+  uint8_t* qb = reinterpret_cast<uint8_t*>(base + L.qb);
+  uint8_t* tb = reinterpret_cast<uint8_t*>(base + L.tb);
+  uint32_t* par = reinterpret_cast<uint32_t*>(base + L.par);
+  int* flag = reinterpret_cast<int*>(base + L.flag);
+  int32_t* part = reinterpret_cast<int32_t*>(base + L.part);
+
+  HPUSM_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  HPUSM_CUDA_OK(cudaMemsetAsync(par, 0, (size_t)L.nt_pad / 8, st));
+  HPUSM_LAUNCH(l2_i8_prep_kernel, (unsigned)((nq + 7) / 8), 256, 0, st, q, nq, nq, 0, qb, par, flag);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(l2_i8_prep_kernel, (unsigned)((L.nt_pad + 7) / 8), 256, 0, st, t, nt, L.nt_pad, 1, tb, par, flag);
+  HPUSM_CHECK_LAUNCH();
+  // the one host read of the engine: do the descriptors fit u8 operands?
+  int h_flag = 0;
+  HPUSM_CUDA_OK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HPUSM_CUDA_OK(cudaStreamSynchronize(st));
+  *eligible = h_flag == 0;
+  if (h_flag != 0) {
+    HPUSM_REQUIRE(!require, HPUSM_ERR_UNSUPPORTED,
+                  "HPUSM_L2_TC_I8 needs integer descriptors in [0,255] with squared norms up to %d", 2 * I8_HB);
+    return HPUSM_OK;
+  }
+  HPUSM_CUDA_OK(cudaMemsetAsync(part, 0xff, (size_t)L.splits * I8_CGS * nq * 2 * sizeof(int32_t), st));
+  CUtensorMap map_t, map_ta;
+  int rc = tc_make_map(&map_t, tb, L.nt_pad, I8_KA, 128, CU_TENSOR_MAP_SWIZZLE_128B, I8_TN, 1);
+  if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, I8_KA, 32, CU_TENSOR_MAP_SWIZZLE_32B, I8_TN, 1);
+  if (rc != HPUSM_OK) return rc;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  HPUSM_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    attr_done[dev] = true;
+  }
+  const int q_blocks = (int)((nq + I8_QB - 1) / I8_QB);
+  int64_t rows_per_split = (nt + L.splits - 1) / L.splits;
+  rows_per_split = (rows_per_split + I8_TN - 1) / I8_TN * I8_TN;
+  const int units = q_blocks * L.splits;
+  const int grid = units < sm_count() ? units : sm_count();
+  HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                     rows_per_split, par, part);
+  HPUSM_CHECK_LAUNCH();
+  return l2_rerank_finalize(q, nq, t, I8_D, part, L.splits * I8_CGS, 2, nullptr, 0, idx, dist, st);
+}
+
+}  // namespace hpusm

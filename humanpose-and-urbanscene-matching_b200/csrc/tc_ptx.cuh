@@ -95,8 +95,9 @@ constexpr uint32_t tc_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// Host: tensor map of a [rows][cols] bf16 row-major array, box = box_cols x box_rows (defined in l2_tc.cu).
+// Host: tensor map of a [rows][cols] row-major array of bf16 (elem_bytes 2) or u8 (elem_bytes 1) elements,
+// box = box_cols x box_rows (defined in l2_tc.cu).
 int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_cols, CUtensorMapSwizzle swizzle,
-                int box_rows = 128);
+                int box_rows = 128, int elem_bytes = 2);
 
 }  // namespace hpusm

@@ -12,7 +12,8 @@ import torch
 from . import _lib
 from ._lib import lib, check
 
-L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT = _lib.L2_AUTO, _lib.L2_SIMT, _lib.L2_TC_INT, _lib.L2_TC_SPLIT
+L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT, L2_TC_I8 = (_lib.L2_AUTO, _lib.L2_SIMT, _lib.L2_TC_INT, _lib.L2_TC_SPLIT,
+                                                       _lib.L2_TC_I8)
 POSE_DETAIL = _lib.POSE_DETAIL
 
 # thresholds.py:7-13 of the reference, in the order hpusm_pose_match_batch expects
@@ -393,7 +394,12 @@ def pose_topk(match, score, k=16, index_offset=0):
 
 
 def microbench_popc(blocks, threads, iters, device, op="popc"):
+    """op: "popc" | "lop3" | "imax3" | "fmax3" | "imax" | "fmax" -- every thread issues `iters` of that instruction."""
     sink = torch.zeros((1,), dtype=torch.int32, device=device)
-    fn = lib.hpusm_microbench_popc if op == "popc" else lib.hpusm_microbench_lop3
+    minmax = {"imax3": 0, "fmax3": 1, "imax": 2, "fmax": 3}
     with torch.cuda.device(device):
+        if op in minmax:
+            check(lib.hpusm_microbench_minmax(minmax[op], int(blocks), int(threads), int(iters), _ptr(sink), _stream(device)))
+            return
+        fn = lib.hpusm_microbench_popc if op == "popc" else lib.hpusm_microbench_lop3
         check(fn(int(blocks), int(threads), int(iters), _ptr(sink), _stream(device)))

@@ -37,12 +37,14 @@ extern "C" {
 #define HPUSM_ERR_UNSUPPORTED (-4) /* shape outside what the sm_100a kernels were built for         */
 
 /* L2 kNN engine selection (hpusm_knn2_l2 `mode`). */
-#define HPUSM_L2_AUTO 0   /* tensor-core path; engine chosen from the data (exact-int, else hi/lo split); reads one
-                             4-byte flag back, i.e. synchronises the stream once per call                          */
+#define HPUSM_L2_AUTO 0   /* tensor-core path; engine chosen from the data (u8 integer MMA, else bf16 exact-int, else
+                             hi/lo split); reads a 4-byte flag back per decision, i.e. synchronises the stream      */
 #define HPUSM_L2_SIMT 1   /* exact FP32 CUDA-core brute force (cross-check / tiny inputs)             */
 #define HPUSM_L2_TC_INT 2 /* tcgen05, bf16 operands, caller asserts integer values in [0,256]         */
 #define HPUSM_L2_TC_SPLIT 3 /* tcgen05, hi/lo bf16 split (general float), top-4 + verified FP32 re-rank; synchronises
                                the stream once (count of rows sent to the exact fallback)                          */
+#define HPUSM_L2_TC_I8 4  /* tcgen05 kind::i8, u8 operands, s32 accumulation: integer values in [0,255] and squared
+                             norms below 2,000,000 (checked on the device; HPUSM_ERR_UNSUPPORTED otherwise)         */
 
 int hpusm_version(void);
 const char* hpusm_last_error(void);
@@ -90,10 +92,11 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
  * Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) (features.py:42,:59).
  *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512.
  *   The tensor-core engines are built for d == 128 (SIFT); HPUSM_L2_AUTO takes the exact FP32 engine for other
- *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT return HPUSM_ERR_UNSUPPORTED there.
- *   HPUSM_L2_TC_INT trusts the caller that every value is an integer with |v| <= 256 (what OpenCV SIFT emits);
- *   HPUSM_L2_AUTO checks that on the device and otherwise uses the split engine, whose answer is the exact FP32 one
- *   as well (candidate lists are proven complete or the row is redone by the FP32 engine).
+ *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 return HPUSM_ERR_UNSUPPORTED there.
+ *   HPUSM_L2_TC_INT trusts the caller that every value is an integer with |v| <= 256;
+ *   HPUSM_L2_AUTO checks the value range on the device: integers in [0,255] (what OpenCV SIFT emits) run on the u8
+ *   integer tensor pipe, other integers with |v| <= 256 on the bf16 engine, anything else on the split engine, whose
+ *   answer is the exact FP32 one as well (candidate lists are proven complete or the row is redone by the FP32 engine).
  *   idx  [nq][2] int32 as above.
  *   dist [nq][2] float32 = sqrtf( sum_k (q_k - t_k)^2 ), the sum taken in FP32 in increasing k with
  *   fused multiply-add (the "exact FP32 re-rank"); this is what DMatch.distance holds in the reference.
@@ -261,6 +264,9 @@ int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t
 int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
 /* Same for LOP3 on the ALU pipe (the Hamming kernel issues 16 LOP3 + 4 POPC per 256-bit pair). */
 int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
+/* Issue rate of the max-scan instructions the fused top-2 epilogues of K1 are made of.
+ * op 0: 3-input s32 max, 1: 3-input f32 max, 2: 2-input s32 max, 3: 2-input f32 max. */
+int hpusm_microbench_minmax(int op, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
 
 #ifdef __cplusplus
 }

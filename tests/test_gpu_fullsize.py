@@ -27,7 +27,7 @@ def test_c2_sift_1m_x_1m_properties(hpusm, cuda_device):
     noise = torch.round(torch.randn((100000, 128), generator=g, device=cuda_device) * 2.0)
     q[planted_q] = torch.clamp(t[planted_t] + noise, 0, 255)
     idx, dist = hpusm.knn2_l2(q, t)
-    assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_INT
+    assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_I8
     # (1) every planted neighbour is found as the nearest row (noise sigma 2 vs typical NN distance > 200)
     assert torch.equal(idx[planted_q, 0].long(), planted_t) or (
         (dist[planted_q, 0] <= (q[planted_q] - t[planted_t]).norm(dim=1)).all())

@@ -104,7 +104,7 @@ L2_MODES = ["auto", "simt"]
 
 def _mode(hpusm, name):
     return {"auto": hpusm.engine.L2_AUTO, "simt": hpusm.engine.L2_SIMT, "tc_int": hpusm.engine.L2_TC_INT,
-            "tc_split": hpusm.engine.L2_TC_SPLIT}[name]
+            "tc_split": hpusm.engine.L2_TC_SPLIT, "tc_i8": hpusm.engine.L2_TC_I8}[name]
 
 
 @pytest.mark.parametrize("mode", L2_MODES)
@@ -135,18 +135,63 @@ def test_l2_scene_pair_sift(hpusm, cuda_device, mode):
     np.testing.assert_array_equal(p_t[:161].cpu().numpy(), g["p_input"].reshape(-1, 2))
 
 
-def test_l2_tensor_engine_units_and_splits(hpusm, cuda_device):
-    """Explicit tcgen05 engine (HPUSM_L2_TC_INT): several 256-query units per CTA wave, database splits, ragged
-    tails on both sides, duplicate database rows (ties -> lower index)."""
+@pytest.mark.parametrize("engine", ["tc_int", "tc_i8"])
+def test_l2_tensor_engine_units_and_splits(hpusm, cuda_device, engine):
+    """Explicit tcgen05 engines (HPUSM_L2_TC_INT bf16, HPUSM_L2_TC_I8 u8): several 256-query units per CTA wave,
+    database splits, ragged tails on both sides, duplicate database rows (ties -> lower index)."""
+    mode = _mode(hpusm, engine)
     for nq, nt, seed in [(5000, 70001, 1), (257, 1085, 2), (40000, 4323, 3), (1, 129, 4)]:
         q, t = hpusm.synth.sift_like(nq, nt, seed=seed, planted=0.3)
         t[nt // 2] = t[3]
         t[nt - 1] = t[0]
-        idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_TC_INT)
-        assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_INT
+        idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=mode)
+        assert hpusm.engine.knn2_l2_last_mode() == mode
         ri, rd = knn_oracle.knn2_l2(q, t)
         np.testing.assert_array_equal(idx.cpu().numpy(), ri)
         np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+
+
+def test_l2_i8_engine_ties_and_parity(hpusm, cuda_device):
+    """HPUSM_L2_TC_I8 orders by s = q.t - (||t||^2 >> 1) and settles the dropped parity bit only for columns that can
+    matter.  Tiny value ranges make thousands of columns tie in s with differing parity, and make exact distance ties:
+    the result must still be the oracle's (distance, then lower index), bit for bit."""
+    for nq, nt, hi, seed in [(700, 9000, 2, 1), (300, 5000, 4, 2), (513, 2049, 3, 3), (64, 300, 180, 4)]:
+        rng = np.random.default_rng(seed)
+        q = rng.integers(0, hi, (nq, 128)).astype(np.float32)
+        t = rng.integers(0, hi, (nt, 128)).astype(np.float32)
+        if hi <= 4:
+            q[:, 24:] = 0  # few active columns -> distances take a handful of values -> massive ties
+            t[:, 24:] = 0
+        idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_TC_I8)
+        ri, rd = knn_oracle.knn2_l2(q, t)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+        np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+
+
+def test_l2_auto_engine_selection(hpusm, cuda_device):
+    """HPUSM_L2_AUTO: u8 engine for integers in [0,255] with bounded norms, bf16 exact-int engine for other integers
+    with |v| <= 256, split engine for the rest; HPUSM_L2_TC_I8 on data it cannot hold is an error, not a wrong answer."""
+    rng = np.random.default_rng(11)
+    E = hpusm.engine
+    cases = [
+        (rng.integers(0, 256, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_I8),
+        (rng.integers(-9, 10, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_INT),      # negative query values
+        (rng.integers(0, 100, (300, 128)), rng.integers(200, 256, (900, 128)), E.L2_TC_INT),    # ||t||^2 > 2e6
+        (rng.integers(0, 100, (300, 128)) + 0.5, rng.integers(0, 100, (900, 128)), E.L2_TC_SPLIT),
+    ]
+    for q, t, want in cases:
+        q, t = q.astype(np.float32), t.astype(np.float32)
+        idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=E.L2_AUTO)
+        assert E.knn2_l2_last_mode() == want
+        ri, rd = knn_oracle.knn2_l2(q, t)
+        if want == E.L2_TC_SPLIT:
+            assert_l2_parity(idx, dist, ri, rd, q, t)
+        else:
+            np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+            np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+        if want != E.L2_TC_I8:
+            with pytest.raises(Exception, match="TC_I8"):
+                hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=E.L2_TC_I8)
 
 
 @pytest.mark.parametrize("mode", L2_MODES)
