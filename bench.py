@@ -40,6 +40,8 @@ def parse_args():
                     help="sift = BASELINE.json's headline config (default); the others are the remaining configs")
     ap.add_argument("--descriptors", default="int", choices=["int", "float"],
                     help="sift: integer-valued SIFT-like rows (the named config) or the general-float variant (x 1.0137)")
+    ap.add_argument("--l2-engine", default="auto", choices=["auto", "i8", "bf16", "split", "simt"],
+                    help="sift: force one L2 engine (default: HPUSM_L2_AUTO picks from the data)")
     ap.add_argument("--nq", type=int, default=1 << 20)
     ap.add_argument("--nt", type=int, default=1 << 20, help="database rows PER GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
@@ -203,6 +205,14 @@ def run_reference(args, rank):
     }
 
 
+DTYPE_OF = {
+    "tcgen05-i8-exact-int": "u8 operands (exact for SIFT's integers 0..255) / s32 accumulate + f32 re-rank",
+    "tcgen05-bf16-exact-int": "bf16 operands (exact for integer-valued SIFT) / f32 accumulate + f32 re-rank",
+    "tcgen05-bf16-split": "bf16 hi/lo split operands / f32 accumulate + verified f32 re-rank",
+    "simt-fp32": "f32",
+}
+
+
 # ---- our path ---------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, device):
     import torch.distributed as dist
@@ -212,12 +222,14 @@ def run_ours(args, rank, world, device):
     q, t = make_workload(nq, nt, rank, device)
     if args.descriptors == "float":  # same rows, no longer integer valued: exercises the split-operand engine
         q, t = (q * 1.0137).contiguous(), (t * 1.0137).contiguous()
-    ws = eng.knn2_l2_workspace(nq, nt, 128, eng.L2_AUTO, device)
+    l2_mode = {"auto": eng.L2_AUTO, "i8": eng.L2_TC_I8, "bf16": eng.L2_TC_INT, "split": eng.L2_TC_SPLIT,
+               "simt": eng.L2_SIMT}[args.l2_engine]
+    ws = eng.knn2_l2_workspace(nq, nt, 128, l2_mode, device)
     idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
     dst = torch.empty((nq, 2), dtype=torch.float32, device=device)
 
     def local_knn(qq, tt):
-        return eng.knn2_l2(qq, tt, mode=eng.L2_AUTO, out=(idx, dst), workspace=ws)
+        return eng.knn2_l2(qq, tt, mode=l2_mode, out=(idx, dst), workspace=ws)
 
     def step():
         mi, md, keep, count = hp.retrieval.knn2_sharded(q, t, rank * nt, kind="l2", ratio=0.8, knn_fn=local_knn)
@@ -292,19 +304,24 @@ def run_ours(args, rank, world, device):
     pairs_per_step = float(nq) * float(nt) * world
     value = pairs_per_step * args.steps / (ms * 1e-3)
     pk = peaks()
-    peak_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
+    bf16_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
+    peak_tf = bf16_tf
     k_ms = kernel_ms / max(kernel_n, 1)
     flops_per_launch = FLOP_PER_PAIR * float(nq) * float(nt) * args.steps / max(kernel_n, 1)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     mode = {0: "auto", 1: "simt-fp32", 2: "tcgen05-bf16-exact-int", 3: "tcgen05-bf16-split",
             4: "tcgen05-i8-exact-int"}.get(eng.knn2_l2_last_mode(), "?")
-    if mode == "tcgen05-bf16-split":
-        pass  # roofline still counts the algorithmic 256 FLOP per pair; the engine executes 25/8 of that on the tensor pipe
+    peak_source = "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"
+    if mode == "tcgen05-i8-exact-int":
+        # kind::i8 retires K=32 per MMA instruction slot where kind::f16 retires K=16: the integer pipe's peak is twice
+        # the bf16 one.  MEASURED_PEAKS.json has no INT8 line, so the denominator is 2 x its measured bf16 figure.
+        peak_tf = 2.0 * bf16_tf
+        peak_source = "2 x (" + peak_source + "): tcgen05 kind::i8 issues twice the MACs per instruction slot of kind::f16"
+    # (the split engine executes 25/8 of the algorithmic 256 FLOP per pair on the tensor pipe; the roofline counts 256)
     out = {
         "metric": "descriptor-pairs/sec (kNN+ratio)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16 operands (exact for integer-valued SIFT) / f32 accumulate + f32 re-rank"
-        if mode.startswith("tcgen05") else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPE_OF.get(mode, "f32"), "data": "synthetic",
         "config": {"workload": "synthetic SIFT 128-d float, 1M query x 1M database kNN k=2 ratio test on 1 B200",
                    "nq": nq, "nt_per_gpu": nt, "d": 128, "ratio": 0.8, "engine": mode, "descriptors": args.descriptors,
                    "fallback_rows": eng.knn2_l2_last_fallback_rows(), "sharding": "database rows",
@@ -314,9 +331,9 @@ def run_ours(args, rank, world, device):
                 "d2h_bytes_per_step": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel())},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%dx%d" % (nq, nt)) if args.descriptors == "int" else None,
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt)),
                      "kernel_ms": k_ms, "kernel_launches": int(kernel_n),
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"},
+                     "frac_of_bf16_peak": achieved / bf16_tf if bf16_tf else None, "peak_source": peak_source},
         "clocks": clocks,
     }
     return out

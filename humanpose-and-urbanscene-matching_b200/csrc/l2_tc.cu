@@ -233,24 +233,24 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      uint32_t it = 0, un = 0;
-      const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
-      for (int u = u_first; u < total_units; u += u_step, ++un) {
-        const int split = u / q_groups;
-        const int64_t t_begin = (int64_t)split * rows_per_split;
-        const int64_t t_end = min(nt, t_begin + rows_per_split);
-        const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
-        mbar_wait(a_full, un & 1);
-        for (int j = 0; j < tiles; ++j, ++it) {
-          const int s = it % TC_STAGES;
-          mbar_wait(full + s, (it / TC_STAGES) & 1);
+    // ===== MMA issuer: the whole warp walks the loop, one elected lane issues (see elect_one in tc_ptx.cuh) =====
+    uint32_t it = 0, un = 0;
+    const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
+    for (int u = u_first; u < total_units; u += u_step, ++un) {
+      const int split = u / q_groups;
+      const int64_t t_begin = (int64_t)split * rows_per_split;
+      const int64_t t_end = min(nt, t_begin + rows_per_split);
+      const int tiles = (int)((t_end - t_begin + TC_TN - 1) / TC_TN);
+      mbar_wait(a_full, un & 1);
+      for (int j = 0; j < tiles; ++j, ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait(full + s, (it / TC_STAGES) & 1);
 #pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            mbar_wait(tmem_empty + m, (it & 1) ^ 1);   // the epilogue has drained this query tile's accumulator
-            tc_fence_after();
-            const uint32_t d_addr = tmem_base + (uint32_t)(m * TC_TN);
+        for (int m = 0; m < 2; ++m) {
+          mbar_wait(tmem_empty + m, (it & 1) ^ 1);   // the epilogue has drained this query tile's accumulator
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + (uint32_t)(m * TC_TN);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_D / 16; ++k) {
               const uint32_t koff_a = (uint32_t)((k >> 2) * TC_HALF_BYTES + (k & 3) * 32);
@@ -263,11 +263,16 @@ l2_tc_knn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         umma_desc_sw32(b_addr + s * TC_B_BYTES + 2 * TC_BHALF_BYTES), TC_IDESC, 1u);
             tc_commit(tmem_full + m);   // this query tile's accumulator is ready for its epilogue warps
           }
+          __syncwarp();
+        }
+        if (elect_one()) {
           if (PAIR) tc_commit_mc(empty + s, 3);  // ... in BOTH CTAs: either producer may overwrite either copy
           else tc_commit(empty + s);    // the stage may be refilled once both blocks have read it
         }
-        tc_commit(a_empty);           // the query tiles may be replaced
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(a_empty);           // the query tiles may be replaced
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue: fused top-2 =====

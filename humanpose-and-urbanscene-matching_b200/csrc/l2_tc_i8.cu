@@ -36,7 +36,7 @@ constexpr int I8_QB = 256;            // queries per unit (two M=128 query tiles
 constexpr int I8_TN = 128;            // database rows per tile (MMA N)
 constexpr int I8_STAGES = 8;
 constexpr int I8_THREADS = 640;       // 4 service warps + 16 epilogue warps
-constexpr int I8_CGS = 4;             // column groups of 32 per 128-column accumulator (one per epilogue warp and lane quarter)
+constexpr int I8_CGS = 2;             // column groups of 64 per 128-column accumulator (one per epilogue warp of a lane quarter)
 constexpr int I8_NBUF = 3;            // accumulators in rotation
 constexpr int I8_KA = 160;            // operand row: 128 descriptor bytes + 32 augmentation bytes
 constexpr int I8_A_COLS = 40;         // a query tile in tensor memory: 160 bytes per row = 40 32-bit columns
@@ -136,40 +136,49 @@ __device__ __forceinline__ void i8_insert(I8Top2& t, int s, int col, int parity,
   }
 }
 
-// 32 accumulator columns of one query row.  Fast path: a 3-input max tree and one compare.  When some column beats the
-// threshold (rare once the sweep is under way) the candidates are pulled out one at a time, largest s first and the
+// The candidates of 32 accumulator columns that beat the threshold, pulled out one at a time, largest s first and the
 // lower column first among equals, by a max tree over (s << 5 | 31 - j): a short loop instead of 32 unrolled
-// insertions, because rarely executed straight-line code runs at instruction-fetch speed and every warp of the CTA
-// waits for the slowest one at the next accumulator hand-over.
-// `pbits`: parity bits of these 32 columns (bit j = column col + j).
-__device__ __forceinline__ void i8_process32(const uint32_t (&acc)[32], int col, I8Top2& t, uint32_t pbits, int* sh) {
+// insertions, because rarely executed straight-line code runs at instruction-fetch speed and every warp that shares
+// the accumulator hand-over waits for the slowest one.  `pbits`: parity bits (bit j = column col + j).
+__device__ __forceinline__ int i8_max32(const uint32_t (&acc)[32]) {
   int m[11];
 #pragma unroll
   for (int i = 0; i < 10; ++i) m[i] = imax3((int)acc[3 * i], (int)acc[3 * i + 1], (int)acc[3 * i + 2]);
   m[10] = max((int)acc[30], (int)acc[31]);
   const int a = imax3(m[0], m[1], m[2]), b = imax3(m[3], m[4], m[5]), c = imax3(m[6], m[7], m[8]);
-  const int hi = max(imax3(a, b, c), max(m[9], m[10]));
-  if (hi > t.thr) {
-    int last = INT_MAX;
+  return max(imax3(a, b, c), max(m[9], m[10]));
+}
+
+__device__ __forceinline__ void i8_slow32(const uint32_t (&acc)[32], int col, I8Top2& t, uint32_t pbits, int* sh) {
+  int last = INT_MAX;
 #pragma unroll 1
-    for (;;) {
-      int pk[32];
+  for (;;) {
+    int pk[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int v = ((int)acc[j] << 5) + (31 - j);
-        pk[j] = v < last ? v : INT_MIN;
-      }
-      int r[11];
-#pragma unroll
-      for (int i = 0; i < 10; ++i) r[i] = imax3(pk[3 * i], pk[3 * i + 1], pk[3 * i + 2]);
-      r[10] = max(pk[30], pk[31]);
-      const int best = max(imax3(imax3(r[0], r[1], r[2]), imax3(r[3], r[4], r[5]), imax3(r[6], r[7], r[8])), max(r[9], r[10]));
-      const int sb = best >> 5;
-      if (sb <= t.thr) break;
-      const int j = 31 - (best & 31);
-      i8_insert(t, sb, col + j, (int)((pbits >> j) & 1u), sh);
-      last = best;
+    for (int j = 0; j < 32; ++j) {
+      const int v = (int)acc[j] * 32 + (31 - j);
+      pk[j] = v < last ? v : INT_MIN;
     }
+    int r[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = imax3(pk[3 * i], pk[3 * i + 1], pk[3 * i + 2]);
+    r[10] = max(pk[30], pk[31]);
+    const int best = max(imax3(imax3(r[0], r[1], r[2]), imax3(r[3], r[4], r[5]), imax3(r[6], r[7], r[8])), max(r[9], r[10]));
+    const int sb = best >> 5;
+    if (sb <= t.thr) break;
+    const int j = 31 - (best & 31);
+    i8_insert(t, sb, col + j, (int)((pbits >> j) & 1u), sh);
+    last = best;
+  }
+}
+
+// 64 accumulator columns of one query row.  Fast path: two 3-input max trees and ONE compare.
+__device__ __forceinline__ void i8_process64(const uint32_t (&acc0)[32], const uint32_t (&acc1)[32], int col, I8Top2& t, uint2 pbits,
+                                             int* sh) {
+  const int h0 = i8_max32(acc0), h1 = i8_max32(acc1);
+  if (max(h0, h1) > t.thr) {
+    if (h0 > t.thr) i8_slow32(acc0, col, t, pbits.x, sh);
+    if (h1 > t.thr) i8_slow32(acc1, col + 32, t, pbits.y, sh);
   }
 }
 
@@ -180,13 +189,6 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// One lane of the (converged) warp, chosen by the hardware.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (query rows) is read from tensor memory
 __device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -202,7 +204,8 @@ __device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __global__ void __launch_bounds__(I8_THREADS, 1)
 l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtensorMap map_t,
                   const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt, int q_blocks, int splits,
-                  int64_t rows_per_split, const uint32_t* __restrict__ par, int32_t* __restrict__ part_idx) {
+                  int64_t rows_per_split, const uint32_t* __restrict__ par, int32_t* __restrict__ part_idx,
+                  long long* __restrict__ trace) {
   extern __shared__ uint8_t i8_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem;                          // [stages][16 KB | 4 KB]
@@ -220,7 +223,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < I8_NBUF; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 16); }
+    for (int b = 0; b < I8_NBUF; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8); }
     mbar_init(a_ready, 16);
     mbar_init(a_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -278,8 +281,15 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         const uint64_t bdesc_aug = umma_desc_sw32(b_addr + s * I8_B_BYTES + I8_BMAIN_BYTES);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
+#ifdef I8_TRACE
+          const bool tr = trace && blockIdx.x == 0 && it >= 6000 && it < 6064 && lane == 0;
+          if (tr) trace[((it - 6000) * 2 + m) * 8 + 0] = clock64();
+#endif
           mbar_wait(tmem_empty + buf, buf_phase ^ 1);   // the epilogue has read this accumulator out
           tc_fence_after();
+#ifdef I8_TRACE
+          if (tr) trace[((it - 6000) * 2 + m) * 8 + 1] = clock64();
+#endif
           const uint32_t d_addr = tmem_base + (uint32_t)(I8_ACC_COL0 + buf * I8_TN);
           const uint32_t a_col = tmem_base + (uint32_t)(m * I8_A_COLS);
           if (elect_one()) {
@@ -291,6 +301,9 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
             tc_commit(tmem_full + buf);
           }
           __syncwarp();
+#ifdef I8_TRACE
+          if (tr) trace[((it - 6000) * 2 + m) * 8 + 2] = clock64();
+#endif
           if (++buf == I8_NBUF) { buf = 0; buf_phase ^= 1; }
         }
         if (elect_one()) tc_commit(empty + s);
@@ -302,15 +315,17 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
   } else if (warp >= 4) {
     // ===== epilogue: fused top-2 =====
     // An accumulator (one 128-query tile x 128 database rows) is only free for its next MMA block once it has been
-    // read out, tcgen05.ld has a long latency and tensor memory reads run at 64 B/clk per SM sub-partition.  So ALL
-    // 16 warps serve EVERY accumulator: warp -> (TMEM lane quarter = warp % 4, column group cg = 32 of the 128
-    // columns); when an accumulator is ready every warp pulls its 32 columns, releases it, and only then scans.
-    // Three accumulators rotate, so the tensor pipe always has one to fill while another is being read out.
-    // A thread carries two running top-2 states (its row in query tile 0 and in tile 1) over its column group; the
-    // groups are separate candidate parts.
-    const int ew = warp - 4, quarter = ew & 3, cg = ew >> 2;
+    // read out, tcgen05.ld has a long latency and tensor memory reads run at 64 B/clk per SM sub-partition.  Three
+    // accumulators rotate, so the tensor pipe always has one to fill while another is being read out, and every
+    // accumulator is pulled by EIGHT warps at once (two per TMEM lane quarter, 64 columns each): they load, release
+    // the accumulator, and only then scan.  Accumulators alternate between the two query tiles, so warps 0-7 always
+    // serve tile 0 and warps 8-15 tile 1: a thread carries one running top-2 (its row, its 64-column group), and the
+    // two groups are separate candidate parts.
+    const int ew = warp - 4, quarter = ew & 3, cg = (ew >> 2) & 1, m = ew >> 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t un = 0, buf = 0, buf_phase = 0;
+    // piece p = 2 * tile + m lives in accumulator p % 3 and completes phase (p / 3) & 1 of its barrier: for fixed m
+    // the accumulators come round as 0,2,1 (m = 0) or 1,0,2 (m = 1) and the phase depends on the accumulator only
+    uint32_t un = 0, buf = (uint32_t)m;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
       const int split = u / q_blocks, qb = u - split * q_blocks;
       const int64_t t_begin = (int64_t)split * rows_per_split;
@@ -318,11 +333,11 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
       const int tiles = (int)((t_end - t_begin + I8_TN - 1) / I8_TN);
       // -- the unit's query rows go into tensor memory: thread = row, 40 words = [q | augmentation] (MMA operand A) --
       {
-        const int am = cg & 1, ahalf = cg >> 1;  // warp (quarter, cg) stores words [20 ahalf, 20 ahalf + 20) of tile am's rows
-        const int64_t row = (int64_t)qb * I8_QB + am * 128 + quarter * 32 + lane;
-        uint32_t w[24];
+        const int ahalf = cg;  // this warp stores words [20 ahalf, 20 ahalf + 20) of its rows
+        const int64_t row = (int64_t)qb * I8_QB + m * 128 + quarter * 32 + lane;
+        uint32_t w[20];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) w[i] = 0u;
+        for (int i = 0; i < 20; ++i) w[i] = 0u;
         if (row < nq) {
           const uint4* src = reinterpret_cast<const uint4*>(qu + row * I8_KA) + ahalf * 5;
 #pragma unroll
@@ -333,65 +348,71 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         }
         mbar_wait(a_free, (un & 1) ^ 1);   // the previous unit's MMAs no longer read the old rows
         tc_fence_after();
-        const uint32_t a_addr = lane_base + (uint32_t)(am * I8_A_COLS + ahalf * 20);
-        uint32_t g0[8], g1[8], g2[8];
+        const uint32_t a_addr = lane_base + (uint32_t)(m * I8_A_COLS + ahalf * 20);
+        uint32_t g0[8], g1[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { g0[i] = w[i]; g1[i] = w[8 + i]; g2[i] = w[16 + i]; }
+        for (int i = 0; i < 8; ++i) { g0[i] = w[i]; g1[i] = w[8 + i]; }
         tc_st8(a_addr, g0);
         tc_st8(a_addr + 8, g1);
-        // words 16..19 of this half: a 4-column store
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_addr + 16), "r"(g2[0]), "r"(g2[1]),
-                     "r"(g2[2]), "r"(g2[3])
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_addr + 16), "r"(w[16]), "r"(w[17]),
+                     "r"(w[18]), "r"(w[19])
                      : "memory");
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
       }
-      I8Top2 top[2];
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        top[m].k0 = top[m].k1 = INT_MIN;
-        top[m].thr = INT_MIN >> 1;
-        top[m].i0 = top[m].i1 = -1;
-      }
-      // The four column-group warps of a row share their thresholds: each keeps its own top-2, but a column is only
-      // looked at when it could beat the best second-best key any of them holds (minus one, so that equal keys still
+      I8Top2 top;
+      top.k0 = top.k1 = INT_MIN;
+      top.thr = INT_MIN >> 1;
+      top.i0 = top.i1 = -1;
+      // The two column-group warps of a row share their thresholds: each keeps its own top-2, but a column is only
+      // looked at when it could beat the better second-best key of the two (minus one, so that equal keys still
       // reach their own list and the final re-rank settles the index order).
+      int* sh = thr_sh + m * 128 + quarter * 32 + lane;
       asm volatile("bar.sync 1, 512;" ::: "memory");   // everybody is done with the previous unit's thresholds
-      if (cg == 0) { thr_sh[quarter * 32 + lane] = INT_MIN >> 1; thr_sh[128 + quarter * 32 + lane] = INT_MIN >> 1; }
+      if (cg == 0) *sh = INT_MIN >> 1;
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      // parity bits of this warp's 32 columns, fetched one tile ahead so that an insertion never waits on memory
-      uint32_t pb_next = __ldg(par + (((int)t_begin + cg * 32) >> 5));
+      // parity bits of this warp's 64 columns, fetched one tile ahead so that an insertion never waits on memory
+      uint2 pb_next = __ldg(reinterpret_cast<const uint2*>(par + (((int)t_begin + cg * 64) >> 5)));
       for (int j = 0; j < tiles; ++j) {
-        const int col0 = (int)(t_begin + (int64_t)j * I8_TN) + cg * 32;
-        const uint32_t pb = pb_next;
-        if (j + 1 < tiles) pb_next = __ldg(par + ((col0 + I8_TN) >> 5));
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          uint32_t acc[32];
-          int* sh = thr_sh + m * 128 + quarter * 32 + lane;
-          const int shared_thr = *reinterpret_cast<volatile int*>(sh);
-          mbar_wait(tmem_full + buf, buf_phase);
-          tc_fence_after();
-          tc_ld32(lane_base + (uint32_t)(I8_ACC_COL0 + buf * I8_TN + cg * 32), acc);
-          tc_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + buf);
-          if (++buf == I8_NBUF) { buf = 0; buf_phase ^= 1; }
-          top[m].thr = max(top[m].thr, shared_thr - 1);
-          i8_process32(acc, col0, top[m], pb, sh);
-        }
+        const int col0 = (int)(t_begin + (int64_t)j * I8_TN) + cg * 64;
+        const uint2 pb = pb_next;
+        if (j + 1 < tiles) pb_next = __ldg(reinterpret_cast<const uint2*>(par + ((col0 + I8_TN) >> 5)));
+        uint32_t acc0[32], acc1[32];
+        const int shared_thr = *reinterpret_cast<volatile int*>(sh);
+        const uint32_t phase = m == 0 ? (buf == 1u ? 1u : 0u) : (buf == 1u ? 0u : 1u);
+#ifdef I8_TRACE
+        const bool tr = trace && blockIdx.x == 0 && un == 0 && j >= 6000 && j < 6064 && lane == 0;
+        if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 8 + (ew & 7)] = clock64();
+#endif
+        mbar_wait(tmem_full + buf, phase);
+        tc_fence_after();
+#ifdef I8_TRACE
+        if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 24 + (ew & 7)] = clock64();
+#endif
+        const uint32_t taddr = lane_base + (uint32_t)(I8_ACC_COL0 + buf * I8_TN + cg * 64);
+        tc_ld32(taddr, acc0);
+        tc_ld32(taddr + 32, acc1);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + buf);
+#ifdef I8_TRACE
+        if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + (ew & 7)] = clock64() + (acc0[0] & 0);
+#endif
+        buf = buf == 0 ? 2u : buf - 1u;   // two pieces on: (buf + 2) % 3
+        top.thr = max(top.thr, shared_thr - 1);
+        i8_process64(acc0, acc1, col0, top, pb, sh);
+#ifdef I8_TRACE
+        if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 16 + (ew & 7)] = clock64() + (top.i0 & 0);
+#endif
       }
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const int64_t row = (int64_t)qb * I8_QB + m * 128 + quarter * 32 + lane;
-        if (row < nq) {
-          int32_t* o = part_idx + ((int64_t)(split * I8_CGS + cg) * nq + row) * 2;
-          o[0] = top[m].i0 < nt ? top[m].i0 : -1;  // a padding row can only surface when the share holds fewer than 2 rows
-          o[1] = top[m].i1 < nt ? top[m].i1 : -1;
-        }
+      const int64_t row = (int64_t)qb * I8_QB + m * 128 + quarter * 32 + lane;
+      if (row < nq) {
+        int32_t* o = part_idx + ((int64_t)(split * I8_CGS + cg) * nq + row) * 2;
+        o[0] = top.i0 < nt ? top.i0 : -1;  // a padding row can only surface when the share holds fewer than 2 rows
+        o[1] = top.i1 < nt ? top.i1 : -1;
       }
     }
   }
@@ -413,7 +434,7 @@ static int i8_splits(int64_t nq, int64_t nt) {
   const int64_t max_s = (nt + 2047) / 2048;
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
-  if (s > 24) s = 24;  // the re-rank holds splits * I8_CGS * 2 <= 192 candidates per query
+  if (s > 48) s = 48;  // the re-rank holds splits * I8_CGS * 2 <= 192 candidates per query
   return (int)s;
 }
 
@@ -488,9 +509,23 @@ int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_
   rows_per_split = (rows_per_split + I8_TN - 1) / I8_TN * I8_TN;
   const int units = q_blocks * L.splits;
   const int grid = units < sm_count() ? units : sm_count();
+  long long* trace = nullptr;
+#ifdef I8_TRACE
+  const char* trace_path = getenv("HPUSM_I8_TRACE");
+  if (trace_path) { HPUSM_CUDA_OK(cudaMalloc(&trace, 8192 * 8)); HPUSM_CUDA_OK(cudaMemset(trace, 0, 8192 * 8)); }
+#endif
   HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
-                     rows_per_split, par, part);
+                     rows_per_split, par, part, trace);
   HPUSM_CHECK_LAUNCH();
+#ifdef I8_TRACE
+  if (trace) {
+    static long long h[8192];
+    HPUSM_CUDA_OK(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "wb");
+    if (f) { fwrite(h, 1, sizeof(h), f); fclose(f); }
+    cudaFree(trace);
+  }
+#endif
   return l2_rerank_finalize(q, nq, t, I8_D, part, L.splits * I8_CGS, 2, nullptr, 0, idx, dist, st);
 }
 

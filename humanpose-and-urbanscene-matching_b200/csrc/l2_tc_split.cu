@@ -191,22 +191,23 @@ l2_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, un = 0;
-      const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
-        const int split = u / q_blocks;
-        const int64_t t_begin = (int64_t)split * rows_per_split;
-        const int64_t t_end = min(nt, t_begin + rows_per_split);
-        const int tiles = (int)((t_end - t_begin + SP_TN - 1) / SP_TN);
-        mbar_wait(a_full, un & 1);
-        for (int j = 0; j < tiles; ++j, ++it) {
-          const int s = it % SP_STAGES, b = it & 1;
-          mbar_wait(full + s, (it / SP_STAGES) & 1);
-          mbar_wait(tmem_empty + b, ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_addr = tmem_base + (uint32_t)(b * SP_TN);
-          const uint32_t bs = b_addr + s * SP_TILE;
+    // the whole warp walks the loop, one elected lane issues (see elect_one in tc_ptx.cuh)
+    uint32_t it = 0, un = 0;
+    const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
+      const int split = u / q_blocks;
+      const int64_t t_begin = (int64_t)split * rows_per_split;
+      const int64_t t_end = min(nt, t_begin + rows_per_split);
+      const int tiles = (int)((t_end - t_begin + SP_TN - 1) / SP_TN);
+      mbar_wait(a_full, un & 1);
+      for (int j = 0; j < tiles; ++j, ++it) {
+        const int s = it % SP_STAGES, b = it & 1;
+        mbar_wait(full + s, (it / SP_STAGES) & 1);
+        mbar_wait(tmem_empty + b, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(b * SP_TN);
+        const uint32_t bs = b_addr + s * SP_TILE;
+        if (elect_one()) {
           // hi.hi, hi.lo, lo.hi: (A part, B part) = (0,0), (0,1), (1,0); a part = two 16 KB slabs
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
@@ -222,8 +223,10 @@ l2_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tc_commit(empty + s);
           tc_commit(tmem_full + b);
         }
-        tc_commit(a_empty);
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(a_empty);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3;
