@@ -35,7 +35,7 @@ constexpr int I8_D = 128;
 constexpr int I8_QB = 256;            // queries per unit (two M=128 query tiles)
 constexpr int I8_TN = 128;            // database rows per tile (MMA N)
 constexpr int I8_STAGES = 8;
-constexpr int I8_THREADS = 640;       // 4 service warps + 16 epilogue warps
+constexpr int I8_THREADS = 576;       // 2 service warps (TMA producer + TMEM allocator, MMA issuer) + 16 epilogue warps
 constexpr int I8_CGS = 2;             // column groups of 64 per 128-column accumulator (one per epilogue warp of a lane quarter)
 constexpr int I8_NBUF = 3;            // accumulators in rotation
 constexpr int I8_KA = 160;            // operand row: 128 descriptor bytes + 32 augmentation bytes
@@ -125,14 +125,14 @@ struct I8Top2 {
 
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
 
-// `sh`: this row's threshold shared by the four warps that scan different column groups of the same row.
-__device__ __forceinline__ void i8_insert(I8Top2& t, int s, int col, int parity, int* sh) {
+// `sh`: shared-memory address of this row's threshold, shared by the warps that scan different column groups of the row.
+__device__ __forceinline__ void i8_insert(I8Top2& t, int s, int col, int parity, uint32_t sh) {
   const int k = 2 * s - parity;
   if (k > t.k1) {  // strict: candidates reach a thread in increasing index order within equal keys
     if (k > t.k0) { t.k1 = t.k0; t.i1 = t.i0; t.k0 = k; t.i0 = col; }
     else { t.k1 = k; t.i1 = col; }
     t.thr = max(t.thr, t.k1 >> 1);
-    atomicMax(sh, t.k1 >> 1);
+    asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(sh), "r"(t.k1 >> 1) : "memory");
   }
 }
 
@@ -149,7 +149,7 @@ __device__ __forceinline__ int i8_max32(const uint32_t (&acc)[32]) {
   return max(imax3(a, b, c), max(m[9], m[10]));
 }
 
-__device__ __forceinline__ void i8_slow32(const uint32_t (&acc)[32], int col, I8Top2& t, uint32_t pbits, int* sh) {
+__device__ __forceinline__ void i8_slow32(const uint32_t (&acc)[32], int col, I8Top2& t, uint32_t pbits, uint32_t sh) {
   int last = INT_MAX;
 #pragma unroll 1
   for (;;) {
@@ -174,7 +174,7 @@ __device__ __forceinline__ void i8_slow32(const uint32_t (&acc)[32], int col, I8
 
 // 64 accumulator columns of one query row.  Fast path: two 3-input max trees and ONE compare.
 __device__ __forceinline__ void i8_process64(const uint32_t (&acc0)[32], const uint32_t (&acc1)[32], int col, I8Top2& t, uint2 pbits,
-                                             int* sh) {
+                                             uint32_t sh) {
   const int h0 = i8_max32(acc0), h1 = i8_max32(acc1);
   if (max(h0, h1) > t.thr) {
     if (h0 > t.thr) i8_slow32(acc0, col, t, pbits.x, sh);
@@ -228,7 +228,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
     mbar_init(a_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -312,7 +312,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
       if (elect_one()) tc_commit(a_free);
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else {
     // ===== epilogue: fused top-2 =====
     // An accumulator (one 128-query tile x 128 database rows) is only free for its next MMA block once it has been
     // read out, tcgen05.ld has a long latency and tensor memory reads run at 64 B/clk per SM sub-partition.  Three
@@ -321,7 +321,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
     // the accumulator, and only then scan.  Accumulators alternate between the two query tiles, so warps 0-7 always
     // serve tile 0 and warps 8-15 tile 1: a thread carries one running top-2 (its row, its 64-column group), and the
     // two groups are separate candidate parts.
-    const int ew = warp - 4, quarter = ew & 3, cg = (ew >> 2) & 1, m = ew >> 3;
+    const int ew = warp - 2, quarter = warp & 3 /* the TMEM lanes a warp may touch */, cg = (ew >> 2) & 1, m = ew >> 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     // piece p = 2 * tile + m lives in accumulator p % 3 and completes phase (p / 3) & 1 of its barrier: for fixed m
     // the accumulators come round as 0,2,1 (m = 0) or 1,0,2 (m = 1) and the phase depends on the accumulator only
@@ -369,9 +369,9 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
       // The two column-group warps of a row share their thresholds: each keeps its own top-2, but a column is only
       // looked at when it could beat the better second-best key of the two (minus one, so that equal keys still
       // reach their own list and the final re-rank settles the index order).
-      int* sh = thr_sh + m * 128 + quarter * 32 + lane;
+      const uint32_t sh = smem_u32(thr_sh + m * 128 + quarter * 32 + lane);
       asm volatile("bar.sync 1, 512;" ::: "memory");   // everybody is done with the previous unit's thresholds
-      if (cg == 0) *sh = INT_MIN >> 1;
+      if (cg == 0) thr_sh[m * 128 + quarter * 32 + lane] = INT_MIN >> 1;
       asm volatile("bar.sync 1, 512;" ::: "memory");
       // parity bits of this warp's 64 columns, fetched one tile ahead so that an insertion never waits on memory
       uint2 pb_next = __ldg(reinterpret_cast<const uint2*>(par + (((int)t_begin + cg * 64) >> 5)));
@@ -380,7 +380,8 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         const uint2 pb = pb_next;
         if (j + 1 < tiles) pb_next = __ldg(reinterpret_cast<const uint2*>(par + ((col0 + I8_TN) >> 5)));
         uint32_t acc0[32], acc1[32];
-        const int shared_thr = *reinterpret_cast<volatile int*>(sh);
+        int shared_thr;
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(shared_thr) : "r"(sh));
         const uint32_t phase = m == 0 ? (buf == 1u ? 1u : 0u) : (buf == 1u ? 0u : 1u);
 #ifdef I8_TRACE
         const bool tr = trace && blockIdx.x == 0 && un == 0 && j >= 6000 && j < 6064 && lane == 0;
@@ -419,7 +420,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
