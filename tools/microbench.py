@@ -1,0 +1,19 @@
+#!/usr/bin/env python
+"""Issue rates of the instructions the hot kernels are made of (hpusm_microbench_*): LOP3 / POPC for the Hamming
+kernel's two-pipe roofline, 2- and 3-input integer / float max for the max-scan epilogues of the L2 engines.
+Output of round 1 on a B200: profiles/r1_microbench.txt."""
+import torch, importlib, sys
+sys.path.insert(0, ".")
+import hpusm
+dev = torch.device("cuda:0")
+for op in ["lop3", "popc", "imax3", "fmax3", "imax", "fmax"]:
+    for thr in (128, 512):
+        iters = 1 << 16
+        blocks = 148 * (1024 // thr)
+        hpusm.engine.microbench_popc(blocks, thr, iters, dev, op=op)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); hpusm.engine.microbench_popc(blocks, thr, iters, dev, op=op); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        ops = blocks * thr * iters
+        print(op, thr, "%.1f Gop/s" % (ops / ms / 1e6), "-> %.1f lanes/clk/SM at 1.9 GHz" % (ops / ms / 1e6 / 148 / 1.9))
