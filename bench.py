@@ -274,12 +274,11 @@ def run_ours(args, rank, world, device):
     h_idx = torch.empty((nq, 2), dtype=torch.int32).pin_memory()
     h_dst = torch.empty((nq, 2), dtype=torch.float32).pin_memory()
     h_keep = torch.empty((nq,), dtype=torch.uint8).pin_memory()
-    dq, dt = torch.empty_like(q), torch.empty_like(t)
+    # the public host-array entry point: row chunks copied on a copy stream while earlier chunks are being matched
+    streamed = hp.retrieval.StreamedL2Matcher(nq, nt, 128, device, mode=l2_mode)
 
     def e2e_step():
-        dq.copy_(hq, non_blocking=True)
-        dt.copy_(ht, non_blocking=True)
-        mi, md, kp, _ = hp.retrieval.knn2_sharded(dq, dt, rank * nt, kind="l2", ratio=0.8, knn_fn=local_knn)
+        mi, md, kp, _ = hp.retrieval.knn2_sharded(hq, ht, rank * nt, kind="l2", ratio=0.8, knn_fn=streamed)
         h_idx.copy_(mi, non_blocking=True)
         h_dst.copy_(md, non_blocking=True)
         h_keep.copy_(kp, non_blocking=True)

@@ -214,6 +214,23 @@ def test_l2_edge_shapes(hpusm, cuda_device, nq, nt, d, kind, mode):
         assert_l2_parity(idx, dist, ri, rd, q, t)
 
 
+def test_l2_streamed_host_matcher(hpusm, cuda_device):
+    """retrieval.StreamedL2Matcher (host arrays, chunked H2D under the compute, per-chunk top-2 merged) returns exactly
+    what one knn2_l2 call on the whole arrays returns: ragged chunks, a 1-row tail, duplicates across chunk borders."""
+    for nq, nt, qc, tf, tc in [(5000, 9001, 2048, 1000, 3000), (300, 4097, 512, 1, 1024), (1000, 700, 4096, 4096, 4096),
+                               (700, 2049, 100, 2048, 1 << 20)]:
+        q, t = hpusm.synth.sift_like(nq, nt, seed=nq + nt, planted=0.3)
+        t[nt - 1] = t[0]
+        t[nt // 2] = t[1]
+        m = hpusm.retrieval.StreamedL2Matcher(nq, nt, 128, cuda_device, q_chunk=qc, t_first=tf, t_chunk=tc)
+        for _ in range(2):  # buffers are reused from call to call
+            idx, dist = m(torch.from_numpy(q).pin_memory(), torch.from_numpy(t).pin_memory())
+            ri, rd = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device))
+            assert torch.equal(idx, ri) and torch.equal(dist, rd)
+    with pytest.raises(ValueError):
+        m(dev(q, cuda_device), dev(t, cuda_device))
+
+
 def test_l2_auto_equals_simt_at_scale(hpusm, cuda_device):
     """Size-independent property at a size no CPU oracle reaches quickly: the tensor-core engine and the exact
     CUDA-core brute force agree bit for bit on integer-valued descriptors (65536 x 262144)."""
