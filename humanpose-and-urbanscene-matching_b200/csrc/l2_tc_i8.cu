@@ -46,6 +46,7 @@ constexpr int I8_BAUG_BYTES = I8_TN * 32;               // [128 rows][32 u8] swi
 constexpr int I8_B_BYTES = I8_BMAIN_BYTES + I8_BAUG_BYTES;      // 20 KB per stage
 constexpr int I8_SMEM_BYTES = I8_STAGES * I8_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
                               I8_QB * 4 /*shared thresholds*/;
+constexpr uint32_t I8_SLEEP_NS = 20000; // suspend-time hint of the pipeline waits
 constexpr int I8_HB = 1000000;        // bias of the folded half-norm; ||t||^2 < 2 HB is required
 
 // Instruction descriptor: D = S32, A = B = U8, both K-major, N = 128, M = 128.
@@ -251,7 +252,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         const int tiles = (int)((t_end - t_begin + I8_TN - 1) / I8_TN);
         for (int j = 0; j < tiles; ++j, ++it) {
           const int s = it % I8_STAGES;
-          mbar_wait(empty + s, ((it / I8_STAGES) & 1) ^ 1);
+          mbar_wait_sleepy(empty + s, ((it / I8_STAGES) & 1) ^ 1, I8_SLEEP_NS);
           mbar_expect_tx(full + s, I8_B_BYTES);
           const int row0 = (int)(t_begin + (int64_t)j * I8_TN);
           uint8_t* bs = smem_b + s * I8_B_BYTES;
@@ -276,7 +277,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
       tc_fence_after();
       for (int j = 0; j < tiles; ++j, ++it) {
         const int s = it % I8_STAGES;
-        mbar_wait(full + s, (it / I8_STAGES) & 1);
+        mbar_wait_sleepy(full + s, (it / I8_STAGES) & 1, I8_SLEEP_NS);
         const uint64_t bdesc = umma_desc_sw128(b_addr + s * I8_B_BYTES);
         const uint64_t bdesc_aug = umma_desc_sw32(b_addr + s * I8_B_BYTES + I8_BMAIN_BYTES);
 #pragma unroll
@@ -285,7 +286,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
           const bool tr = trace && blockIdx.x == 0 && it >= 6000 && it < 6064 && lane == 0;
           if (tr) trace[((it - 6000) * 2 + m) * 8 + 0] = clock64();
 #endif
-          mbar_wait(tmem_empty + buf, buf_phase ^ 1);   // the epilogue has read this accumulator out
+          mbar_wait_sleepy(tmem_empty + buf, buf_phase ^ 1, I8_SLEEP_NS);   // the epilogue has read this accumulator out
           tc_fence_after();
 #ifdef I8_TRACE
           if (tr) trace[((it - 6000) * 2 + m) * 8 + 1] = clock64();
@@ -387,7 +388,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         const bool tr = trace && blockIdx.x == 0 && un == 0 && j >= 6000 && j < 6064 && lane == 0;
         if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 8 + (ew & 7)] = clock64();
 #endif
-        mbar_wait(tmem_full + buf, phase);
+        mbar_wait_sleepy(tmem_full + buf, phase, I8_SLEEP_NS);
         tc_fence_after();
 #ifdef I8_TRACE
         if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 24 + (ew & 7)] = clock64();

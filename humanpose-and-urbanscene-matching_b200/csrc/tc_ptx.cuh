@@ -29,6 +29,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait with a suspend-time hint: the thread may sleep up to `ns` nanoseconds per try (it is woken when the phase
+// completes), which takes polling instructions out of the issue slots the epilogue warps need.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -86,6 +86,19 @@ def test_shard_range_covers_everything():
             assert all(lo % 128 == 0 or lo == n for lo, _ in spans)
 
 
+def test_streamed_matcher_chunk_bounds():
+    """StreamedL2Matcher._bounds: the ranges tile [0, n) in order, and no range has fewer than 2 rows unless n does."""
+    import importlib
+    rt = importlib.import_module("humanpose-and-urbanscene-matching_b200").retrieval
+    for n in (1, 2, 3, 700, 2049, 4097, 1 << 20):
+        for first in (0, 1, 2, 2048, n, n + 5):
+            for chunk in (1, 2, 1000, 4096, 1 << 20):
+                b = rt.StreamedL2Matcher._bounds(n, first, chunk)
+                assert b[0][0] == 0 and b[-1][1] == n
+                assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+                assert all(hi - lo >= min(2, n) for lo, hi in b), (n, first, chunk, b)
+
+
 def test_world2_gloo_sharded_equals_unsharded(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
