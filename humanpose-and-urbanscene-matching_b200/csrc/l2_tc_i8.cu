@@ -11,16 +11,26 @@
 // folded into the contraction through 32 augmentation columns: A = [q | 1 128 128 ...], B = [t | d0 d1 d2 ...] with
 // HB - h = d0 + 128 (d1 + ... + d31)) and  K + 2 HB = 2 s - (||t||^2 & 1).  The epilogue max-scans s; only a column
 // with 2 s > K1 (the running second best) can matter, and for those few the comparison is made on the exact K with the
-// parity bit taken from a bit array (each epilogue warp keeps the 64 bits of its columns in registers).  The result is the exact top-2 on (K, index), ties to the lower index
-// as OpenCV resolves them; the candidates then go through l2_rerank_finalize (exact FP32 distances from the ORIGINAL
-// float32 rows).
+// parity bit taken from a bit array (each epilogue warp keeps the 64 bits of its columns in registers).  The result is
+// the exact top-2 on (K, index), ties to the lower index as OpenCV resolves them; the candidates then go through
+// l2_rerank_finalize (exact FP32 distances from the ORIGINAL float32 rows).
 //
 // The prep kernel verifies the value range for every row (integers in [0,255], ||t||^2 < 2 HB); HPUSM_L2_AUTO falls
 // through to the bf16 engines (l2_tc.cu, l2_tc_split.cu) when it does not hold.
 //
-// Kernel shape: as l2_tc.cu (persistent CTA per SM, TMA producer warp, MMA issuer warp, two 128-query tiles
-// ping-ponging on two 256-column TMEM accumulators), with a 4-stage ring of [256 x 160] u8 tiles and 16 epilogue warps
-// (the integer MMA block of a tile lasts only 640 cycles, so the accumulator read-out has to be twice as parallel).
+// Kernel shape (one persistent CTA per SM, 18 warps; a unit = 256 queries x one split of the database):
+//   warp 0      TMEM allocator, then TMA producer: an 8-stage ring of database tiles ([128 rows x 160 B] u8, 20 KB:
+//               a SWIZZLE_128B slab of the 128 descriptor bytes + a SWIZZLE_32B slab of the 32 augmentation bytes)
+//   warp 1      MMA issuer (one ELECTED lane): per piece = (database tile, 128-query tile) 5 tcgen05.mma.kind::i8
+//               (M = 128, N = 128, K = 32).  The A operand (query rows) is read from TENSOR MEMORY, so shared memory
+//               serves only the database operand; three 128-column accumulators rotate.
+//   warps 2-17  epilogue.  At the start of a unit they copy the unit's query rows into TMEM (tcgen05.st, thread = row).
+//               Then every accumulator is pulled by eight warps at once (two per TMEM lane quarter, 64 columns each):
+//               tcgen05.ld, release the accumulator, scan (VIMNMX3 trees + one compare per 64 values; the rare
+//               insertion is a compact loop).  Warps 2-9 serve query tile 0, warps 10-17 tile 1; the two column
+//               groups of a row share their threshold through shared memory and are separate candidate parts.
+// DESIGN.md (K1) has the measurements behind each of these choices.  -DI8_TRACE compiles an in-kernel timestamp trace
+// of the pipeline (tools/i8_trace.py prints it).
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
@@ -51,15 +61,6 @@ constexpr int I8_HB = 1000000;        // bias of the folded half-norm; ||t||^2 <
 
 // Instruction descriptor: D = S32, A = B = U8, both K-major, N = 128, M = 128.
 constexpr uint32_t I8_IDESC = (2u << 4) | ((uint32_t)(I8_TN >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 
 // ---- operand preparation --------------------------------------------------------------------------------
 // One warp per row: float32 -> u8 operand row of 160 bytes and the range check (flag[0] |= 1 when a value is not an
