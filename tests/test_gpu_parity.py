@@ -168,6 +168,30 @@ def test_l2_i8_engine_ties_and_parity(hpusm, cuda_device):
         np.testing.assert_array_equal(dist.cpu().numpy(), rd)
 
 
+def test_l2_i8_fuzz_against_fp32_engine(hpusm, cuda_device):
+    """Random shapes (ragged tails on both sides, fewer rows than one tile, several database splits), random value
+    ranges (sparse rows, saturated rows, duplicates): the u8 engine and the exact FP32 CUDA-core engine agree bit for
+    bit on indices and distances."""
+    rng = np.random.default_rng(2024)
+    E = hpusm.engine
+    for case in range(24):
+        nq = int(rng.integers(1, 3000))
+        nt = int(rng.integers(2, 40000)) if case % 4 else int(rng.integers(2, 300))
+        hi = int(rng.choice([2, 16, 100, 256]))
+        q = rng.integers(0, hi, (nq, 128)).astype(np.float32)
+        t = rng.integers(0, hi, (nt, 128)).astype(np.float32)
+        if hi == 256:  # keep ||t||^2 under the engine's 2e6 bound: zero two thirds of every row
+            t *= rng.integers(0, 3, (nt, 128)) == 0
+            q *= rng.integers(0, 3, (nq, 128)) == 0
+        dup = rng.integers(0, nt, max(1, nt // 50))
+        t[dup] = t[rng.integers(0, nt, dup.size)]  # exact duplicates -> distance ties
+        q[rng.integers(0, nq, max(1, nq // 20))] = t[rng.integers(0, nt, max(1, nq // 20))]  # zero-distance hits
+        dq, dt = dev(q, cuda_device), dev(t, cuda_device)
+        ia, da = hpusm.knn2_l2(dq, dt, mode=E.L2_TC_I8)
+        ib, db_ = hpusm.knn2_l2(dq, dt, mode=E.L2_SIMT)
+        assert torch.equal(ia, ib) and torch.equal(da, db_), (case, nq, nt, hi)
+
+
 def test_l2_auto_engine_selection(hpusm, cuda_device):
     """HPUSM_L2_AUTO: u8 engine for integers in [0,255] with bounded norms, bf16 exact-int engine for other integers
     with |v| <= 256, split engine for the rest; HPUSM_L2_TC_I8 on data it cannot hold is an error, not a wrong answer."""
