@@ -8,8 +8,8 @@
 //   ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t      ->  per query, order the database by  K = 2 q.t - ||t||^2  (largest first)
 //
 // u8 operands cannot carry the factor 2, so the accumulator holds  s = q.t + (HB - (||t||^2 >> 1))  (the bracket is
-// folded into the contraction through 32 augmentation columns: A = [q | 1 128 128 ...], B = [t | d0 d1 d2 ...] with
-// HB - h = d0 + 128 (d1 + ... + d31)) and  K + 2 HB = 2 s - (||t||^2 & 1).  The epilogue max-scans s; only a column
+// folded into the contraction through 32 augmentation columns: A = [q | 1 255 255 ...], B = [t | d0 d1 d2 ...] with
+// HB - h = d0 + 255 (d1 + ... + d31)) and  K + 2 HB = 2 s - (||t||^2 & 1).  The epilogue max-scans s; only a column
 // with 2 s > K1 (the running second best) can matter, and for those few the comparison is made on the exact K with the
 // parity bit taken from a bit array (each epilogue warp keeps the 64 bits of its columns in registers).  The result is
 // the exact top-2 on (K, index), ties to the lower index as OpenCV resolves them; the candidates then go through
@@ -57,7 +57,7 @@ constexpr int I8_B_BYTES = I8_BMAIN_BYTES + I8_BAUG_BYTES;      // 20 KB per sta
 constexpr int I8_SMEM_BYTES = I8_STAGES * I8_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
                               I8_QB * 4 /*shared thresholds*/;
 constexpr uint32_t I8_SLEEP_NS = 20000; // suspend-time hint of the pipeline waits
-constexpr int I8_HB = 1000000;        // bias of the folded half-norm; ||t||^2 < 2 HB is required
+constexpr int I8_HB = 2000000;        // bias of the folded half-norm; ||t||^2 < 2 HB is required (32 u8 x u8 columns hold 2.08e6)
 
 // Instruction descriptor: D = S32, A = B = U8, both K-major, N = 128, M = 128.
 constexpr uint32_t I8_IDESC = (2u << 4) | ((uint32_t)(I8_TN >> 3) << 17) | ((128u >> 4) << 24);
@@ -65,8 +65,8 @@ constexpr uint32_t I8_IDESC = (2u << 4) | ((uint32_t)(I8_TN >> 3) << 17) | ((128
 // ---- operand preparation --------------------------------------------------------------------------------
 // One warp per row: float32 -> u8 operand row of 160 bytes and the range check (flag[0] |= 1 when a value is not an
 // integer in [0,255] or a database norm exceeds 2 HB).
-//   query side    (is_db == 0): [q | 1 128 128 ... 128]
-//   database side (is_db == 1): [t | d0 d1 ... d31] with HB - (||t||^2 >> 1) = d0 + 128 (d1 + ... + d31), d0 < 128;
+//   query side    (is_db == 0): [q | 1 255 255 ... 255]
+//   database side (is_db == 1): [t | d0 d1 ... d31] with HB - (||t||^2 >> 1) = d0 + 255 (d1 + ... + d31), d0 < 255;
 //                               bit `row` of par = ||t||^2 & 1.  Rows n..n_pad are zero: s = 0, below or tied with every real
 //                               row, and their index is the highest.
 __global__ void __launch_bounds__(256)
@@ -98,13 +98,13 @@ l2_i8_prep_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int is_
   reinterpret_cast<uint32_t*>(dst)[lane] = packed;
   // augmentation byte `lane`
   uint32_t a;
-  if (!is_db) a = lane == 0 ? 1u : 128u;
+  if (!is_db) a = lane == 0 ? 1u : 255u;
   else if (row >= n || bad) a = 0u;
   else {
     const int rem = I8_HB - h;
-    if (lane == 0) a = (uint32_t)(rem & 127);
+    if (lane == 0) a = (uint32_t)(rem % 255);
     else {
-      int m = (rem >> 7) - 255 * (lane - 1);
+      int m = rem / 255 - 255 * (lane - 1);
       a = (uint32_t)(m < 0 ? 0 : (m > 255 ? 255 : m));
     }
   }

@@ -44,7 +44,7 @@ extern "C" {
 #define HPUSM_L2_TC_SPLIT 3 /* tcgen05, hi/lo bf16 split (general float), top-4 + verified FP32 re-rank; synchronises
                                the stream once (count of rows sent to the exact fallback)                          */
 #define HPUSM_L2_TC_I8 4  /* tcgen05 kind::i8, u8 operands, s32 accumulation: integer values in [0,255] and squared
-                             norms below 2,000,000 (checked on the device; HPUSM_ERR_UNSUPPORTED otherwise)         */
+                             norms below 4,000,000 (checked on the device; HPUSM_ERR_UNSUPPORTED otherwise)         */
 
 int hpusm_version(void);
 const char* hpusm_last_error(void);

@@ -155,7 +155,7 @@ def test_l2_i8_engine_ties_and_parity(hpusm, cuda_device):
     """HPUSM_L2_TC_I8 orders by s = q.t - (||t||^2 >> 1) and settles the dropped parity bit only for columns that can
     matter.  Tiny value ranges make thousands of columns tie in s with differing parity, and make exact distance ties:
     the result must still be the oracle's (distance, then lower index), bit for bit."""
-    for nq, nt, hi, seed in [(700, 9000, 2, 1), (300, 5000, 4, 2), (513, 2049, 3, 3), (64, 300, 180, 4)]:
+    for nq, nt, hi, seed in [(700, 9000, 2, 1), (300, 5000, 4, 2), (513, 2049, 3, 3), (64, 300, 256, 4)]:
         rng = np.random.default_rng(seed)
         q = rng.integers(0, hi, (nq, 128)).astype(np.float32)
         t = rng.integers(0, hi, (nt, 128)).astype(np.float32)
@@ -180,7 +180,7 @@ def test_l2_i8_fuzz_against_fp32_engine(hpusm, cuda_device):
         hi = int(rng.choice([2, 16, 100, 256]))
         q = rng.integers(0, hi, (nq, 128)).astype(np.float32)
         t = rng.integers(0, hi, (nt, 128)).astype(np.float32)
-        if hi == 256:  # keep ||t||^2 under the engine's 2e6 bound: zero two thirds of every row
+        if hi == 256 and case % 2:  # sparse rows next to dense ones (a dense uniform row has ||t||^2 ~ 2.8e6 < 4e6)
             t *= rng.integers(0, 3, (nt, 128)) == 0
             q *= rng.integers(0, 3, (nq, 128)) == 0
         dup = rng.integers(0, nt, max(1, nt // 50))
@@ -200,7 +200,7 @@ def test_l2_auto_engine_selection(hpusm, cuda_device):
     cases = [
         (rng.integers(0, 256, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_I8),
         (rng.integers(-9, 10, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_INT),      # negative query values
-        (rng.integers(0, 100, (300, 128)), rng.integers(200, 256, (900, 128)), E.L2_TC_INT),    # ||t||^2 > 2e6
+        (rng.integers(0, 100, (300, 128)), rng.integers(200, 256, (900, 128)), E.L2_TC_INT),    # ||t||^2 > 4e6
         (rng.integers(0, 100, (300, 128)) + 0.5, rng.integers(0, 100, (900, 128)), E.L2_TC_SPLIT),
     ]
     for q, t, want in cases:
