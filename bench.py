@@ -461,7 +461,7 @@ def run_orb(args, rank, world, device, hp):
                   "d2h_bytes_per_step": int(hs.numel() * 4)}
     out["gpu_launches"] = int(r["launches"])
     out["roofline"] = {"bound": "integer pipes (16 LOP3 + 4 POPC.32 per pair)", "achieved": ach / 1e12, "peak": lpeak / 1e12, "unit": "Tlop3/s",
-                       "frac": t_bound / (k_ms * 1e-3), "traffic": None, "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
+                       "frac": t_bound / (k_ms * 1e-3), "traffic": measured_traffic("orb:%dx%d" % (args.images, world)), "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
                        "peak_source": "hpusm_microbench_lop3 / hpusm_microbench_popc measured in this run",
                        "popc_peak_Tpopc": ppeak / 1e12, "naive_popc_bound_ms": 8.0 * pairs_per_launch / ppeak * 1e3,
                        "hbm_GBps_algorithmic": (db.numel() + query.numel()) / (k_ms * 1e-3) / 1e9}
@@ -552,7 +552,7 @@ def run_ransac(args, rank, world, device, hp):
                   "d2h_bytes_per_step": int(hH.numel() * 8 + hm.numel()), "note": "full findHomography replacement incl. refinement, %d pairs per step" % ne}
     out["gpu_launches"] = int(r["launches"])
     out["roofline"] = {"bound": "fp32 pipe", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s",
-                       "frac": flops / (k_ms * 1e-3) / (148 * 128 * 2 * 1.965e9), "traffic": None, "kernel_ms": k_ms,
+                       "frac": flops / (k_ms * 1e-3) / (148 * 128 * 2 * 1.965e9), "traffic": measured_traffic("ransac:%dx%d" % (args.pairs, world)), "kernel_ms": k_ms,
                        "kernel_launches": int(r["kernel_n"]), "peak_source": "nominal 148 SM x 128 FMA lanes x 1965 MHz (no measured FP32 peak in MEASURED_PEAKS.json)",
                        "hbm_GBps_algorithmic": src.numel() * 8 / (k_ms * 1e-3) / 1e9, "reprojections_per_s": evals / (k_ms * 1e-3)}
     out["clocks"] = r["clocks"]
@@ -633,7 +633,7 @@ def run_pose(args, rank, world, device, hp):
     out["e2e"] = {"value": ne * world * args.steps / (e["ms"] * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": int(hdb.numel() * 4),
                   "d2h_bytes_per_step": 16 * 12, "note": "%d poses per step from pinned host memory" % ne}
     out["gpu_launches"] = int(r["launches"])
-    out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
+    out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("pose:%dx%d" % (args.poses, world)), "kernel_ms": k_ms,
                        "kernel_launches": int(r["kernel_n"]), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk else "fallback 6650 GB/s"}
     out["clocks"] = r["clocks"]
     if not args.no_cpu_baseline and world == 1:
