@@ -432,13 +432,12 @@ def run_orb(args, rank, world, device, hp):
     r = tm.run(step)
     scores = r["out"]
     hq, hdb = query.cpu().pin_memory(), db.cpu().pin_memory()
-    dq, ddb = torch.empty_like(query), torch.empty_like(db)
     hs = torch.empty((args.images,), dtype=torch.int32).pin_memory()
+    # the public host-array entry point: runs of whole images uploaded on a copy stream while earlier runs are scored
+    streamed = rt.StreamedImageScorer(per, 32, offs, device)
 
     def e2e_step():
-        dq.copy_(hq, non_blocking=True)
-        ddb.copy_(hdb, non_blocking=True)
-        hs.copy_(rt.image_scores_sharded(dq, ddb, offs, 0.8), non_blocking=True)
+        hs.copy_(rt.image_scores_sharded(hq, hdb, offs, 0.8, score_fn=streamed), non_blocking=True)
 
     e = tm.run(e2e_step, profile=False)
     if rank != 0:
@@ -526,13 +525,12 @@ def run_ransac(args, rank, world, device, hp):
     # end to end = the full findHomography replacement (score + early-exit replay + refinement + mask) on a host batch
     ne = min(n, 4096)
     hs, hd = src[:ne * K].cpu().pin_memory(), dst[:ne * K].cpu().pin_memory()
-    ds, dd = torch.empty_like(src[:ne * K]), torch.empty_like(dst[:ne * K])
     hH, hm = torch.empty((ne, 3, 3), dtype=torch.float64).pin_memory(), torch.empty((ne * K,), dtype=torch.uint8).pin_memory()
+    # the public host-array entry point: runs of whole pairs uploaded on a copy stream while earlier runs are solved
+    streamed = hp.retrieval.StreamedHomographyBatch(offs[:ne + 1], device, 5.0, nhyp, 0.0, seed=2)
 
     def e2e_step():
-        ds.copy_(hs, non_blocking=True)
-        dd.copy_(hd, non_blocking=True)
-        Hh, mask, ninl, bh = eng.ransac_homography_batch(ds, dd, offs[:ne + 1], 5.0, nhyp, 0.0, seed=2)
+        Hh, mask, ninl = streamed(hs, hd)
         hH.copy_(Hh, non_blocking=True)
         hm.copy_(mask, non_blocking=True)
 

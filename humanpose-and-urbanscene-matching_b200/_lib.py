@@ -66,6 +66,9 @@ SIGNATURES = {
     "hpusm_ransac_homography_batch": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _f64, _u64, _i32, _p, _p, _p, _p,
                                              _p, _sz, _p]),
     "hpusm_ransac_score_batch": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _u64, _p, _p]),
+    "hpusm_ransac_homography_batch_at": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _f64, _u64, _i64, _i32, _p, _p, _p,
+                                                _p, _p, _sz, _p]),
+    "hpusm_ransac_score_batch_at": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _u64, _i64, _p, _p]),
     "hpusm_perspective_transform": (_i32, [_p, _i64, _p, _p, _p]),
     "hpusm_affine_lsq_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p]),
     "hpusm_procrustes_batch": (_i32, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -293,8 +293,8 @@ constexpr int RS_SEG = 256;
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst,
                     const int64_t* __restrict__ pair_offsets, float thresh, int nhyp, double confidence,
-                    uint64_t seed, int chunk, int32_t* __restrict__ counts_out, int32_t* __restrict__ best_hyp,
-                    int32_t* __restrict__ best_count) {
+                    uint64_t seed, int64_t pair0, int chunk, int32_t* __restrict__ counts_out,
+                    int32_t* __restrict__ best_hyp, int32_t* __restrict__ best_count) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   float4* pts = reinterpret_cast<float4*>(rs_smem);
   float* models = reinterpret_cast<float*>(rs_smem + (size_t)chunk * sizeof(float4));
@@ -340,8 +340,8 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
     bool ok = false;
     if (h < nhyp && K >= 4) {
       double sx[4], sy[4], dx[4], dy[4];
-      if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
-      else hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+      if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
+      else hypothesis_points(s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
       ok = !degenerate4(sx, sy, dx, dy);
     }
     const unsigned b = __ballot_sync(0xffffffffu, ok);
@@ -358,8 +358,8 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   for (int j = tid; j < nv; j += RS_THREADS) {
     const int h = hyp_of[j];
     double sx[4], sy[4], dx[4], dy[4], H[9];
-    if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
-    else hypothesis_points(s, d, K, seed, (uint64_t)pair, (uint64_t)h, sx, sy, dx, dy);
+    if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
+    else hypothesis_points(s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
     const bool ok = hypothesis_solve(sx, sy, dx, dy, H);
 #pragma unroll
     for (int i = 0; i < 9; ++i) models[j * 9 + i] = ok ? (float)H[i] : 0.f;
@@ -488,7 +488,7 @@ __device__ __forceinline__ void accumulate_rows(double (&acc)[RF_NSUM], const do
 // grid.x = pairs.
 __global__ void __launch_bounds__(RF_THREADS)
 ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ dst,
-                       const int64_t* __restrict__ pair_offsets, float thresh, uint64_t seed, int refine,
+                       const int64_t* __restrict__ pair_offsets, float thresh, uint64_t seed, int64_t pair0, int refine,
                        const int32_t* __restrict__ best_hyp, double* __restrict__ Hout, uint8_t* __restrict__ mask,
                        int32_t* __restrict__ ninl) {
   __shared__ double sh_H[9];
@@ -511,7 +511,7 @@ ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ 
 
   if (tid == 0) {
     double H[9];
-    bool ok = bh >= 0 && hypothesis_model(src + m0 * 2, dst + m0 * 2, (uint32_t)K, seed, (uint64_t)pair, (uint64_t)bh, H);
+    bool ok = bh >= 0 && hypothesis_model(src + m0 * 2, dst + m0 * 2, (uint32_t)K, seed, (uint64_t)(pair + pair0), (uint64_t)bh, H);
     sh_ok = ok ? 1 : 0;
     for (int i = 0; i < 9; ++i) { sh_H[i] = ok ? H[i] : 0.0; sh_Hf[i] = ok ? (float)H[i] : 0.f; }
   }
@@ -729,14 +729,14 @@ static int ransac_pick_chunk(int nhyp) {
 }
 
 static int launch_score(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                        float thresh, int nhyp, double confidence, uint64_t seed, int32_t* counts,
+                        float thresh, int nhyp, double confidence, uint64_t seed, int64_t pair0, int32_t* counts,
                         int32_t* best_hyp, int32_t* best_count, cudaStream_t st) {
   const int chunk = ransac_pick_chunk(nhyp);
   HPUSM_REQUIRE(chunk > 0, HPUSM_ERR_UNSUPPORTED, "ransac: %d hypotheses do not fit in shared memory", nhyp);
   const size_t smem = ransac_smem_bytes(nhyp, chunk);
   HPUSM_CUDA_OK(cudaFuncSetAttribute(ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HPUSM_LAUNCH_TIMED(ransac_score_kernel, (unsigned)npairs, RS_THREADS, smem, st, src, dst, pair_offsets, thresh, nhyp,
-               confidence, seed, chunk, counts, best_hyp, best_count);
+               confidence, seed, pair0, chunk, counts, best_hyp, best_count);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }
@@ -752,23 +752,30 @@ size_t hpusm_ransac_homography_workspace_bytes(int64_t total_matches, int64_t np
   return align_up((size_t)(npairs > 0 ? npairs : 1) * sizeof(int32_t), 256) * 2;
 }
 
-int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                             int64_t total_matches, float thresh, int nhyp, uint64_t seed, int32_t* counts,
-                             void* stream) {
-  HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0, HPUSM_ERR_INVALID, "hpusm_ransac_score_batch: bad sizes");
+int hpusm_ransac_score_batch_at(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
+                                int64_t total_matches, float thresh, int nhyp, uint64_t seed, int64_t pair_index0,
+                                int32_t* counts, void* stream) {
+  HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0 && pair_index0 >= 0, HPUSM_ERR_INVALID,
+                "hpusm_ransac_score_batch: bad sizes");
   if (npairs == 0) return HPUSM_OK;
   HPUSM_REQUIRE(pair_offsets && counts && ((src && dst) || total_matches == 0), HPUSM_ERR_INVALID,
                 "hpusm_ransac_score_batch: null pointer");
   HPUSM_REQUIRE(npairs < 0x40000000, HPUSM_ERR_UNSUPPORTED, "hpusm_ransac_score_batch: too many pairs for one call");
-  return launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, 0.0, seed, counts, nullptr, nullptr,
+  return launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, 0.0, seed, pair_index0, counts, nullptr, nullptr,
                       as_stream(stream));
 }
 
-int hpusm_ransac_homography_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                                  int64_t total_matches, float thresh, int nhyp, double confidence, uint64_t seed,
-                                  int refine, double* H, uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
-                                  size_t ws_bytes, void* stream) {
-  HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0, HPUSM_ERR_INVALID,
+int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
+                             int64_t total_matches, float thresh, int nhyp, uint64_t seed, int32_t* counts,
+                             void* stream) {
+  return hpusm_ransac_score_batch_at(src, dst, pair_offsets, npairs, total_matches, thresh, nhyp, seed, 0, counts, stream);
+}
+
+int hpusm_ransac_homography_batch_at(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
+                                     int64_t total_matches, float thresh, int nhyp, double confidence, uint64_t seed,
+                                     int64_t pair_index0, int refine, double* H, uint8_t* mask, int32_t* ninl,
+                                     int32_t* best_hyp, void* ws, size_t ws_bytes, void* stream) {
+  HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0 && pair_index0 >= 0, HPUSM_ERR_INVALID,
                 "hpusm_ransac_homography_batch: bad sizes");
   if (npairs == 0) return HPUSM_OK;
   HPUSM_REQUIRE(pair_offsets && H && ninl && (mask || total_matches == 0) && ((src && dst) || total_matches == 0),
@@ -780,12 +787,20 @@ int hpusm_ransac_homography_batch(const float* src, const float* dst, const int6
   cudaStream_t st = as_stream(stream);
   int32_t* bh = best_hyp ? best_hyp : reinterpret_cast<int32_t*>(ws);
   int32_t* bc = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + part);
-  int rc = launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, confidence, seed, nullptr, bh, bc, st);
+  int rc = launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, confidence, seed, pair_index0, nullptr, bh, bc, st);
   if (rc != HPUSM_OK) return rc;
   HPUSM_LAUNCH(ransac_finalize_kernel, (unsigned)npairs, RF_THREADS, 0, st, src, dst, pair_offsets, thresh, seed,
-               refine, bh, H, mask, ninl);
+               pair_index0, refine, bh, H, mask, ninl);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
+}
+
+int hpusm_ransac_homography_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
+                                  int64_t total_matches, float thresh, int nhyp, double confidence, uint64_t seed,
+                                  int refine, double* H, uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  return hpusm_ransac_homography_batch_at(src, dst, pair_offsets, npairs, total_matches, thresh, nhyp, confidence, seed, 0,
+                                          refine, H, mask, ninl, best_hyp, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -216,10 +216,12 @@ def validate_homography_batch(H):
 
 
 # ---- K3: RANSAC ----------------------------------------------------------------------------------------
-def ransac_homography_batch(src, dst, pair_offsets, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, refine=True):
+def ransac_homography_batch(src, dst, pair_offsets, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, refine=True,
+                            pair_index0=0):
     """cv2.findHomography(src, dst, RANSAC, thresh) per pair (features.py:66,:69).
 
-    Returns (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32, best_hyp [npairs] i32)."""
+    Returns (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32, best_hyp [npairs] i32).  `pair_index0`: the
+    index of this call's first pair in the sample table (a slice of a larger batch draws the larger batch's samples)."""
     src = _cuda(src, torch.float32, "src")
     dst = _cuda(dst, torch.float32, "dst")
     pair_offsets = _cuda(pair_offsets, torch.int64, "pair_offsets")
@@ -232,13 +234,14 @@ def ransac_homography_batch(src, dst, pair_offsets, thresh=5.0, nhyp=2000, confi
         ninl = torch.empty((npairs,), dtype=torch.int32, device=dev)
         best = torch.empty((npairs,), dtype=torch.int32, device=dev)
         ws = _workspace(lib.hpusm_ransac_homography_workspace_bytes(total, npairs, nhyp), dev)
-        check(lib.hpusm_ransac_homography_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
-                                                int(nhyp), float(confidence), int(seed), 1 if refine else 0, _ptr(H),
-                                                _ptr(mask), _ptr(ninl), _ptr(best), _ptr(ws), ws.numel(), _stream(dev)))
+        check(lib.hpusm_ransac_homography_batch_at(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
+                                                   int(nhyp), float(confidence), int(seed), int(pair_index0),
+                                                   1 if refine else 0, _ptr(H), _ptr(mask), _ptr(ninl), _ptr(best),
+                                                   _ptr(ws), ws.numel(), _stream(dev)))
     return H, mask, ninl, best
 
 
-def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, out=None):
+def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, out=None, pair_index0=0):
     """Inlier count of every hypothesis of every pair: counts [npairs, nhyp] i32 (-1 = degenerate sample)."""
     src = _cuda(src, torch.float32, "src")
     dst = _cuda(dst, torch.float32, "dst")
@@ -248,8 +251,8 @@ def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, ou
     dev = src.device
     with torch.cuda.device(dev):
         counts = out if out is not None else torch.empty((npairs, nhyp), dtype=torch.int32, device=dev)
-        check(lib.hpusm_ransac_score_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
-                                           int(nhyp), int(seed), _ptr(counts), _stream(dev)))
+        check(lib.hpusm_ransac_score_batch_at(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
+                                              int(nhyp), int(seed), int(pair_index0), _ptr(counts), _stream(dev)))
     return counts
 
 

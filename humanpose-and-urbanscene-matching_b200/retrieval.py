@@ -158,6 +158,109 @@ class StreamedL2Matcher:
         return engine.knn2_merge(self.part_idx, self.part_dist)
 
 
+class StreamedImageScorer:
+    """Per-image ratio-survivor counts (retrieval, C3) for a HOST descriptor database, the upload pipelined under the
+    compute: the database is cut into runs of whole images, every run is queued on a copy stream and scored by
+    hpusm_knn2_hamming_segmented as soon as it has landed.  Images are independent, so there is nothing to merge.
+
+    Callable as score_fn(q_host, db_host, seg_offsets, ratio) -> scores [nimg] int32 on the device, so it drops into
+    image_scores_sharded.  `seg_offsets` (host or device int64, [nimg + 1]) is fixed at construction.
+    """
+
+    def __init__(self, nq, nbytes, seg_offsets, device, images_per_chunk=512):
+        self.device = torch.device(device)
+        offs = torch.as_tensor(seg_offsets, dtype=torch.int64).cpu()
+        self.nimg = int(offs.numel() - 1)
+        self.nt = int(offs[-1]) if offs.numel() else 0
+        self.nq, self.nb = int(nq), int(nbytes)
+        step = max(int(images_per_chunk), 1)
+        self.chunks = []  # (first image, last image + 1, first row, last row + 1, local offsets on the device)
+        for i0 in range(0, self.nimg, step):
+            i1 = min(self.nimg, i0 + step)
+            r0, r1 = int(offs[i0]), int(offs[i1])
+            self.chunks.append((i0, i1, r0, r1, (offs[i0:i1 + 1] - r0).to(self.device)))
+        self.dq = torch.empty((self.nq, self.nb), dtype=torch.uint8, device=self.device)
+        self.ddb = torch.empty((self.nt, self.nb), dtype=torch.uint8, device=self.device)
+        self.scores = torch.empty((self.nimg,), dtype=torch.int32, device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ready = [torch.cuda.Event() for _ in self.chunks]
+        self.q_ready = torch.cuda.Event()
+
+    def __call__(self, hq, hdb, seg_offsets=None, ratio=0.8):
+        if tuple(hq.shape) != (self.nq, self.nb) or tuple(hdb.shape) != (self.nt, self.nb):
+            raise ValueError("StreamedImageScorer was built for [%d,%d] x [%d,%d]" % (self.nq, self.nb, self.nt, self.nb))
+        if hq.is_cuda or hdb.is_cuda:
+            raise ValueError("StreamedImageScorer takes HOST tensors; use engine.knn2_hamming_segmented for device tensors")
+        cur = torch.cuda.current_stream(self.device)
+        cs = self.copy_stream
+        cs.wait_stream(cur)  # the previous call's kernels no longer read the device copies
+        with torch.cuda.stream(cs):
+            self.dq.copy_(hq, non_blocking=True)
+            self.q_ready.record(cs)
+            for c, (i0, i1, r0, r1, _) in enumerate(self.chunks):
+                self.ddb[r0:r1].copy_(hdb[r0:r1], non_blocking=True)
+                self.ready[c].record(cs)
+        cur.wait_event(self.q_ready)
+        for c, (i0, i1, r0, r1, local) in enumerate(self.chunks):
+            cur.wait_event(self.ready[c])
+            if r1 == r0:  # a run of empty images
+                self.scores[i0:i1] = 0
+                continue
+            self.scores[i0:i1] = engine.knn2_hamming_segmented(self.dq, self.ddb[r0:r1], local, ratio)
+        return self.scores
+
+
+class StreamedHomographyBatch:
+    """cv2.findHomography(.., RANSAC, ..) for a batch of image pairs whose putative matches live in HOST memory
+    (features.py:66,:69 called once per pair), the upload pipelined under the compute: the batch is cut into runs of
+    whole pairs, every run is queued on a copy stream and solved as soon as it has landed.  `pair_index0` keeps each
+    run on its rows of the (seed, pair, hypothesis) sample table, so the answer is the one-call answer bit for bit.
+
+    __call__(src_host, dst_host) -> (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32) on the device.
+    """
+
+    def __init__(self, pair_offsets, device, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, pairs_per_chunk=512):
+        self.device = torch.device(device)
+        offs = torch.as_tensor(pair_offsets, dtype=torch.int64).cpu()
+        self.npairs, self.total = int(offs.numel() - 1), int(offs[-1])
+        self.args = (float(thresh), int(nhyp), float(confidence), int(seed))
+        step = max(int(pairs_per_chunk), 1)
+        self.chunks = []
+        for p0 in range(0, self.npairs, step):
+            p1 = min(self.npairs, p0 + step)
+            r0, r1 = int(offs[p0]), int(offs[p1])
+            self.chunks.append((p0, p1, r0, r1, (offs[p0:p1 + 1] - r0).to(self.device)))
+        dev = self.device
+        self.src = torch.empty((self.total, 2), dtype=torch.float32, device=dev)
+        self.dst = torch.empty((self.total, 2), dtype=torch.float32, device=dev)
+        self.H = torch.empty((self.npairs, 3, 3), dtype=torch.float64, device=dev)
+        self.mask = torch.empty((self.total,), dtype=torch.uint8, device=dev)
+        self.ninl = torch.empty((self.npairs,), dtype=torch.int32, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in self.chunks]
+
+    def __call__(self, hsrc, hdst):
+        if tuple(hsrc.shape) != (self.total, 2) or tuple(hdst.shape) != (self.total, 2):
+            raise ValueError("StreamedHomographyBatch was built for %d matches" % self.total)
+        if hsrc.is_cuda or hdst.is_cuda:
+            raise ValueError("StreamedHomographyBatch takes HOST tensors; use engine.ransac_homography_batch for device tensors")
+        cur = torch.cuda.current_stream(self.device)
+        cs = self.copy_stream
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            for c, (p0, p1, r0, r1, _) in enumerate(self.chunks):
+                self.src[r0:r1].copy_(hsrc[r0:r1], non_blocking=True)
+                self.dst[r0:r1].copy_(hdst[r0:r1], non_blocking=True)
+                self.ready[c].record(cs)
+        thresh, nhyp, conf, seed = self.args
+        for c, (p0, p1, r0, r1, local) in enumerate(self.chunks):
+            cur.wait_event(self.ready[c])
+            H, mask, ninl, _ = engine.ransac_homography_batch(self.src[r0:r1], self.dst[r0:r1], local, thresh, nhyp, conf,
+                                                              seed=seed, pair_index0=p0)
+            self.H[p0:p1], self.mask[r0:r1], self.ninl[p0:p1] = H, mask, ninl
+        return self.H, self.mask, self.ninl
+
+
 def image_scores_sharded(q, db_shard, seg_offsets_shard, ratio=0.8, score_fn=None):
     """Per-image ratio-survivor counts for a database sharded by images: [total images] int32 on every rank.
     Ranks may own different numbers of images; counts are padded to the largest shard for the gather."""

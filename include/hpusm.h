@@ -176,6 +176,17 @@ int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* 
                              int64_t npairs, int64_t total_matches, float thresh, int nhyp,
                              uint64_t seed, int32_t* counts, void* stream);
 
+/* The same two calls for a SLICE of a larger batch: pair p of this call is pair `pair_index0 + p` of the sample table, so a
+ * batch cut into chunks (pipelined uploads) or sharded over GPUs draws exactly the samples of the one-call run. */
+int hpusm_ransac_homography_batch_at(const float* src, const float* dst, const int64_t* pair_offsets,
+                                     int64_t npairs, int64_t total_matches, float thresh, int nhyp,
+                                     double confidence, uint64_t seed, int64_t pair_index0, int refine, double* H,
+                                     uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
+                                     size_t ws_bytes, void* stream);
+int hpusm_ransac_score_batch_at(const float* src, const float* dst, const int64_t* pair_offsets,
+                                int64_t npairs, int64_t total_matches, float thresh, int nhyp,
+                                uint64_t seed, int64_t pair_index0, int32_t* counts, void* stream);
+
 /* Projective transform of points, replaces cv2.perspectiveTransform (features.py:77,
  * transformation.py:38): pts [n][2] float32, H [9] float64 (device) -> out [n][2] float32. */
 int hpusm_perspective_transform(const float* pts, int64_t n, const double* H, float* out, void* stream);

@@ -238,6 +238,44 @@ def test_l2_edge_shapes(hpusm, cuda_device, nq, nt, d, kind, mode):
         assert_l2_parity(idx, dist, ri, rd, q, t)
 
 
+def test_ransac_streamed_batch_equals_one_call(hpusm, cuda_device):
+    """retrieval.StreamedHomographyBatch (host matches uploaded in runs of whole pairs, each run solved with its
+    pair_index0) returns the one-call H, mask and inlier counts bit for bit -- the sample table is keyed on the pair's
+    index in the whole batch, not in the run."""
+    src, dst, offs = hpusm.synth.ransac_batch(23, 300, 0.4, seed=3)
+    sizes = np.random.default_rng(1).integers(3, 301, 23)  # ragged pairs, one with fewer than 4 matches (no model)
+    sizes[7] = 3
+    keep = np.concatenate([np.arange(offs[p], offs[p] + sizes[p]) for p in range(23)])
+    src, dst = np.ascontiguousarray(src[keep]), np.ascontiguousarray(dst[keep])
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    want = hpusm.engine.ransac_homography_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device), 5.0, 256,
+                                                0.995, seed=7)
+    sb = hpusm.retrieval.StreamedHomographyBatch(offs, cuda_device, 5.0, 256, 0.995, seed=7, pairs_per_chunk=4)
+    for _ in range(2):
+        H, mask, ninl = sb(torch.from_numpy(src).pin_memory(), torch.from_numpy(dst).pin_memory())
+        assert torch.equal(torch.nan_to_num(H, nan=-7.0), torch.nan_to_num(want[0], nan=-7.0))
+        assert torch.equal(mask, want[1]) and torch.equal(ninl, want[2])
+    # and the slice entry point on its own: pairs 5.. of the batch, scored as pairs 5.. of the sample table
+    p0 = 5
+    r0 = int(offs[p0])
+    local = torch.from_numpy(offs[p0:] - r0).to(cuda_device)
+    c_all = hpusm.engine.ransac_score_batch(dev(src, cuda_device), dev(dst, cuda_device), dev(offs, cuda_device), 5.0, 128, seed=9)
+    c_tail = hpusm.engine.ransac_score_batch(dev(src[r0:], cuda_device), dev(dst[r0:], cuda_device), local, 5.0, 128, seed=9,
+                                             pair_index0=p0)
+    assert torch.equal(c_all[p0:], c_tail)
+
+
+def test_hamming_streamed_image_scorer(hpusm, cuda_device):
+    """retrieval.StreamedImageScorer (host database uploaded in runs of whole images under the compute) returns the
+    per-image counts of one hpusm_knn2_hamming_segmented call: ragged images, a run size that does not divide them."""
+    q, db, offs, _ = hpusm.synth.orb_database(37, per_image=300, seed=5, ragged=True)
+    want = hpusm.engine.knn2_hamming_segmented(dev(q, cuda_device), dev(db, cuda_device), dev(offs, cuda_device), 0.8)
+    sc = hpusm.retrieval.StreamedImageScorer(q.shape[0], q.shape[1], offs, cuda_device, images_per_chunk=5)
+    for _ in range(2):
+        got = sc(torch.from_numpy(q).pin_memory(), torch.from_numpy(db).pin_memory(), None, 0.8)
+        assert torch.equal(got, want)
+
+
 def test_l2_streamed_host_matcher(hpusm, cuda_device):
     """retrieval.StreamedL2Matcher (host arrays, chunked H2D under the compute, per-chunk top-2 merged) returns exactly
     what one knn2_l2 call on the whole arrays returns: ragged chunks, a 1-row tail, duplicates across chunk borders."""
