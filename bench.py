@@ -517,7 +517,7 @@ def run_ransac(args, rank, world, device, hp):
     tm = Timer(args, rank, world, device, hp)
 
     def step():
-        return eng.ransac_score_batch(src, dst, offs, 5.0, nhyp, seed=2, out=counts)
+        return eng.ransac_score_batch(src, dst, offs, 5.0, nhyp, seed=2, out=counts, pair_index0=a)  # a = this shard's first pair
 
     r = tm.run(step)
     scored = int((counts >= 0).sum().item())
