@@ -79,6 +79,7 @@ SIGNATURES = {
     "hpusm_feature_scaling_batch": (_i32, [_p, _i64, _i32, _p, _p]),
     "hpusm_pose_topk_workspace_bytes": (_sz, [_i64, _i32]),
     "hpusm_pose_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "hpusm_pose_topk_merge": (_i32, [_p, _p, _i64, _i32, _p, _p, _p]),
     "hpusm_microbench_popc": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_lop3": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_minmax": (_i32, [_i32, _i64, _i32, _i64, _p, _p]),

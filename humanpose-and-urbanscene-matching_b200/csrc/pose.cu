@@ -933,4 +933,16 @@ int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t
   return HPUSM_OK;
 }
 
+int hpusm_pose_topk_merge(const float* cand_score, const int64_t* cand_index, int64_t count, int k, float* top_score,
+                          int64_t* top_index, void* stream) {
+  HPUSM_REQUIRE(count >= 0 && count <= TK_TILE && k > 0 && k <= TK_MAXK, HPUSM_ERR_INVALID,
+                "hpusm_pose_topk_merge: count must be in 0..%d and k in 1..%d", TK_TILE, TK_MAXK);
+  HPUSM_REQUIRE(top_score && top_index && (count == 0 || (cand_score && cand_index)), HPUSM_ERR_INVALID,
+                "hpusm_pose_topk_merge: null pointer");
+  HPUSM_LAUNCH(pose_topk_reduce_kernel, 1, TK_THREADS, 0, as_stream(stream), cand_score, cand_index, count, k, top_score,
+               top_index);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
 }  // extern "C"

@@ -396,6 +396,19 @@ def pose_topk(match, score, k=16, index_offset=0):
     return ts, ti, cnt
 
 
+def pose_topk_merge(cand_score, cand_index, k=16):
+    """k lexicographically smallest (score, index) of up to 4096 candidates (index < 0 = padding): (score [k], index [k])."""
+    cand_score = _cuda(cand_score.reshape(-1), torch.float32, "cand_score")
+    cand_index = _cuda(cand_index.reshape(-1), torch.int64, "cand_index")
+    dev = cand_score.device
+    with torch.cuda.device(dev):
+        ts = torch.empty((k,), dtype=torch.float32, device=dev)
+        ti = torch.empty((k,), dtype=torch.int64, device=dev)
+        check(lib.hpusm_pose_topk_merge(_ptr(cand_score), _ptr(cand_index), cand_score.numel(), int(k), _ptr(ts), _ptr(ti),
+                                        _stream(dev)))
+    return ts, ti
+
+
 def microbench_popc(blocks, threads, iters, device, op="popc"):
     """op: "popc" | "lop3" | "imax3" | "fmax3" | "imax" | "fmax" -- every thread issues `iters` of that instruction."""
     sink = torch.zeros((1,), dtype=torch.int32, device=device)

@@ -276,42 +276,30 @@ def image_scores_sharded(q, db_shard, seg_offsets_shard, ratio=0.8, score_fn=Non
     return torch.cat([g[r, :sizes[r]] for r in range(n)])
 
 
-def pose_topk_sharded(query, db_shard, row_offset, k=16, match_fn=None, topk_fn=None):
-    """k best-scoring matching poses of a pose database sharded by rows: (scores [k], global indices [k], matches)."""
+def pose_topk_sharded(query, db_shard, row_offset, k=16, match_fn=None, topk_fn=None, merge_fn=None):
+    """k best-scoring matching poses of a pose database sharded by rows: (scores [k], global indices [k], matches).
+
+    One all-gather: every rank packs its k (score, index) pairs and its match count into one int64 vector.  The union
+    is reduced by `merge_fn` (default on CUDA tensors: one launch of the top-k merge kernel; otherwise torch sorts)."""
     match_fn = match_fn or engine.pose_match_batch
     topk_fn = topk_fn or engine.pose_topk
     match, score = match_fn(query, db_shard)
     ts, ti, cnt = topk_fn(match, score, k, row_offset)
-    gs, gi, gc = allgather(ts), allgather(ti), allgather(cnt)
-    s, i = gs.flatten(), gi.flatten()
+    rank, n = world()
+    if n == 1:
+        return ts, ti, cnt.sum()
+    packed = torch.cat([ts.contiguous().view(torch.int32).to(torch.int64), ti.to(torch.int64), cnt.reshape(1).to(torch.int64)])
+    g = allgather(packed)  # [n, 2k + 1]
+    s = g[:, :k].to(torch.int32).contiguous().view(torch.float32).flatten()
+    i = g[:, k:2 * k].contiguous().flatten()
+    total = g[:, 2 * k].sum()
+    if merge_fn is None and s.is_cuda and s.numel() <= 4096:
+        merge_fn = engine.pose_topk_merge
+    if merge_fn is not None:
+        ms, mi = merge_fn(s, i, k)
+        return ms, mi, total
     s = torch.where(i >= 0, s, torch.full_like(s, float("inf")))
     # lexicographic (score, index): stable sort by index first, then by score
     by_idx = torch.argsort(i, stable=True)
     order = by_idx[torch.argsort(s[by_idx], stable=True)][:k]
-    return s[order], i[order], gc.sum()
-
-
-def scene_retrieval(query_desc, query_kp, db_desc, db_kp, seg_offsets, ratio=0.8, min_match=16, thresh=5.0, nhyp=2000,
-                    confidence=0.995, seed=0, query_pose=None, db_poses=None, query_size=None):
-    """One query image against an image database, the whole of features.match_and_draw + validate_homography per
-    database image (features.py:57-105,:177-211) without leaving the device: segmented Hamming kNN-2 + ratio ->
-    per-image match lists -> batched RANSAC in both directions -> homography sanity flags.
-
-    Returns a dict of device tensors, one entry per database image: n_matches, n_inliers, H (model->input, i.e.
-    query->image), H2 (image->query), valid, plus the match lists (pair_offsets, src, dst, mask).  With `query_pose`
-    [18,2], `db_poses` [nimg,18,2] (float64) and `query_size` = (width, height) of the query image the scene score of
-    urban_scene.match_scene_multi (perspective correction + affine fit of pose and 5 background matches,
-    urban_scene.py:80-145) is added as `score`: +inf where the homography is missing or fails validate_homography,
-    to be compared with thresholds.AFFINE_TRANS_WHOLE_DISTANCE (matching.py:75)."""
-    score, best = engine.knn2_hamming_segmented(query_desc, db_desc, seg_offsets, ratio, want_best_idx=True)
-    offs, src, dst, sel = engine.segment_matches(best, score, query_kp, db_kp, min_match)
-    H, mask, ninl, _ = engine.ransac_homography_batch(src, dst, offs, thresh, nhyp, confidence, seed)
-    H2, _, _, _ = engine.ransac_homography_batch(dst, src, offs, thresh, nhyp, confidence, seed)
-    valid = engine.validate_homography_batch(H)
-    out = {"n_matches": score, "n_inliers": ninl, "H": H, "H2": H2, "valid": valid, "pair_offsets": offs, "src": src,
-           "dst": dst, "mask": mask, "sel": sel}
-    if query_pose is not None and db_poses is not None and query_size is not None:
-        sc, picks = engine.scene_score_batch(src, dst, offs, mask, H2, query_pose, db_poses, query_size[0], query_size[1], seed)
-        out["score"] = torch.where(valid.bool(), sc, torch.full_like(sc, float("inf")))
-        out["picks"] = picks
-    return out
+    return s[order], i[order], total

@@ -269,6 +269,10 @@ size_t hpusm_pose_topk_workspace_bytes(int64_t n, int k);
 int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t index_offset, int k,
                     float* top_score, int64_t* top_index, int32_t* match_count, void* ws,
                     size_t ws_bytes, void* stream);
+/* Merge of candidate lists (the all-gathered per-rank top-k lists): the k lexicographically smallest (score, index)
+ * among `count` <= 4096 candidates; entries with index < 0 are padding.  One launch. */
+int hpusm_pose_topk_merge(const float* cand_score, const int64_t* cand_index, int64_t count, int k, float* top_score,
+                          int64_t* top_index, void* stream);
 
 /* Integer-pipe micro-benchmarks: every thread issues `iters` POPC.32 (resp. LOP3) in 8 independent chains; returns
  * nothing useful in `sink`.  bench.py uses them as the measured denominators of the Hamming roofline. */

@@ -449,6 +449,31 @@ def test_pose_topk(hpusm, cuda_device):
     assert int(cnt.item()) == int(match.sum())
 
 
+def test_pose_topk_large_and_merge(hpusm, cuda_device):
+    """More than one reduction level (3 M entries -> 733 partial lists -> 3 -> 1) and the candidate-list merge used
+    after the all-gather: both equal the lexicographic (score, index) reference, padding and ties included."""
+    rng = np.random.default_rng(9)
+    n = 3_000_000
+    match = (rng.random(n) < 0.5).astype(np.uint8)
+    score = np.round(rng.random(n) * 1000).astype(np.float32)  # heavy ties
+    ts, ti, cnt = hpusm.pose_topk(dev(match, cuda_device), dev(score, cuda_device), k=32, index_offset=0)
+    order = np.lexsort((np.arange(n), np.where(match == 1, score, np.inf)))[:32]
+    np.testing.assert_array_equal(ti.cpu().numpy(), order)
+    np.testing.assert_array_equal(ts.cpu().numpy(), score[order])
+    assert int(cnt.item()) == int(match.sum())
+    # merge of 8 per-rank lists of 16, some padded
+    cs = np.round(rng.random((8, 16)) * 20).astype(np.float32)
+    ci = rng.permutation(10_000_000)[:128].reshape(8, 16).astype(np.int64)
+    cs[3, 9:], ci[3, 9:] = np.inf, -1
+    cs[6, :], ci[6, :] = np.inf, -1
+    ms, mi = hpusm.engine.pose_topk_merge(dev(cs, cuda_device), dev(ci, cuda_device), k=16)
+    flat_s, flat_i = cs.ravel(), ci.ravel()
+    valid = flat_i >= 0
+    ref = np.lexsort((flat_i[valid], flat_s[valid]))[:16]
+    np.testing.assert_array_equal(mi.cpu().numpy(), flat_i[valid][ref])
+    np.testing.assert_array_equal(ms.cpu().numpy(), flat_s[valid][ref])
+
+
 # ---- fused post-match stage (SURVEY 8f #1) ---------------------------------------------------------------------
 def _scene_database(hpusm, nimg=14, per=400, nq=500, seed=21):
     """A query image (descriptors + keypoints) and a database in which some images show the query scene under a
