@@ -52,10 +52,11 @@ def parse_args():
     return ap.parse_args()
 
 
-def measured_traffic(key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
+def measured_traffic(key, field="bytes"):
+    """DRAM bytes per launch of the dominant kernel (or the pipe-utilisation figures, field="ncu") from the committed
+    ncu capture of this workload, or None."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key, {}).get("bytes")
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key, {}).get(field)
     except Exception:
         return None
 
@@ -332,7 +333,8 @@ def run_ours(args, rank, world, device):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt)),
                      "kernel_ms": k_ms, "kernel_launches": int(kernel_n),
-                     "frac_of_bf16_peak": achieved / bf16_tf if bf16_tf else None, "peak_source": peak_source},
+                     "frac_of_bf16_peak": achieved / bf16_tf if bf16_tf else None, "peak_source": peak_source,
+                     "ncu": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt), "ncu")},
         "clocks": clocks,
     }
     return out
