@@ -374,6 +374,12 @@ static int tc_splits(int64_t nq, int64_t nt) {
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
+  // every split must own at least one row after its length is rounded up to whole tiles
+  while (s > 1) {
+    const int64_t rps = ((nt + s - 1) / s + TC_TN - 1) / TC_TN * TC_TN;
+    if ((s - 1) * rps < nt) break;
+    --s;
+  }
   return (int)s;
 }
 

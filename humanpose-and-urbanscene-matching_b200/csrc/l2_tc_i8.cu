@@ -376,7 +376,8 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
       if (cg == 0) thr_sh[m * 128 + quarter * 32 + lane] = INT_MIN >> 1;
       asm volatile("bar.sync 1, 512;" ::: "memory");
       // parity bits of this warp's 64 columns, fetched one tile ahead so that an insertion never waits on memory
-      uint2 pb_next = __ldg(reinterpret_cast<const uint2*>(par + (((int)t_begin + cg * 64) >> 5)));
+      uint2 pb_next = make_uint2(0u, 0u);
+      if (tiles > 0) pb_next = __ldg(reinterpret_cast<const uint2*>(par + (((int)t_begin + cg * 64) >> 5)));
       for (int j = 0; j < tiles; ++j) {
         const int col0 = (int)(t_begin + (int64_t)j * I8_TN) + cg * 64;
         const uint2 pb = pb_next;
@@ -438,6 +439,12 @@ static int i8_splits(int64_t nq, int64_t nt) {
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 48) s = 48;  // the re-rank holds splits * I8_CGS * 2 <= 192 candidates per query
+  // every split must own at least one row after its length is rounded up to whole tiles
+  while (s > 1) {
+    const int64_t rps = ((nt + s - 1) / s + I8_TN - 1) / I8_TN * I8_TN;
+    if ((s - 1) * rps < nt) break;
+    --s;
+  }
   return (int)s;
 }
 

@@ -348,6 +348,12 @@ static int split_splits(int64_t nq, int64_t nt) {
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 32) s = 32;
+  // every split must own at least one row after its length is rounded up to whole tiles
+  while (s > 1) {
+    const int64_t rps = ((nt + s - 1) / s + SP_TN - 1) / SP_TN * SP_TN;
+    if ((s - 1) * rps < nt) break;
+    --s;
+  }
   return (int)s;
 }
 

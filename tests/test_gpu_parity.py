@@ -140,7 +140,7 @@ def test_l2_tensor_engine_units_and_splits(hpusm, cuda_device, engine):
     """Explicit tcgen05 engines (HPUSM_L2_TC_INT bf16, HPUSM_L2_TC_I8 u8): several 256-query units per CTA wave,
     database splits, ragged tails on both sides, duplicate database rows (ties -> lower index)."""
     mode = _mode(hpusm, engine)
-    for nq, nt, seed in [(5000, 70001, 1), (257, 1085, 2), (40000, 4323, 3), (1, 129, 4)]:
+    for nq, nt, seed in [(5000, 70001, 1), (257, 1085, 2), (40000, 4323, 3), (1, 129, 4), (200, 100000, 5)]:
         q, t = hpusm.synth.sift_like(nq, nt, seed=seed, planted=0.3)
         t[nt // 2] = t[3]
         t[nt - 1] = t[0]
