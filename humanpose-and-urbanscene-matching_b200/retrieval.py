@@ -80,7 +80,8 @@ class StreamedL2Matcher:
     the exact re-rank.
 
     Callable as knn_fn(q_host, t_host) -> (idx [nq,2] int32, dist [nq,2] float32) on the device, so it drops into
-    knn2_sharded.  Buffers, streams and events are created once.
+    knn2_sharded.  Buffers, streams and events are created once; the returned tensors may alias them and are valid
+    until the next call.
     """
 
     def __init__(self, nq, nt, d, device, q_chunk=None, t_first=1 << 17, t_chunk=1 << 20, mode=None):
@@ -164,7 +165,8 @@ class StreamedImageScorer:
     hpusm_knn2_hamming_segmented as soon as it has landed.  Images are independent, so there is nothing to merge.
 
     Callable as score_fn(q_host, db_host, seg_offsets, ratio) -> scores [nimg] int32 on the device, so it drops into
-    image_scores_sharded.  `seg_offsets` (host or device int64, [nimg + 1]) is fixed at construction.
+    image_scores_sharded.  `seg_offsets` (host or device int64, [nimg + 1]) is fixed at construction.  The returned
+    tensor is an internal buffer, valid until the next call.
     """
 
     def __init__(self, nq, nbytes, seg_offsets, device, images_per_chunk=512):
@@ -216,7 +218,8 @@ class StreamedHomographyBatch:
     whole pairs, every run is queued on a copy stream and solved as soon as it has landed.  `pair_index0` keeps each
     run on its rows of the (seed, pair, hypothesis) sample table, so the answer is the one-call answer bit for bit.
 
-    __call__(src_host, dst_host) -> (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32) on the device.
+    __call__(src_host, dst_host) -> (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32) on the device (internal
+    buffers, valid until the next call).
     """
 
     def __init__(self, pair_offsets, device, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, pairs_per_chunk=512):
