@@ -88,6 +88,28 @@ def record_scene_pair(tag, img_model, img_input):
         save("scene_%s_%s.npz" % (tag, det_name), **arrays)
 
 
+EXTRA_SIFT_PAIRS = [("taj1_taj2", "taj1.jpg", "taj2.jpg"), ("eifel2_eifel3", "eifel2.jpg", "eifel3.jpg"),
+                    ("india1_india2", "india1.jpg", "india2.jpg")]
+
+
+def record_scene_pairs_sift_extra():
+    """More real image pairs of the reference's img/ directory, SIFT + BFMatcher(NORM_L2).knnMatch (features.py:59) +
+    filter_matches (features.py:45): real descriptor statistics (not the synthetic generator's) for the kNN engines."""
+    for tag, img_model, img_input in EXTRA_SIFT_PAIRS:
+        model = cv2.imread(os.path.join(REF, "img", img_model), 0)
+        inp = cv2.imread(os.path.join(REF, "img", img_input), 0)
+        detector, matcher = cv2.SIFT_create(), cv2.BFMatcher(cv2.NORM_L2)
+        kp_m, desc_m = detector.detectAndCompute(model, None)
+        kp_i, desc_i = detector.detectAndCompute(inp, None)
+        raw = matcher.knnMatch(desc_m, trainDescriptors=desc_i, k=2)
+        idx, dist = matches_to_arrays(raw, len(kp_m))
+        p1, p2, _ = ref_features.filter_matches(kp_m, kp_i, raw)
+        assert np.array_equal(desc_m, np.rint(desc_m)) and desc_m.max() <= 255 and desc_m.min() >= 0
+        save("scene_%s_sift_knn.npz" % tag, desc_model=desc_m.astype(np.uint8), desc_input=desc_i.astype(np.uint8),
+             kp_model=np.float32([k.pt for k in kp_m]), kp_input=np.float32([k.pt for k in kp_i]), knn_idx=idx, knn_dist=dist,
+             p_model=p1, p_input=p2)
+
+
 def record_knn_synthetic():
     # L2, SIFT-like integer-valued descriptors (C2 generator, small), with planted matches and exact ties
     q, t = synth.sift_like(700, 1500, seed=10, planted=0.1)
@@ -336,7 +358,7 @@ def record_multi_person():
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
-               record_pose, record_multi_person, record_json_parser, record_scene_score):
+               record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

@@ -135,6 +135,26 @@ def test_l2_scene_pair_sift(hpusm, cuda_device, mode):
     np.testing.assert_array_equal(p_t[:161].cpu().numpy(), g["p_input"].reshape(-1, 2))
 
 
+@pytest.mark.parametrize("mode", ["auto", "tc_i8", "tc_int", "tc_split", "simt"])
+@pytest.mark.parametrize("tag", ["taj1_taj2", "eifel2_eifel3", "india1_india2"])
+def test_l2_more_scene_pairs_sift(hpusm, cuda_device, tag, mode):
+    """Three more real image pairs of the reference (785 x 1129, 2554 x 997, 1115 x 3080 SIFT descriptors): every
+    engine returns cv2's knnMatch indices and distances bit for bit, and filter_matches' survivors."""
+    g = load_golden("scene_%s_sift_knn.npz" % tag)
+    q, t = g["desc_model"].astype(np.float32), g["desc_input"].astype(np.float32)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=_mode(hpusm, mode))
+    if mode == "auto":
+        assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_I8
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["knn_idx"])
+    np.testing.assert_array_equal(dist.cpu().numpy(), g["knn_dist"])
+    keep, count = hpusm.ratio_filter(idx, dist, 0.8)
+    n = len(g["p_model"].reshape(-1, 2))
+    assert int(count.item()) == n
+    p_q, p_t, sel, cnt = hpusm.gather_matches(dev(g["kp_model"], cuda_device), dev(g["kp_input"], cuda_device), idx, keep)
+    np.testing.assert_array_equal(p_q[:n].cpu().numpy(), g["p_model"].reshape(-1, 2))
+    np.testing.assert_array_equal(p_t[:n].cpu().numpy(), g["p_input"].reshape(-1, 2))
+
+
 @pytest.mark.parametrize("engine", ["tc_int", "tc_i8"])
 def test_l2_tensor_engine_units_and_splits(hpusm, cuda_device, engine):
     """Explicit tcgen05 engines (HPUSM_L2_TC_INT bf16, HPUSM_L2_TC_I8 u8): several 256-query units per CTA wave,

@@ -45,6 +45,19 @@ def test_scene_pair_knn_and_ratio(det):
     assert len(p1) == {"sift": 161, "orb": 250}[det]
 
 
+@pytest.mark.parametrize("tag", ["taj1_taj2", "eifel2_eifel3", "india1_india2"])
+def test_more_scene_pairs_sift_knn_and_ratio(tag):
+    """Three more image pairs of the reference's img/ directory (real SIFT statistics) through knnMatch and
+    filter_matches, recorded from the unmodified reference."""
+    g = load_golden("scene_%s_sift_knn.npz" % tag)
+    idx, dist = knn_oracle.knn2_l2(g["desc_model"].astype(np.float32), g["desc_input"].astype(np.float32))
+    np.testing.assert_array_equal(idx, g["knn_idx"])
+    np.testing.assert_array_equal(dist, g["knn_dist"])
+    p1, p2, _ = knn_oracle.filter_matches_points(g["kp_model"], g["kp_input"], idx, dist)
+    np.testing.assert_array_equal(p1, g["p_model"])
+    np.testing.assert_array_equal(p2, g["p_input"])
+
+
 def test_ransac_matches_cv2():
     """findHomography (features.py:66) on inputs whose consensus set is unique.  cv2's sampler cannot be seeded, so
     its internal winning sample differs from ours; what does not depend on it is pinned:
