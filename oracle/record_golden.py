@@ -110,6 +110,21 @@ def record_scene_pairs_sift_extra():
              p_model=p1, p_input=p2)
 
 
+def record_scene_pair_orb_extra():
+    """One more real image pair through the reference's ORB detector + BFMatcher(NORM_HAMMING).knnMatch + filter_matches."""
+    for tag, img_model, img_input in [("taj1_taj2", "taj1.jpg", "taj2.jpg")]:
+        model = cv2.imread(os.path.join(REF, "img", img_model), 0)
+        inp = cv2.imread(os.path.join(REF, "img", img_input), 0)
+        detector, matcher = ref_features.init_feature("orb")
+        kp_m, desc_m = detector.detectAndCompute(model, None)
+        kp_i, desc_i = detector.detectAndCompute(inp, None)
+        raw = matcher.knnMatch(desc_m, trainDescriptors=desc_i, k=2)
+        idx, dist = matches_to_arrays(raw, len(kp_m))
+        p1, p2, _ = ref_features.filter_matches(kp_m, kp_i, raw)
+        save("scene_%s_orb_knn.npz" % tag, desc_model=desc_m, desc_input=desc_i, kp_model=np.float32([k.pt for k in kp_m]),
+             kp_input=np.float32([k.pt for k in kp_i]), knn_idx=idx, knn_dist=dist, p_model=p1, p_input=p2)
+
+
 def record_knn_synthetic():
     # L2, SIFT-like integer-valued descriptors (C2 generator, small), with planted matches and exact ties
     q, t = synth.sift_like(700, 1500, seed=10, planted=0.1)
@@ -358,7 +373,8 @@ def record_multi_person():
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
-               record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra):
+               record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra,
+               record_scene_pair_orb_extra):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

@@ -54,6 +54,20 @@ def test_hamming_scene_pair_orb(hpusm, cuda_device):
     np.testing.assert_array_equal(p_t[:n].cpu().numpy(), g["p_input"].reshape(-1, 2))
 
 
+def test_hamming_second_scene_pair_orb(hpusm, cuda_device):
+    """taj1 x taj2 through the reference's ORB detector (3626 x 5108 descriptors): knnMatch and filter_matches."""
+    g = load_golden("scene_taj1_taj2_orb_knn.npz")
+    idx, dist = hpusm.knn2_hamming(dev(g["desc_model"], cuda_device), dev(g["desc_input"], cuda_device))
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["knn_idx"])
+    np.testing.assert_array_equal(dist.cpu().numpy().astype(np.float32), g["knn_dist"])
+    keep, count = hpusm.ratio_filter(idx, dist, 0.8)
+    n = len(g["p_model"])
+    assert int(count.item()) == n
+    p_q, p_t, sel, cnt = hpusm.gather_matches(dev(g["kp_model"], cuda_device), dev(g["kp_input"], cuda_device), idx, keep)
+    np.testing.assert_array_equal(p_q[:n].cpu().numpy(), g["p_model"].reshape(-1, 2))
+    np.testing.assert_array_equal(p_t[:n].cpu().numpy(), g["p_input"].reshape(-1, 2))
+
+
 @pytest.mark.parametrize("nq,nt,nb", [(1, 1, 32), (3, 2, 32), (513, 129, 32), (1000, 5000, 32), (37, 70000, 32),
                                       (4100, 300, 64), (5, 0, 32), (0, 5, 32)])
 def test_hamming_edge_shapes(hpusm, cuda_device, nq, nt, nb):

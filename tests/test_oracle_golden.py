@@ -58,6 +58,16 @@ def test_more_scene_pairs_sift_knn_and_ratio(tag):
     np.testing.assert_array_equal(p2, g["p_input"])
 
 
+def test_second_scene_pair_orb_knn_and_ratio():
+    g = load_golden("scene_taj1_taj2_orb_knn.npz")
+    idx, dist = knn_oracle.knn2_hamming(g["desc_model"], g["desc_input"])
+    np.testing.assert_array_equal(idx, g["knn_idx"])
+    np.testing.assert_array_equal(dist.astype(np.float32), g["knn_dist"])
+    p1, p2, _ = knn_oracle.filter_matches_points(g["kp_model"], g["kp_input"], idx, dist)
+    np.testing.assert_array_equal(p1, g["p_model"])
+    np.testing.assert_array_equal(p2, g["p_input"])
+
+
 def test_ransac_matches_cv2():
     """findHomography (features.py:66) on inputs whose consensus set is unique.  cv2's sampler cannot be seeded, so
     its internal winning sample differs from ours; what does not depend on it is pinned:
