@@ -225,7 +225,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < I8_NBUF; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8); }
+    for (int b = 0; b < I8_NBUF; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 8 * 32); }
     mbar_init(a_ready, 16);
     mbar_init(a_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -400,8 +400,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         tc_ld32(taddr + 32, acc1);
         tc_wait_ld();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + buf);
+        mbar_arrive(tmem_empty + buf);   // every lane arrives: one hop fewer on the hand-over than syncwarp + elected arrive
 #ifdef I8_TRACE
         if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + (ew & 7)] = clock64() + (acc0[0] & 0);
 #endif
