@@ -158,3 +158,26 @@ def test_bench_reference_arm_contract():
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/hpusm.h is the boundary a cgo / JNI / ctypes binding sees: it must compile as C (no C++, no CUDA types),
+    and a C program that only uses it must link against libhpusm.so."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "hpusm.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s\\n", hpusm_version(), hpusm_last_error()); '
+                   'return hpusm_version() == HPUSM_ABI_VERSION ? 0 : 1; }\n')
+    lib_dir = os.path.join(root, "humanpose-and-urbanscene-matching_b200")
+    exe = tmp_path / "t"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                        "-o", str(exe), "-L", lib_dir, "-l:libhpusm.so", "-Wl,-rpath," + lib_dir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)  # no GPU needed: version + error string only
+    assert r.returncode == 0, (r.stdout, r.stderr)
