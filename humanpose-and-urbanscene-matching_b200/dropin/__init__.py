@@ -7,6 +7,7 @@ types and sentinels -- bodies call the sm_100a kernels through the C ABI (no CPU
     posematching/procrustes.py               dropin.posematching.procrustes
     posematching/pose_comparison.py          dropin.posematching.pose_comparison
     posematching/single_person.py            dropin.posematching.single_person  (match_single)
+    posematching/multi_person.py             dropin.posematching.multi_person   (match, find_ordered_matches, order_poses)
     common.py (hot subset)                   dropin.common
     thresholds.py                            dropin.thresholds
 
@@ -25,6 +26,7 @@ _OVERRIDES = {
     "posematching.pose_comparison": "posematching/pose_comparison.py",
     "posematching.procrustes": "posematching/procrustes.py",
     "posematching.single_person": "posematching/single_person.py",
+    "posematching.multi_person": "posematching/multi_person.py",
 }
 
 

@@ -8,6 +8,7 @@ Follows (file:line relative to /root/reference):
   pose_comparison.*                 posematching/pose_comparison.py:8-81
   single_person.match_single        posematching/single_person.py:80-189
   procrustes.procrustes / superimpose / superimpose_old   posematching/procrustes.py:150-259, :7-54, :68-106
+  multi_person.match (permutation stage)  posematching/multi_person.py:80-160
 
 Pinned by tests/golden/pose_*.npz, which oracle/record_golden.py recorded from the UNMODIFIED reference
 modules imported in the build container (numpy 2.3.5); tests/test_oracle_golden.py replays them.
@@ -224,6 +225,30 @@ def superimpose_old(inp, model):
     foot = 10 if inp[10][1] >= inp[13][1] else 13
     Z[:, 1] += inp[foot][1] - Z[foot][1]
     return Z, model
+
+
+def multi_person_permutations(model_poses, input_poses, matches_dict, mp_distance=0.38, normalise=True):
+    """The permutation stage of multi_person.match (multi_person.py:80-160) on the ORDERED poses and candidate lists
+    that find_ordered_matches returned: {permutation tuple: score} of the permutations that pass the MP_DISCTANCE gate."""
+    import itertools
+    out = {}
+    for perm in itertools.product(*(matches_dict[k] for k in sorted(matches_dict))):
+        if len(perm) != len(set(perm)):
+            continue
+        inputs, models = [], []
+        for mi, ii in enumerate(perm):
+            ip, mo = handle_undetected_points(input_poses[ii], model_poses[mi])
+            Z, _ = superimpose_old(ip, mo)
+            inputs.append(Z)
+            models.append(mo)
+        inputs, models = np.vstack(inputs), np.vstack(models)
+        if normalise:
+            inputs, models = feature_scaling(inputs), feature_scaling(models)
+        full, _ = find_transformation(models, inputs)
+        score = max_euclidean_distance(models, full)
+        if score <= mp_distance:
+            out[tuple(int(x) for x in perm)] = float(score)
+    return out
 
 
 def perspective_transform32(pts, H):

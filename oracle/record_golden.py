@@ -370,11 +370,73 @@ def record_multi_person():
     save("pose_multi_person.npz", A=A, B=B, na=na, nb=nb, found=found, table=table, n_model=n_model)
 
 
+def record_multi_person_match():
+    """multi_person.match (multi_person.py:15-166): the permutation stage behind find_ordered_matches -- Procrustes
+    superimposition of every (model person, input person) of every injective permutation, min/max scaling of the stacked
+    poses, one affine fit of the whole group, the MP_DISCTANCE gate -- on the multi-person fixtures."""
+    import posematching.multi_person as ref_mp
+    groups = []
+    for f in sorted(glob.glob(os.path.join(REF, "json_data", "*.json"))):
+        try:
+            people = [p for p in ref_common.parse_JSON_multi_person(f) if p.shape == (18, 2)]
+        except Exception:
+            continue
+        if 2 <= len(people) <= 5 and all(((p != 0).any(1)).sum() >= 8 for p in people):
+            groups.append(np.stack(people))
+    rng = np.random.default_rng(41)
+    cases = []
+    for k in range(60):
+        a = groups[rng.integers(len(groups))]
+        if k % 4 == 3:
+            b = groups[rng.integers(len(groups))]          # unrelated group: mostly no candidates
+        else:
+            s, th = rng.uniform(0.8, 1.25), rng.uniform(-0.12, 0.12)
+            R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+            b = ((a @ R.T) * s + rng.uniform(-30, 30, 2) + rng.normal(0, 2.5, a.shape)) * (a != 0).any(2, keepdims=True)
+            if k % 4 == 1 and len(b) > 2:
+                b = b[rng.permutation(len(b))]             # people in a different order
+            if k % 4 == 2:
+                b = np.concatenate([b, groups[rng.integers(len(groups))][:1]])  # one extra (background) person
+        try:
+            md, mo, ip = ref_mp.find_ordered_matches(list(a), list(b))
+            res = ref_mp.match(list(a), list(b))
+        except Exception:
+            continue
+        cases.append((a, b, md, mo, ip, res))
+    P, NP = 6, 16
+    n = len(cases)
+    A = np.zeros((n, P, 18, 2)); B = np.zeros((n, P, 18, 2))
+    na = np.zeros(n, np.int32); nb = np.zeros(n, np.int32)
+    found = np.zeros(n, np.int8); n_model = np.zeros(n, np.int32); n_input = np.zeros(n, np.int32)
+    table = -np.ones((n, P, P), np.int32)
+    MO = np.zeros((n, P, 18, 2)); IP = np.zeros((n, P, 18, 2))
+    ok = np.zeros(n, np.int8); nperm = np.zeros(n, np.int32)
+    perms = -np.ones((n, NP, P), np.int32); scores = np.full((n, NP), np.nan)
+    for c, (a, b, md, mo, ip, res) in enumerate(cases):
+        A[c, :len(a)], B[c, :len(b)], na[c], nb[c] = a, b, len(a), len(b)
+        if md is not None:
+            found[c], n_model[c], n_input[c] = 1, len(mo), len(ip)
+            MO[c, :len(mo)], IP[c, :len(ip)] = np.stack(mo), np.stack(ip)
+            for m, lst in md.items():
+                table[c, m, :len(lst)] = lst
+        ok[c] = 1 if res.match_bool else 0
+        if res.matching_permutations:
+            items = sorted(res.matching_permutations.items())
+            assert len(items) <= NP
+            nperm[c] = len(items)
+            for k, (perm, val) in enumerate(items):
+                perms[c, k, :len(perm)] = perm
+                scores[c, k] = val["score"]
+    print("multi_person.match: %d cases, %d matched, %d permutations kept" % (n, int(ok.sum()), int(nperm.sum())))
+    save("pose_multi_person_match.npz", A=A, B=B, na=na, nb=nb, found=found, n_model=n_model, n_input=n_input, table=table,
+         MO=MO, IP=IP, ok=ok, nperm=nperm, perms=perms, scores=scores, mp_distance=np.array(0.38))
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
                record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra,
-               record_scene_pair_orb_extra):
+               record_scene_pair_orb_extra, record_multi_person_match):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

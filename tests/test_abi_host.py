@@ -115,6 +115,8 @@ hpusm.dropin.install(reference_root="/root/reference")
 import matching, urbanscene.urban_scene as us, posematching.multi_person as mp, common, urbanscene.features as ft
 assert ft.match_and_draw.__module__.endswith("dropin.urbanscene.features")
 assert us.features is ft and mp.find_transformation.__module__.endswith("dropin.common")
+assert mp.match.__module__.endswith("dropin.posematching.multi_person")               # batched permutation stage
+assert mp.plot_match.__module__.startswith("_hpusm_reference")                        # fall-through to the plot helper
 assert common.parse_JSON_multi_person.__module__.startswith("_hpusm_reference")      # fall-through
 poses = common.parse_JSON_multi_person("/root/reference/json_data/duo1.json")
 assert poses[0].shape == (18, 2)

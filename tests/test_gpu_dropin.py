@@ -158,6 +158,32 @@ def test_multi_person_candidate_stage(cuda_device):
     assert n_found >= 10
 
 
+def test_multi_person_match_permutation_stage(cuda_device):
+    """multi_person.match (multi_person.py:15-166) end to end -- candidate stage, every injective permutation superimposed,
+    scaled and fitted in three batched launches -- against results recorded from the reference: same verdict, same
+    surviving permutations, same scores, same (model, input) arrays."""
+    mp = importlib.import_module(DROPIN + ".posematching.multi_person")
+    g = load_golden("pose_multi_person_match.npz")
+    n_perm = 0
+    for c in range(len(g["ok"])):
+        a = [p for p in g["A"][c][:g["na"][c]]]
+        b = [p for p in g["B"][c][:g["nb"][c]]]
+        res = mp.match(a, b)
+        assert bool(res.match_bool) == bool(g["ok"][c]), c
+        want = {tuple(int(x) for x in g["perms"][c, k] if x >= 0): float(g["scores"][c, k]) for k in range(int(g["nperm"][c]))}
+        got = res.matching_permutations or {}
+        assert set(got) == set(want), (c, sorted(got), sorted(want))
+        for perm, score in want.items():
+            assert abs(got[perm]["score"] - score) <= 1e-9 * max(1.0, abs(score)), (c, perm)
+            assert got[perm]["model"].shape == got[perm]["input"].shape == (18 * len(perm), 2)
+            n_perm += 1
+    assert n_perm >= 30
+    # the 1 x 1 shortcut goes through match_single
+    one = mp.match([g["A"][0][0]], [g["A"][0][0]])
+    assert one.match_bool and list(one.matching_permutations) == [0]
+    assert not mp.match([], [g["A"][0][0]]).match_bool and not mp.match(list(g["A"][0][:2]), [g["A"][0][0]]).match_bool
+
+
 def test_pose_match_pairs_equals_batch(hpusm, cuda_device):
     import torch
     g = load_golden("pose_match_single.npz")

@@ -198,3 +198,25 @@ def test_scene_score_matches_reference():
         s = pose_oracle.scene_score(g["src"][lo:hi], g["dst"][lo:hi], g["H2"][p], g["model_pose"][p], g["input_pose"][p],
                                     g["model_wh"][0], g["model_wh"][1], g["picks"][p])
         np.testing.assert_allclose(s, g["score"][p], rtol=1e-8)
+
+
+def test_multi_person_permutation_stage_matches_reference():
+    """multi_person.match (multi_person.py:80-160) on the ordered poses and candidate lists the reference produced:
+    the same permutations pass the MP_DISCTANCE gate, with the same scores."""
+    g = load_golden("pose_multi_person_match.npz")
+    checked = 0
+    for c in range(len(g["ok"])):
+        if not g["found"][c]:
+            assert not g["ok"][c]
+            continue
+        nm, ni = int(g["n_model"][c]), int(g["n_input"][c])
+        md = {m: [int(x) for x in g["table"][c, m] if x >= 0] for m in range(nm)}
+        with np.errstate(all="ignore"):
+            got = pose_oracle.multi_person_permutations(list(g["MO"][c, :nm]), list(g["IP"][c, :ni]), md, float(g["mp_distance"]))
+        want = {tuple(int(x) for x in g["perms"][c, k] if x >= 0): float(g["scores"][c, k]) for k in range(int(g["nperm"][c]))}
+        assert set(got) == set(want), (c, got, want)
+        for perm in want:
+            assert abs(got[perm] - want[perm]) <= 1e-9 * max(1.0, abs(want[perm]))
+        assert bool(g["ok"][c]) == bool(want)
+        checked += len(want)
+    assert checked >= 30
