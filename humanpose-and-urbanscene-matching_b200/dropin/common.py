@@ -49,6 +49,12 @@ def handle_undetected_points(input_features, model_features):
     return (input_copy, model_copy)
 
 
+def split_in_face_legs_torso(features):
+    """common.py:261-267: torso = neck .. left wrist (joints 1-7), legs = joints 8-13, face = nose + eyes/ears."""
+    features = np.asarray(features)
+    return (np.vstack([features[0], features[14:18]]), features[1:8], features[8:14])
+
+
 def split_in_face_legs_torso_v2(features):
     torso = features[[0, 1, 2, 3, 4, 5, 6, 7, 8, 11]]
     legs = features[[1, 8, 9, 10, 11, 12, 13]]

@@ -277,3 +277,31 @@ def scene_score(p_model_good, p_input_good, H2, model_pose, input_pose, model_w,
     a = np.stack([model_pts[:, 0] / model_w, model_pts[:, 1] / model_h], 1)
     b = np.stack([trans[:, 0] / model_w, trans[:, 1] / model_h], 1)
     return _py_max(euclidean_distances(a, b))
+
+
+def split_v1(pose):
+    """common.split_in_face_legs_torso (common.py:261-267): (face, torso = joints 1..7, legs = joints 8..13)."""
+    pose = np.asarray(pose)
+    return np.vstack([pose[0], pose[14:18]]), pose[1:8], pose[8:14]
+
+
+def scene_score_single(p_model_good, p_input_good, H2, model_pose, input_pose):
+    """urban_scene.match_scene_single_person steps 4-5 (urban_scene.py:196-240) = transformation.perspective_correction
+    + transformation.affine_trans_interaction_pose_rand_scene (transformation.py:736-790):
+    (max torso, max legs, sum torso, sum legs) of the min/max-normalised residuals."""
+    p_model_good = np.asarray(p_model_good, np.float64)
+    bg_in = perspective_transform32(p_input_good, H2).astype(np.float64)
+    pose_in = perspective_transform32(input_pose, H2).astype(np.float64)
+    _, m_torso, m_legs = split_v1(np.asarray(model_pose, np.float64))
+    _, i_torso, i_legs = split_v1(pose_in)
+    extra_m = np.vstack([p_model_good[0], p_model_good[1], p_model_good[10]])
+    extra_i = np.vstack([bg_in[0], bg_in[1], bg_in[10]])
+    out = []
+    for m_part, i_part in ((m_torso, i_torso), (m_legs, i_legs)):
+        m_part, i_part = np.vstack([m_part, extra_m]), np.vstack([i_part, extra_i])
+        _, M = find_transformation(m_part, i_part)
+        stacked = np.vstack([bg_in, i_part])
+        trans = (np.hstack([stacked, np.ones((len(stacked), 1))]) @ M)[:, :2]
+        err = euclidean_distances(feature_scaling(np.vstack([p_model_good, m_part])), feature_scaling(trans))
+        out.append((_py_max(err), sum(err)))
+    return out[0][0], out[1][0], out[0][1], out[1][1]

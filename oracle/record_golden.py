@@ -370,6 +370,37 @@ def record_multi_person():
     save("pose_multi_person.npz", A=A, B=B, na=na, nb=nb, found=found, table=table, n_model=n_model)
 
 
+def record_scene_score_single():
+    """urban_scene.match_scene_single_person steps 4-5 (urban_scene.py:196-240): transformation.perspective_correction +
+    transformation.affine_trans_interaction_pose_rand_scene (transformation.py:736-790: torso and legs each fitted
+    together with background matches 0, 1 and 10; min/max-normalised residuals)."""
+    import urbanscene.transformation as ref_tr
+    poses, _ = load_fixture_poses()
+    full = poses[((poses != 0).any(2)).sum(1) == 18]
+    rng = np.random.default_rng(70)
+    out = {k: [] for k in ("src", "dst", "H2", "model_pose", "input_pose", "result", "n")}
+    img = np.zeros((480, 640), np.uint8)
+    for case in range(20):
+        src, dst, Ht = synth.ransac_pair(40 + 7 * case, inlier_ratio=1.0, seed=80 + case, noise=0.7)
+        H2, _ = cv2.findHomography(dst.reshape(-1, 1, 2), src.reshape(-1, 1, 2), cv2.RANSAC, 5.0)
+        model_pose = full[rng.integers(len(full))] * 0.5 + 20.0
+        if case % 5 == 4:
+            model_pose = model_pose.copy(); model_pose[[4, 12]] = 0      # undetected joints
+        pp = np.c_[model_pose, np.ones(18)] @ Ht.T
+        input_pose = pp[:, :2] / pp[:, 2:] + rng.normal(0, 1.0 + case % 3, (18, 2))
+        input_pose[(model_pose == 0).all(1)] = 0
+        (p_trans, pose_trans, _img) = ref_tr.perspective_correction(H2, np.vstack((src, model_pose)), np.vstack((dst, input_pose)),
+                                                                    model_pose, input_pose, img, img, False)
+        only_buildings = p_trans[0:len(p_trans) - 18]
+        res = ref_tr.affine_trans_interaction_pose_rand_scene(src, only_buildings, model_pose, pose_trans, img, img, "g", False)
+        for k, v in (("src", src), ("dst", dst), ("H2", H2), ("model_pose", model_pose), ("input_pose", input_pose),
+                     ("result", np.array(res, np.float64)), ("n", len(src))):
+            out[k].append(v)
+    save("scene_score_single.npz", src=np.concatenate(out["src"]), dst=np.concatenate(out["dst"]), H2=np.stack(out["H2"]),
+         model_pose=np.stack(out["model_pose"]), input_pose=np.stack(out["input_pose"]), result=np.stack(out["result"]),
+         pair_offsets=np.concatenate([[0], np.cumsum(out["n"])]).astype(np.int64))
+
+
 def record_multi_person_match():
     """multi_person.match (multi_person.py:15-166): the permutation stage behind find_ordered_matches -- Procrustes
     superimposition of every (model person, input person) of every injective permutation, min/max scaling of the stacked
@@ -436,7 +467,7 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
                record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra,
-               record_scene_pair_orb_extra, record_multi_person_match):
+               record_scene_pair_orb_extra, record_multi_person_match, record_scene_score_single):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

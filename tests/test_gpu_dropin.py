@@ -158,6 +158,21 @@ def test_multi_person_candidate_stage(cuda_device):
     assert n_found >= 10
 
 
+def test_scene_score_single_person(cuda_device):
+    """urban_scene.match_scene_single_person steps 4-5 through the drop-in transformation module: perspective_correction +
+    affine_trans_interaction_pose_rand_scene against the reference's own results on 20 scenes."""
+    tr = importlib.import_module(DROPIN + ".urbanscene.transformation")
+    g = load_golden("scene_score_single.npz")
+    offs = g["pair_offsets"]
+    for c in range(len(g["result"])):
+        a, b = int(offs[c]), int(offs[c + 1])
+        src, dst, mp_, ip_ = g["src"][a:b], g["dst"][a:b], g["model_pose"][c], g["input_pose"][c]
+        (p_trans, pose_trans, _img) = tr.perspective_correction(g["H2"][c], np.vstack((src, mp_)), np.vstack((dst, ip_)), mp_, ip_,
+                                                                None, None, False)
+        got = tr.affine_trans_interaction_pose_rand_scene(src, p_trans[0:len(p_trans) - 18], mp_, pose_trans, None, None, "g")
+        np.testing.assert_allclose(got, g["result"][c], rtol=1e-7, atol=1e-10)
+
+
 def test_multi_person_match_permutation_stage(cuda_device):
     """multi_person.match (multi_person.py:15-166) end to end -- candidate stage, every injective permutation superimposed,
     scaled and fitted in three batched launches -- against results recorded from the reference: same verdict, same

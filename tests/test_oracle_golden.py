@@ -220,3 +220,14 @@ def test_multi_person_permutation_stage_matches_reference():
         assert bool(g["ok"][c]) == bool(want)
         checked += len(want)
     assert checked >= 30
+
+
+def test_scene_score_single_matches_reference():
+    """match_scene_single_person's score (perspective_correction + affine_trans_interaction_pose_rand_scene) recorded from
+    the reference on 20 synthetic scenes."""
+    g = load_golden("scene_score_single.npz")
+    offs = g["pair_offsets"]
+    for c in range(len(g["result"])):
+        a, b = int(offs[c]), int(offs[c + 1])
+        got = pose_oracle.scene_score_single(g["src"][a:b], g["dst"][a:b], g["H2"][c], g["model_pose"][c], g["input_pose"][c])
+        np.testing.assert_allclose(got, g["result"][c], rtol=1e-7, atol=1e-10)
