@@ -314,9 +314,11 @@ def run_ours(args, rank, world, device):
     peak_source = "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"
     if mode == "tcgen05-i8-exact-int":
         # kind::i8 retires K=32 per MMA instruction slot where kind::f16 retires K=16: the integer pipe's peak is twice
-        # the bf16 one.  MEASURED_PEAKS.json has no INT8 line, so the denominator is 2 x its measured bf16 figure.
+        # the bf16 one (measured issue rates, profiles/r1_microbench.txt: 4438 vs 2164 T op/s).  MEASURED_PEAKS.json has
+        # no INT8 line, so the denominator is 2 x its measured bf16 figure.
         peak_tf = 2.0 * bf16_tf
-        peak_source = "2 x (" + peak_source + "): tcgen05 kind::i8 issues twice the MACs per instruction slot of kind::f16"
+        peak_source = ("2 x (" + peak_source + "): tcgen05 kind::i8 issues twice the MACs per instruction slot of kind::f16 "
+                       "(measured 4438 vs 2164 T op/s back-to-back issue, profiles/r1_microbench.txt)")
     # (the split engine executes 25/8 of the algorithmic 256 FLOP per pair on the tensor pipe; the roofline counts 256)
     out = {
         "metric": "descriptor-pairs/sec (kNN+ratio)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

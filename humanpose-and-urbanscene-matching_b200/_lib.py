@@ -83,6 +83,7 @@ SIGNATURES = {
     "hpusm_microbench_popc": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_lop3": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_minmax": (_i32, [_i32, _i64, _i32, _i64, _p, _p]),
+    "hpusm_microbench_mma": (_i32, [_i32, _i32, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -409,6 +409,15 @@ def pose_topk_merge(cand_score, cand_index, k=16):
     return ts, ti
 
 
+def microbench_mma(kind, rounds, device):
+    """Back-to-back tcgen05.mma on every SM (kind "bf16" | "i8"); returns the operations issued (2 x MACs) for timing."""
+    k = {"bf16": 0, "i8": 1}[kind]
+    with torch.cuda.device(device):
+        check(lib.hpusm_microbench_mma(k, int(rounds), _stream(device)))
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    return 2.0 * 128 * 256 * (16 if k == 0 else 32) * 64 * int(rounds) * sms
+
+
 def microbench_popc(blocks, threads, iters, device, op="popc"):
     """op: "popc" | "lop3" | "imax3" | "fmax3" | "imax" | "fmax" -- every thread issues `iters` of that instruction."""
     sink = torch.zeros((1,), dtype=torch.int32, device=device)

@@ -282,6 +282,9 @@ int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* 
 /* Issue rate of the max-scan instructions the fused top-2 epilogues of K1 are made of.
  * op 0: 3-input s32 max, 1: 3-input f32 max, 2: 2-input s32 max, 3: 2-input f32 max. */
 int hpusm_microbench_minmax(int op, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
+/* Tensor-pipe issue rate: every SM issues rounds x 64 back-to-back tcgen05.mma of 128 x 256 x (16 bf16 | 32 u8) and nothing
+ * else.  kind 0 = bf16 operands (kind::f16), 1 = u8 operands (kind::i8).  The measured denominator of the K1 roofline. */
+int hpusm_microbench_mma(int kind, int rounds, void* stream);
 
 #ifdef __cplusplus
 }

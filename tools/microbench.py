@@ -17,3 +17,11 @@ for op in ["lop3", "popc", "imax3", "fmax3", "imax", "fmax"]:
         ms = e0.elapsed_time(e1)
         ops = blocks * thr * iters
         print(op, thr, "%.1f Gop/s" % (ops / ms / 1e6), "-> %.1f lanes/clk/SM at 1.9 GHz" % (ops / ms / 1e6 / 148 / 1.9))
+for kind in ("bf16", "i8"):
+    for rounds in (2000, 20000):
+        hpusm.engine.microbench_mma(kind, 200, dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops = hpusm.engine.microbench_mma(kind, rounds, dev); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("mma %s rounds %d: %.1f ms -> %.0f T op/s" % (kind, rounds, ms, ops / ms / 1e9))
