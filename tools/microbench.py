@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Issue rates of the instructions the hot kernels are made of (hpusm_microbench_*): LOP3 / POPC for the Hamming
-kernel's two-pipe roofline, 2- and 3-input integer / float max for the max-scan epilogues of the L2 engines.
+kernel's two-pipe roofline, 2- and 3-input integer / float max for the max-scan epilogues of the L2 engines, and the
+tensor pipe itself (back-to-back tcgen05.mma with bf16 and with u8 operands).
 Output of round 1 on a B200: profiles/r1_microbench.txt."""
 import torch, importlib, sys
 sys.path.insert(0, ".")
