@@ -177,6 +177,55 @@ def record_ransac_cv2():
     save("perspective_transform.npz", pts=pts, H=Hs[0], out=cv2.perspectiveTransform(pts, Hs[0]))
 
 
+RANSAC_REAL_PAIRS = [("sift", "pisa9.jpg", "pisa10.jpg"), ("sift", "notredam1.jpg", "notredam2.jpg"),
+                     ("sift", "india1.jpg", "india2.jpg"), ("sift", "jochen_foto4.jpg", "jochen_foto5.jpg"),
+                     ("sift", "foto3.jpg", "foto4.jpg"), ("sift", "emma1.jpg", "emma2.jpg"),
+                     ("orb", "taj1.jpg", "taj3.jpg"), ("orb", "eifel2.jpg", "eifel4.jpg"),
+                     ("orb", "notredam1.jpg", "notredam3.jpg"), ("orb", "pisa9.jpg", "pisa10.jpg"),
+                     # pairs whose homography the reference itself rejects (validate_homography False): ill-posed fits
+                     ("sift", "pisa1.jpg", "pisa2.jpg"), ("orb", "pisa1.jpg", "pisa2.jpg"), ("sift", "pisa8.jpg", "pisa9.jpg")]
+
+
+def record_ransac_real_pairs():
+    """features.match_and_draw (features.py:57-105) on real image pairs of the reference's img/ directory: the matched
+    point lists (filter_matches, features.py:45) and what the two cv2.findHomography calls (features.py:66,:69) return.
+    Ten pairs have a homography the reference accepts (validate_homography, features.py:177), three do not."""
+    arrays, names = {}, []
+    for k, (det_name, img_model, img_input) in enumerate(RANSAC_REAL_PAIRS):
+        model = cv2.imread(os.path.join(REF, "img", img_model), 0)
+        inp = cv2.imread(os.path.join(REF, "img", img_input), 0)
+        if det_name == "sift":
+            detector, matcher = cv2.SIFT_create(), cv2.BFMatcher(cv2.NORM_L2)
+        else:
+            detector, matcher = ref_features.init_feature("orb")
+        kp_m, desc_m = detector.detectAndCompute(model, None)
+        kp_i, desc_i = detector.detectAndCompute(inp, None)
+        raw = matcher.knnMatch(desc_m, trainDescriptors=desc_i, k=2)
+        p1, p2, _ = ref_features.filter_matches(kp_m, kp_i, raw)
+        mask, good_m, good_i, H, H2, n_good = ref_features.match_and_draw("w", matcher, desc_m, desc_i, kp_m, kp_i, model,
+                                                                           inp.copy(), False)
+        H2b, mask2 = cv2.findHomography(p2, p1, cv2.RANSAC, 5.0)  # features.py:69 (the reference drops this mask)
+        assert np.array_equal(H2, H2b)
+        names.append("%s:%s:%s" % (det_name, img_model, img_input))
+        arrays.update({"p_model_%d" % k: p1, "p_input_%d" % k: p2, "mask_%d" % k: mask, "mask2_%d" % k: mask2,
+                       "H_%d" % k: H, "H2_%d" % k: H2, "n_good_%d" % k: np.array(n_good),
+                       "valid_%d" % k: np.array([ref_features.validate_homography(H), ref_features.validate_homography(H2)])})
+    save("ransac_real_pairs.npz", names=np.array(names), **arrays)
+
+
+def record_ransac_synth_cv2():
+    """cv2.findHomography(src, dst, cv2.RANSAC, 5.0) (features.py:66) on 1000 seeded noisy synthetic pairs: H, mask."""
+    Hs, masks, offs = [], [], [0]
+    from oracle.ransac_cases import N_SYNTH, ransac_synth_case
+    for k in range(N_SYNTH):
+        src, dst, _ = ransac_synth_case(k)
+        H, mask = cv2.findHomography(src.reshape(-1, 1, 2), dst.reshape(-1, 1, 2), cv2.RANSAC, 5.0)
+        assert H is not None
+        Hs.append(H); masks.append(mask.ravel()); offs.append(offs[-1] + len(src))
+    save("ransac_synth_cv2.npz", H=np.stack(Hs), mask_bits=np.packbits(np.concatenate(masks)),
+         pair_offsets=np.array(offs, np.int64))
+
+
 def load_fixture_poses():
     poses, names = [], []
     for f in sorted(glob.glob(os.path.join(REF, "json_data", "*.json"))):
@@ -467,7 +516,8 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
                record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra,
-               record_scene_pair_orb_extra, record_multi_person_match, record_scene_score_single):
+               record_scene_pair_orb_extra, record_multi_person_match, record_scene_score_single, record_ransac_real_pairs,
+               record_ransac_synth_cv2):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()
