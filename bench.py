@@ -7,9 +7,13 @@ query x 1M database kNN k=2 ratio test on 1 B200").
     python bench.py --impl reference ...                      # the reference's CPU path (cv2.BFMatcher + ratio loop)
 
 One step = one full kNN-2 + ratio pass of the query set over this rank's database shard.  With N > 1 the database
-is sharded by rows across ranks (weak scaling: every rank owns `--nt` rows), queries are replicated, each rank
-produces a local top-2, and one NCCL all-gather of the 16 B/query partial results followed by the lexicographic
-merge + ratio kernel gives every rank the global answer.  Prints ONE JSON line on rank 0.
+is sharded by rows across ranks, queries are replicated, each rank produces a local top-2, and one NCCL all-gather of
+the 16 B/query partial results followed by the lexicographic merge + ratio kernel gives every rank the global answer.
+The headline `value` is WEAK scaling (every rank owns `--nt` rows, config.nt_global = N x nt); the same line carries
+`strong_scaling` (the fixed nq x nt problem with the database rows divided over the ranks), `nccl_parity` (rank 0
+checks the merged answer of a query slice against one single-GPU pass over the gathered database) and `others`: the
+remaining BASELINE.json configs (ORB retrieval, batched RANSAC, pose database), each with its own value / e2e /
+roofline / clocks and, at N = 1, cpu_baseline.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import importlib
@@ -49,6 +53,11 @@ def parse_args():
     ap.add_argument("--images", type=int, default=10000, help="orb: database images (2048 descriptors each)")
     ap.add_argument("--pairs", type=int, default=100000, help="ransac: image pairs (2000 matches x 1024 hypotheses each)")
     ap.add_argument("--poses", type=int, default=10_000_000, help="pose: database poses")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="sift at N > 1: what `value` reports (the other form is still measured and reported beside it)")
+    ap.add_argument("--no-others", action="store_true", help="sift: skip the orb / ransac / pose workloads of the default line")
+    ap.add_argument("--min-region-ms", type=float, default=2500.0,
+                    help="orb / ransac / pose: steps are raised until the timed region lasts at least this long")
     return ap.parse_args()
 
 
@@ -176,13 +185,31 @@ def pick_cpu_sample(nt, want):
     return int(max(64, min(4096, 2.5e9 // max(nt, 1))))  # about 10-20 s of host work at 1-3e8 pairs/s
 
 
+def load_synth():
+    """The synthetic-data generators (numpy only) loaded by path: the reference arm must not import the package, which
+    would load libhpusm.so into a process that is supposed to run none of our code."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_hpusm_synth", os.path.join(ROOT, PKG, "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def sift_config(args, world):
+    """`config` of the sift line: the same keys on both arms."""
+    return {"workload": "synthetic SIFT 128-d float, 1M query x 1M database kNN k=2 ratio test on 1 B200",
+            "nq": args.nq, "nt_per_gpu": args.nt, "nt_global": args.nt * world, "d": 128, "ratio": 0.8,
+            "descriptors": args.descriptors}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return None
     cores = cpu_threads()
-    hp = importlib.import_module(PKG)
     ns = pick_cpu_sample(args.nt, args.cpu_sample)
-    q, t = hp.synth.sift_like(ns, args.nt, seed=7, planted=0.1)
+    q, t = load_synth().sift_like(ns, args.nt, seed=7, planted=0.1)
+    if args.descriptors == "float":
+        q, t = q * np.float32(1.0137), t * np.float32(1.0137)
     for _ in range(min(args.warmup, 1)):
         reference_step(q[:max(16, ns // 8)], t)
     times = []
@@ -196,8 +223,7 @@ def run_reference(args, rank):
         "metric": "descriptor-pairs/sec (kNN+ratio)", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "synthetic SIFT 128-d float, 1M query x 1M database kNN k=2 ratio test on 1 B200",
-                   "nq": args.nq, "nt_per_gpu": args.nt, "d": 128, "ratio": 0.8},
+        "config": sift_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference",
                          "sample": "%d queries x %d db rows per step, cv2.BFMatcher(NORM_L2).knnMatch k=2 + ratio loop "
                                    "(features.py:59,:45-55)" % (ns, args.nt)},
@@ -215,17 +241,18 @@ DTYPE_OF = {
 
 
 # ---- our path ---------------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, device):
+def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
+    """Times the sharded kNN-2 + ratio pass with `nt_rank` database rows on this rank (global row offset `row0`):
+    resident (inputs in HBM) and end to end (host buffers, copies inside the timed region)."""
     import torch.distributed as dist
-    hp = importlib.import_module(PKG)
-    eng = hp.engine
-    nq, nt = args.nq, args.nt
-    q, t = make_workload(nq, nt, rank, device)
+    eng, rt = hp.engine, hp.retrieval
+    nq = args.nq
+    q, t = make_workload(nq, nt_rank, rank, device)
     if args.descriptors == "float":  # same rows, no longer integer valued: exercises the split-operand engine
         q, t = (q * 1.0137).contiguous(), (t * 1.0137).contiguous()
     l2_mode = {"auto": eng.L2_AUTO, "i8": eng.L2_TC_I8, "bf16": eng.L2_TC_INT, "split": eng.L2_TC_SPLIT,
                "simt": eng.L2_SIMT}[args.l2_engine]
-    ws = eng.knn2_l2_workspace(nq, nt, 128, l2_mode, device)
+    ws = eng.knn2_l2_workspace(nq, nt_rank, 128, l2_mode, device)
     idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
     dst = torch.empty((nq, 2), dtype=torch.float32, device=device)
 
@@ -233,112 +260,128 @@ def run_ours(args, rank, world, device):
         return eng.knn2_l2(qq, tt, mode=l2_mode, out=(idx, dst), workspace=ws)
 
     def step():
-        mi, md, keep, count = hp.retrieval.knn2_sharded(q, t, rank * nt, kind="l2", ratio=0.8, knn_fn=local_knn)
-        return keep, count
+        return rt.knn2_sharded(q, t, row0, kind="l2", ratio=0.8, knn_fn=local_knn)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
-    sampler = ClockSampler(device.index or 0)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    if rank == 0:
-        sampler.mark()
-    eng.profile_enable(True)
-    eng.profile_collect()
-    launches0 = hp.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        keep, count = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    kernel_ms, kernel_n = eng.profile_collect()
-    eng.profile_enable(False)
-    launches = hp.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    tm = Timer(args, rank, world, device, hp)
+    r = tm.run(step)
+    mi, md, keep, count = r["out"]
     survivors = int(count.item())
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    mode = {0: "auto", 1: "simt-fp32", 2: "tcgen05-bf16-exact-int", 3: "tcgen05-bf16-split",
+            4: "tcgen05-i8-exact-int"}.get(eng.knn2_l2_last_mode(), "?")
 
-    # end to end through the public API with HOST buffers: H2D of the descriptors and D2H of the answer every step
-    hq, ht = q.cpu().pin_memory(), t.cpu().pin_memory()
+    # on-hardware parity of the NCCL path: the merged answer of a query slice == ONE single-GPU pass over the gathered database
+    parity = None
+    if world > 1 and label == "weak":
+        ns = min(4096, nq)
+        t_all = rt.allgather(t).reshape(-1, 128)  # every rank takes part in the gather; rank 0 checks
+        if rank == 0:
+            ri, rd = eng.knn2_l2(q[:ns].contiguous(), t_all, mode=l2_mode)
+            ok = bool(torch.equal(ri, mi[:ns]) and torch.equal(rd, md[:ns]))
+            parity = {"queries": ns, "db_rows": int(t_all.shape[0]), "identical": ok}
+            assert ok, "NCCL all-gather + merge disagrees with the single-GPU pass over the gathered database"
+        del t_all
+        tm.barrier()
+
+    # end to end through the public API with HOST buffers.  The database shard and this rank's SLICE of the queries are
+    # copied host->device (pinned) every step; the query slices are exchanged over NVLink (one all-gather), so each query
+    # row crosses PCIe once per node instead of once per rank; the answer is read back every step.
+    qa, qb = rt.shard_range(nq, rank, world)
+    hq, ht = q[qa:qb].cpu().pin_memory(), t.cpu().pin_memory()
     h_idx = torch.empty((nq, 2), dtype=torch.int32).pin_memory()
     h_dst = torch.empty((nq, 2), dtype=torch.float32).pin_memory()
     h_keep = torch.empty((nq,), dtype=torch.uint8).pin_memory()
-    # the public host-array entry point: row chunks copied on a copy stream while earlier chunks are being matched
-    streamed = hp.retrieval.StreamedL2Matcher(nq, nt, 128, device, mode=l2_mode)
+    streamed = rt.StreamedL2Matcher(nq, nt_rank, 128, device, mode=l2_mode, query_slices=world > 1)
 
     def e2e_step():
-        mi, md, kp, _ = hp.retrieval.knn2_sharded(hq, ht, rank * nt, kind="l2", ratio=0.8, knn_fn=streamed)
-        h_idx.copy_(mi, non_blocking=True)
-        h_dst.copy_(md, non_blocking=True)
+        gi, gd, kp, _ = rt.knn2_sharded(hq, ht, row0, kind="l2", ratio=0.8, knn_fn=streamed)
+        h_idx.copy_(gi, non_blocking=True)
+        h_dst.copy_(gd, non_blocking=True)
         h_keep.copy_(kp, non_blocking=True)
 
-    e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    if world > 1:
-        tms = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tms.item())
+    e = tm.run(e2e_step, profile=False)
     assert int(h_keep.sum()) == survivors, "e2e pass disagrees with the resident pass"
+    del streamed
+    return {"ms": r["ms"], "e2e_ms": e["ms"], "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "launches": r["launches"],
+            "clocks": r["clocks"], "survivors": survivors, "mode": mode, "parity": parity, "nt_rank": nt_rank,
+            "h2d": int(hq.numel() * 4 + ht.numel() * 4), "d2h": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel()),
+            "fallback_rows": eng.knn2_l2_last_fallback_rows()}
 
+
+def i8_sustained_peak(hp, device, seconds=2.0):
+    """Sustained issue rate of tcgen05.mma kind::i8 on this GPU (T op/s): the K1 kernel's roofline denominator, measured in
+    this run -- back-to-back MMAs on every SM for `seconds`, clocks sampled beside it (MEASURED_PEAKS.json has no INT8 line)."""
+    eng = hp.engine
+    rounds = 4096  # ~10 ms per launch
+    eng.microbench_mma("i8", 64, device)
+    torch.cuda.synchronize(device)
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n, ops, t0 = 0, 0.0, time.perf_counter()
+    e0.record()
+    while time.perf_counter() - t0 < seconds:
+        ops = eng.microbench_mma("i8", rounds, device)
+        n += 1
+        if n % 8 == 0:
+            torch.cuda.synchronize(device)
+    e1.record()
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop()
+    return ops * n / (e0.elapsed_time(e1) * 1e-3) / 1e12, clocks
+
+
+def run_sift(args, rank, world, device, hp):
+    weak = sift_pass(args, rank, world, device, hp, args.nt, rank * args.nt, "weak")
+    strong = weak
+    if world > 1:
+        a, b = hp.retrieval.shard_range(args.nt, rank, world, align=128)
+        strong = sift_pass(args, rank, world, device, hp, b - a, a, "strong")
     if rank != 0:
         return None
-    pairs_per_step = float(nq) * float(nt) * world
-    value = pairs_per_step * args.steps / (ms * 1e-3)
+    nq, nt = args.nq, args.nt
+    head, other = (weak, strong) if args.scaling == "weak" else (strong, weak)
+    pairs_weak, pairs_strong = float(nq) * nt * world, float(nq) * nt
+    pairs_head = pairs_weak if args.scaling == "weak" else pairs_strong
+    value = pairs_head * args.steps / (head["ms"] * 1e-3)
     pk = peaks()
     bf16_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
-    peak_tf = bf16_tf
-    k_ms = kernel_ms / max(kernel_n, 1)
-    flops_per_launch = FLOP_PER_PAIR * float(nq) * float(nt) * args.steps / max(kernel_n, 1)
+    k_ms = head["kernel_ms"] / max(head["kernel_n"], 1)
+    flops_per_launch = FLOP_PER_PAIR * float(nq) * head["nt_rank"] * args.steps / max(head["kernel_n"], 1)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    mode = {0: "auto", 1: "simt-fp32", 2: "tcgen05-bf16-exact-int", 3: "tcgen05-bf16-split",
-            4: "tcgen05-i8-exact-int"}.get(eng.knn2_l2_last_mode(), "?")
+    mode = head["mode"]
+    peak_tf, peak_clocks = bf16_tf, None
     peak_source = "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"
     if mode == "tcgen05-i8-exact-int":
-        # kind::i8 retires K=32 per MMA instruction slot where kind::f16 retires K=16: the integer pipe's peak is twice
-        # the bf16 one (measured issue rates, profiles/r1_microbench.txt: 4438 vs 2164 T op/s).  MEASURED_PEAKS.json has
-        # no INT8 line, so the denominator is 2 x its measured bf16 figure.
-        peak_tf = 2.0 * bf16_tf
-        peak_source = ("2 x (" + peak_source + "): tcgen05 kind::i8 issues twice the MACs per instruction slot of kind::f16 "
-                       "(measured 4438 vs 2164 T op/s back-to-back issue, profiles/r1_microbench.txt)")
-    # (the split engine executes 25/8 of the algorithmic 256 FLOP per pair on the tensor pipe; the roofline counts 256)
+        # MEASURED_PEAKS.json has no INT8 line: the denominator is this GPU's own sustained kind::i8 issue rate, measured now
+        peak_tf, peak_clocks = i8_sustained_peak(hp, device)
+        peak_source = ("hpusm_microbench_mma(kind::i8) sustained for 2 s in this run: every SM issuing back-to-back 128x256x32 "
+                       "u8 MMAs and nothing else (clocks under that load in roofline.peak_clocks)")
     out = {
         "metric": "descriptor-pairs/sec (kNN+ratio)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": head["ms"] / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": DTYPE_OF.get(mode, "f32"), "data": "synthetic",
-        "config": {"workload": "synthetic SIFT 128-d float, 1M query x 1M database kNN k=2 ratio test on 1 B200",
-                   "nq": nq, "nt_per_gpu": nt, "d": 128, "ratio": 0.8, "engine": mode, "descriptors": args.descriptors,
-                   "fallback_rows": eng.knn2_l2_last_fallback_rows(), "sharding": "database rows",
-                   "l2_flush": "inputs (2 x %.0f MB) exceed the 126 MB L2" % (nq * 512 / 1e6), "ratio_survivors": survivors},
-        "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
-                "h2d_bytes_per_step": int(hq.numel() * 4 + ht.numel() * 4),
-                "d2h_bytes_per_step": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel())},
-        "gpu_launches": int(launches),
+        "config": sift_config(args, world),
+        "detail": {"engine": mode, "fallback_rows": head["fallback_rows"], "sharding": "database rows",
+                   "l2_flush": "inputs (2 x %.0f MB) exceed the 126 MB L2" % (nq * 512 / 1e6), "ratio_survivors": head["survivors"]},
+        "e2e": {"value": pairs_head * args.steps / (head["e2e_ms"] * 1e-3), "unit": "pairs/s",
+                "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
+                "note": "per rank: its database shard + its 1/N slice of the queries over PCIe, query slices all-gathered over NVLink"},
+        "gpu_launches": int(head["launches"]),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt)),
-                     "kernel_ms": k_ms, "kernel_launches": int(kernel_n),
+                     "kernel_ms": k_ms, "kernel_launches": int(head["kernel_n"]),
                      "frac_of_bf16_peak": achieved / bf16_tf if bf16_tf else None, "peak_source": peak_source,
-                     "ncu": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt), "ncu")},
-        "clocks": clocks,
+                     "peak_clocks": peak_clocks, "ncu": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt), "ncu")},
+        "clocks": head["clocks"],
     }
+    for name, res, pairs in (("weak_scaling", weak, pairs_weak), ("strong_scaling", strong, pairs_strong)):
+        out[name] = {"value": pairs * args.steps / (res["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": res["ms"] / args.steps,
+                     "e2e": pairs * args.steps / (res["e2e_ms"] * 1e-3), "nq": nq, "nt_global": int(pairs / nq),
+                     "nt_per_gpu": res["nt_rank"], "kernel_ms": res["kernel_ms"] / max(res["kernel_n"], 1),
+                     "note": "efficiency at N GPUs = value(N) / (N x value(1)) for weak, value(N) / (N x value(1)) for strong "
+                             "(strong: the same nq x nt pairs in 1/N of the time)"}
+    if weak["parity"] is not None:
+        out["nccl_parity"] = weak["parity"]
     return out
 
 
@@ -348,6 +391,20 @@ class Timer:
 
     def __init__(self, args, rank, world, device, hp):
         self.args, self.rank, self.world, self.device, self.hp = args, rank, world, device, hp
+        self.steps = args.steps
+
+    def fit_region(self, step):
+        """Raises the step count until the timed region lasts --min-region-ms (short steps: >= 20 clock samples)."""
+        step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        self.barrier()
+        ms = max(self.max_over_ranks(e0.elapsed_time(e1)), 1e-3)
+        self.steps = int(max(self.args.steps, min(100000, -(-self.args.min_region_ms // ms))))
+        return self.steps
 
     def barrier(self):
         if self.world > 1:
@@ -379,12 +436,12 @@ class Timer:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         e0.record()
-        for _ in range(self.args.steps):
+        for _ in range(self.steps):
             out = step()
         e1.record()
         self.barrier()
         ms = self.max_over_ranks(e0.elapsed_time(e1))
-        res = {"ms": ms, "out": out, "launches": self.hp.launch_count() - l0}
+        res = {"ms": ms, "out": out, "launches": self.hp.launch_count() - l0, "steps": self.steps}
         if profile:
             res["kernel_ms"], res["kernel_n"] = eng.profile_collect()
             eng.profile_enable(False)
@@ -392,9 +449,10 @@ class Timer:
         return res
 
 
-def base_line(args, world, metric, unit, value, ms, dtype, scaling, config):
-    return {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dtype,
+def base_line(args, world, metric, unit, value, ms, dtype, scaling, config, steps=None):
+    steps = steps or args.steps
+    return {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dtype,
             "data": "synthetic", "config": config}
 
 
@@ -433,6 +491,7 @@ def run_orb(args, rank, world, device, hp):
     def step():
         return rt.image_scores_sharded(query, db, offs, 0.8)
 
+    tm.fit_region(step)
     r = tm.run(step)
     scores = r["out"]
     hq, hdb = query.cpu().pin_memory(), db.cpu().pin_memory()
@@ -450,17 +509,17 @@ def run_orb(args, rank, world, device, hp):
     top = torch.topk(scores, min(len(planted) * world, 16)).indices.tolist()
     ppeak, lpeak = popc_peak(hp, device, "popc"), popc_peak(hp, device, "lop3")
     k_ms = r["kernel_ms"] / max(r["kernel_n"], 1)
-    pairs_per_launch = float(per) * (b - a) * per * args.steps / max(r["kernel_n"], 1)
+    pairs_per_launch = float(per) * (b - a) * per * tm.steps / max(r["kernel_n"], 1)
     # per 256-bit pair the kernel issues 16 LOP3 (8 XOR + 4 carry-save adders) on the ALU pipe and 4 POPC on the XU pipe;
     # the two pipes run side by side, so the bound is the slower of the two
     t_bound = max(16.0 * pairs_per_launch / lpeak, 4.0 * pairs_per_launch / ppeak)
     ach = 16.0 * pairs_per_launch / (k_ms * 1e-3)
-    out = base_line(args, world, "descriptor-pairs/sec (kNN+ratio)", "pairs/s", pairs * args.steps / (r["ms"] * 1e-3), r["ms"], "u32 popc",
+    out = base_line(args, world, "descriptor-pairs/sec (kNN+ratio)", "pairs/s", pairs * tm.steps / (r["ms"] * 1e-3), r["ms"], "u32 popc",
                     "strong", {"workload": "synthetic ORB 256-bit Hamming, 10k-image database retrieval sharded across 2/4/8 B200",
                                "images": args.images, "descriptors_per_image": per, "query_descriptors": per, "ratio": 0.8,
                                "sharding": "database images", "l2_flush": "database shard (%.0f MB) exceeds the 126 MB L2" % (db.numel() / 1e6),
-                               "top_images": top[:8]})
-    out["e2e"] = {"value": pairs * args.steps / (e["ms"] * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(hq.numel() + hdb.numel()),
+                               "top_images": top[:8]}, steps=tm.steps)
+    out["e2e"] = {"value": pairs * tm.steps / (e["ms"] * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(hq.numel() + hdb.numel()),
                   "d2h_bytes_per_step": int(hs.numel() * 4)}
     out["gpu_launches"] = int(r["launches"])
     out["roofline"] = {"bound": "integer pipes (16 LOP3 + 4 POPC.32 per pair)", "achieved": ach / 1e12, "peak": lpeak / 1e12, "unit": "Tlop3/s",
@@ -523,7 +582,13 @@ def run_ransac(args, rank, world, device, hp):
     def step():
         return eng.ransac_score_batch(src, dst, offs, 5.0, nhyp, seed=2, out=counts, pair_index0=a)  # a = this shard's first pair
 
+    tm.fit_region(step)
     r = tm.run(step)
+    scored_t = (counts >= 0).sum().to(torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(scored_t)
+    scored_all = float(scored_t.item())        # hypotheses whose model was scored, over all ranks (every one of them, by design)
     scored = int((counts >= 0).sum().item())
     best = counts.max(dim=1).values.float().mean().item()
     # end to end = the full findHomography replacement (score + early-exit replay + refinement + mask) on a host batch
@@ -539,19 +604,30 @@ def run_ransac(args, rank, world, device, hp):
         hm.copy_(mask, non_blocking=True)
 
     e = tm.run(e2e_step, profile=False)
+    # the same full replacement with the matches already resident (no copies): score + replay + refinement + mask
+    nf = min(n, 16384)
+    Hf, mf, nif = [None], [None], [None]
+
+    def full_step():
+        Hf[0], mf[0], nif[0], _ = eng.ransac_homography_batch(src[:nf * K], dst[:nf * K], offs[:nf + 1], 5.0, nhyp, 0.0, seed=2,
+                                                              pair_index0=a)
+
+    f = tm.run(full_step, profile=False)
     if rank != 0:
         return None
-    hyps = float(args.pairs) * nhyp
+    hyps = scored_all   # `value` counts SCORED hypotheses only (round 1 counted the 79 % rejected as degenerate too)
     k_ms = r["kernel_ms"] / max(r["kernel_n"], 1)
-    evals = float(scored) * K  # reprojections actually evaluated on this rank per step (degenerate samples are rejected first)
+    evals = float(scored) * K  # reprojections evaluated on this rank per step
     flops = evals * 22.0
-    out = base_line(args, world, "RANSAC hyps/sec", "hyps/s", hyps * args.steps / (r["ms"] * 1e-3), r["ms"], "f32 score / f64 solve", "strong",
+    out = base_line(args, world, "RANSAC hyps/sec", "hyps/s", hyps * tm.steps / (r["ms"] * 1e-3), r["ms"], "f32 score / f64 solve", "strong",
                     {"workload": "batched RANSAC homography: 100k image pairs x 2k putative matches x 1024 hypotheses", "pairs": args.pairs,
                      "matches_per_pair": K, "hypotheses": nhyp, "thresh": 5.0, "inlier_ratio": 0.3, "sharding": "image pairs",
-                     "non_degenerate_fraction": scored / float(n * nhyp), "mean_best_inliers": best,
-                     "l2_flush": "match coordinates (%.1f GB) exceed the 126 MB L2" % (src.numel() * 8 / 1e9)})
-    out["e2e"] = {"value": ne * world * nhyp * args.steps / (e["ms"] * 1e-3), "unit": "hyps/s", "h2d_bytes_per_step": int(hs.numel() * 8),
+                     "sampler": "counter", "scored_fraction": scored / float(n * nhyp), "mean_best_inliers": best,
+                     "l2_flush": "match coordinates (%.1f GB) exceed the 126 MB L2" % (src.numel() * 8 / 1e9)}, steps=tm.steps)
+    out["e2e"] = {"value": ne * world * nhyp * tm.steps / (e["ms"] * 1e-3), "unit": "hyps/s", "h2d_bytes_per_step": int(hs.numel() * 8),
                   "d2h_bytes_per_step": int(hH.numel() * 8 + hm.numel()), "note": "full findHomography replacement incl. refinement, %d pairs per step" % ne}
+    out["find_homography_resident"] = {"value": nf * world * nhyp * tm.steps / (f["ms"] * 1e-3), "unit": "hyps/s", "pairs_per_step": nf,
+                                       "note": "score + early-exit replay + DLT/LM refinement + final mask, matches resident in HBM"}
     out["gpu_launches"] = int(r["launches"])
     out["roofline"] = {"bound": "fp32 pipe", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s",
                        "frac": flops / (k_ms * 1e-3) / (148 * 128 * 2 * 1.965e9), "traffic": measured_traffic("ransac:%dx%d" % (args.pairs, world)), "kernel_ms": k_ms,
@@ -607,6 +683,7 @@ def run_pose(args, rank, world, device, hp):
     def step():
         return rt.pose_topk_sharded(query, db, a, k=16, match_fn=match_fn)
 
+    tm.fit_region(step)
     r = tm.run(step)
     ts, ti, cnt = r["out"]
     ne = min(n, 2_000_000)
@@ -626,13 +703,13 @@ def run_pose(args, rank, world, device, hp):
     k_ms = r["kernel_ms"] / max(r["kernel_n"], 1)
     pk = peaks()
     peak = (pk or {}).get("hbm_gbs", 6650.0)
-    bytes_per_launch = n * (144.0 + 5.0) * args.steps / max(r["kernel_n"], 1)
+    bytes_per_launch = n * (144.0 + 5.0) * tm.steps / max(r["kernel_n"], 1)
     ach = bytes_per_launch / (k_ms * 1e-3) / 1e9
-    out = base_line(args, world, "pose pairs/sec (match_single)", "poses/s", float(args.poses) * args.steps / (r["ms"] * 1e-3), r["ms"], "f64", "strong",
+    out = base_line(args, world, "pose pairs/sec (match_single)", "poses/s", float(args.poses) * tm.steps / (r["ms"] * 1e-3), r["ms"], "f64", "strong",
                     {"workload": "OpenPose 18-joint Procrustes/affine pose matching: 1 query vs 10M synthetic pose database, multi-GPU",
                      "poses": args.poses, "matches": int(cnt.item()), "best_score": float(ts[0].item()), "sharding": "database poses",
-                     "l2_flush": "database shard (%.2f GB) exceeds the 126 MB L2" % (db.numel() * 4 / 1e9)})
-    out["e2e"] = {"value": ne * world * args.steps / (e["ms"] * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": int(hdb.numel() * 4),
+                     "l2_flush": "database shard (%.2f GB) exceeds the 126 MB L2" % (db.numel() * 4 / 1e9)}, steps=tm.steps)
+    out["e2e"] = {"value": ne * world * tm.steps / (e["ms"] * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": int(hdb.numel() * 4),
                   "d2h_bytes_per_step": 16 * 12, "note": "%d poses per step from pinned host memory" % ne}
     out["gpu_launches"] = int(r["launches"])
     out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("pose:%dx%d" % (args.poses, world)), "kernel_ms": k_ms,
@@ -670,20 +747,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+    hp = importlib.import_module(PKG)
+    runners = {"orb": run_orb, "ransac": run_ransac, "pose": run_pose}
     if args.workload != "sift":
-        hp = importlib.import_module(PKG)
-        out = {"orb": run_orb, "ransac": run_ransac, "pose": run_pose}[args.workload](args, rank, world, device, hp)
-        if rank == 0:
-            print(json.dumps(out), flush=True)
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
-        return
-    out = run_ours(args, rank, world, device)
-    if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
+        out = runners[args.workload](args, rank, world, device, hp)
+    else:
+        out = run_sift(args, rank, world, device, hp)
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
             cores = cpu_threads()
-            hp = importlib.import_module(PKG)
             ns = pick_cpu_sample(args.nt, args.cpu_sample)
             qn, tn = hp.synth.sift_like(ns, args.nt, seed=7, planted=0.1)
             reference_step(qn[:max(16, ns // 8)], tn)
@@ -693,6 +764,19 @@ def main():
             out["cpu_baseline"] = {"value": ns * args.nt / dt, "unit": "pairs/s", "cores": cores, "kind": "reference",
                                    "sample": "%d queries x %d db rows, cv2.BFMatcher(NORM_L2).knnMatch k=2 + ratio loop "
                                              "(features.py:59,:45-55), %.1f s" % (ns, args.nt, dt)}
+        if not args.no_others:
+            others = {}
+            for name in ("orb", "ransac", "pose"):
+                torch.cuda.empty_cache()
+                try:
+                    res = runners[name](args, rank, world, device, hp)
+                except Exception as exc:  # one workload failing must not cost the headline line
+                    res = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                if rank == 0:
+                    others[name] = res
+            if rank == 0:
+                out["others"] = others
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist

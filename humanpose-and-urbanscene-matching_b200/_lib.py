@@ -62,13 +62,11 @@ SIGNATURES = {
     "hpusm_gather_matches": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "hpusm_segment_matches": (_i32, [_p, _p, _i64, _i64, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "hpusm_validate_homography_batch": (_i32, [_p, _i64, _p, _p]),
-    "hpusm_ransac_homography_workspace_bytes": (_sz, [_i64, _i64, _i32]),
-    "hpusm_ransac_homography_batch": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _f64, _u64, _i32, _p, _p, _p, _p,
-                                             _p, _sz, _p]),
-    "hpusm_ransac_score_batch": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _u64, _p, _p]),
-    "hpusm_ransac_homography_batch_at": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _f64, _u64, _i64, _i32, _p, _p, _p,
-                                                _p, _p, _sz, _p]),
-    "hpusm_ransac_score_batch_at": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _u64, _i64, _p, _p]),
+    "hpusm_ransac_homography_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "hpusm_ransac_homography_batch": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _f64, _i32, _u64, _i64, _i32, _p, _p, _p,
+                                             _p, _p, _sz, _p]),
+    "hpusm_ransac_score_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "hpusm_ransac_score_batch": (_i32, [_p, _p, _p, _i64, _i64, _f32, _i32, _i32, _u64, _i64, _p, _p, _sz, _p]),
     "hpusm_perspective_transform": (_i32, [_p, _i64, _p, _p, _p]),
     "hpusm_affine_lsq_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p]),
     "hpusm_procrustes_batch": (_i32, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -196,13 +196,15 @@ __global__ void validate_homography_kernel(const double* __restrict__ H, int64_t
   if (i >= n) return;
   const double* h = H + i * 9;
   bool ok = h[0] == h[0];
-  const double det = h[0] * h[4] - h[1] * h[3];
+  // Python evaluates these in double with one rounding per operation: no FMA contraction here, or a singular
+  // top-left block (h00*h11 == h01*h10 after rounding) could come out as a tiny negative determinant
+  const double det = __dsub_rn(__dmul_rn(h[0], h[4]), __dmul_rn(h[1], h[3]));
   if (det < 0) ok = false;
-  const double n1 = sqrt(h[0] * h[0] + h[1] * h[1]);
+  const double n1 = sqrt(__dadd_rn(__dmul_rn(h[0], h[0]), __dmul_rn(h[1], h[1])));
   if (n1 > 4 || n1 < 0.1) ok = false;
-  const double n2 = sqrt(h[3] * h[3] + h[4] * h[4]);
+  const double n2 = sqrt(__dadd_rn(__dmul_rn(h[3], h[3]), __dmul_rn(h[4], h[4])));
   if (n2 > 4 || n2 < 0.1) ok = false;
-  const double n3 = sqrt(h[6] * h[6] + h[7] * h[7]);
+  const double n3 = sqrt(__dadd_rn(__dmul_rn(h[6], h[6]), __dmul_rn(h[7], h[7])));
   if (n3 > 0.002) ok = false;
   valid[i] = ok ? 1 : 0;
 }

@@ -1,26 +1,26 @@
 // K3: batched RANSAC homography.
 //
-// Replaces cv2.findHomography(src, dst, cv2.RANSAC, 5.0) at reference urbanscene/features.py:66,:69.
-// OpenCV's sampler cannot be seeded from Python, so parity is defined against oracle/ransac_oracle.c,
-// which restates exactly the arithmetic below (same counter-based sample table, same operation order,
-// explicit round-to-nearest intrinsics / no FMA contraction), giving identical hypotheses, identical
-// inlier sets and an identical winner on CPU and GPU.
-//
-// One CTA per image pair:
-//   phase A  each LANE derives one hypothesis: sample 4 matches from the (seed, pair, hypothesis) key,
-//            reject degenerate samples (collinear triples, inconsistent orientation), and solve the
-//            exact 4-point homography in FP64 in closed form (unit square -> quad on both sides,
-//            H = S_dst * adj(S_src)); the FP32 model is parked in shared memory.
-//   phase B  the surviving hypotheses are compacted; a warp takes 32 of them (one per LANE, model in registers) and
-//            streams a segment of the pair's matches, staged in shared memory as float4 (x, y, x', y') and read as
-//            broadcast LDS.128; the inlier test is division free, (u - x'w)^2 + (v - y'w)^2 <= thr^2 w^2, the count
-//            lives in a register.  (Round-1 first version: one warp per hypothesis + popc(ballot), as north_star
-//            sketches; ncu showed 2.6x the instructions per reprojection -- ballot, POPC on the 16-lane XU pipe, and
-//            half-empty hypothesis pairs -- see profiles/r1_ransac_score_ncu.txt.)
-//   phase C  the sequential early-exit of RANSAC (cv2's adaptive iteration bound) is replayed over the
-//            counts by one thread, so the parallel evaluation returns what the sequential loop would.
-// A second kernel re-derives the winner, writes its inlier mask, and refines: normalised least-squares
-// DLT on the inliers, then Levenberg-Marquardt on the reprojection error (FP64, block reductions).
+// Replaces cv2.findHomography(src, dst, cv2.RANSAC, 5.0) at reference urbanscene/features.py:66,:69.  OpenCV is not
+// vendored under /root/reference; its algorithm is restated function by function in oracle/ransac_oracle.c (pinned on
+// cv2's own outputs, see the header there) and this file computes the same thing on the GPU:
+//   * sampler.  HPUSM_RANSAC_SAMPLER_CV2 replays OpenCV's fixed-seed generator (RNG((uint64)-1), multiply-with-carry,
+//     uniform(0, count), duplicate redraw, checkSubset, up to 10000 attempts) in a per-pair sequential pre-pass, so the
+//     hypotheses -- and with them mask and H -- are cv2.findHomography's own.  HPUSM_RANSAC_SAMPLER_COUNTER draws from a
+//     counter-based table keyed on (seed, pair, hypothesis, attempt): every hypothesis is a pure function of its key and
+//     the lanes draw them in parallel.  Both redraw until OpenCV's checkSubset passes, so each of the nhyp iterations
+//     scores a model (round 1 drew once and left 79 % of C4's hypotheses unscored).
+//   * minimal solver: closed form in FP64 (unit square -> quad on both sides, H = S_dst * adj(S_src)), op for op the
+//     oracle's, instead of OpenCV's 9x9 eigen decomposition (same unique homography, rounding apart).
+//   * scoring.  One CTA per image pair, matches staged in shared memory as float4 pairs; a warp takes 32 hypotheses
+//     (one per LANE, model in registers) and streams the matches as broadcast LDS.128 through sm_100's packed FP32
+//     pipe.  Under the counter sampler the test is division free, (u - x'w)^2 + (v - y'w)^2 <= thr^2 w^2; under the cv2
+//     sampler it is OpenCV's computeError, float32 with a correctly rounded division, one rounding per operation.
+//   * the sequential early exit of RANSAC (RANSACUpdateNumIters) is replayed over the counts by one thread, so the
+//     parallel evaluation returns what the sequential loop would.
+//   * refinement (findHomography's post-processing): one WARP per pair.  runKernel's normalised DLT on the inliers of
+//     the winning model (smallest eigenvector of the 9x9 LtL by inverse iteration on a Cholesky factor), then
+//     LMSolver's <= 10 Levenberg-Marquardt iterations with its lambda schedule on HomographyRefineCallback's residuals
+//     (FP64, pixel coordinates), then the mask of the REFINED model under computeError -- what cv2 4.x returns.
 #include <float.h>
 #include <math.h>
 #include "common.cuh"
@@ -30,6 +30,8 @@ namespace hpusm {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_CHUNK = 4096;  // matches staged in shared memory at a time (64 KB)
+constexpr int COUNTER_MAX_ATTEMPTS = 256;
+constexpr int CV_MAX_ATTEMPTS = 10000;
 
 // ---- counter-based sample table -----------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
@@ -40,10 +42,11 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-// Four distinct indices in [0, K), K >= 4, as a function of (seed, pair, hyp) only.
-__host__ __device__ __forceinline__ void sample4(uint64_t seed, uint64_t pair, uint64_t hyp, uint32_t K,
+// Four distinct indices in [0, K), K >= 4, as a function of (seed, pair, hyp, attempt) only.
+__host__ __device__ __forceinline__ void sample4(uint64_t seed, uint64_t pair, uint64_t hyp, uint32_t attempt, uint32_t K,
                                                  uint32_t out[4]) {
-  uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (pair + 1)) ^ (0x8CB92BA72F3D8DD7ull * (hyp + 1));
+  uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (pair + 1)) ^ (0x8CB92BA72F3D8DD7ull * (hyp + 1)) ^
+               (0xA0761D6478BD642Full * (uint64_t)attempt);
   (void)splitmix64(s);
   uint32_t sorted[4];
   for (int j = 0; j < 4; ++j) {
@@ -59,6 +62,12 @@ __host__ __device__ __forceinline__ void sample4(uint64_t seed, uint64_t pair, u
   }
 }
 
+// OpenCV's RNG::next(): multiply-with-carry.
+__device__ __forceinline__ uint32_t cv_rng_next(uint64_t& state) {
+  state = (uint64_t)(uint32_t)state * 4164903690ull + (uint32_t)(state >> 32);
+  return (uint32_t)state;
+}
+
 // ---- minimal solver (FP64, explicit rounding so that the C oracle reproduces every bit) ----------
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -68,32 +77,6 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 // 2x2 determinant a*d - b*c with two roundings of the products and one of the difference.
 __device__ __forceinline__ double det2(double a, double b, double c, double d) {
   return dsub(dmul(a, d), dmul(b, c));
-}
-
-// orientation of the triangle (p, q, r): (q-p) x (r-p)
-__device__ __forceinline__ double orient(const double* x, const double* y, int p, int q, int r) {
-  return det2(dsub(x[q], x[p]), dsub(y[q], y[p]), dsub(x[r], x[p]), dsub(y[r], y[p]));
-}
-
-// True when the 4-point sample is unusable: a (near-)collinear triple on either side, or the four
-// triangles do not keep a common orientation relation between the two images.
-__device__ __forceinline__ bool degenerate4(const double* sx, const double* sy, const double* dx, const double* dy) {
-  const int tri[4][3] = {{0, 1, 2}, {1, 2, 3}, {0, 2, 3}, {0, 1, 3}};
-  int flipped = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int p = tri[k][0], q = tri[k][1], r = tri[k][2];
-    const double os = orient(sx, sy, p, q, r);
-    const double od = orient(dx, dy, p, q, r);
-    const double ms = dadd(dadd(fabs(dsub(sx[q], sx[p])), fabs(dsub(sy[q], sy[p]))),
-                           dadd(fabs(dsub(sx[r], sx[p])), fabs(dsub(sy[r], sy[p]))));
-    const double md = dadd(dadd(fabs(dsub(dx[q], dx[p])), fabs(dsub(dy[q], dy[p]))),
-                           dadd(fabs(dsub(dx[r], dx[p])), fabs(dsub(dy[r], dy[p]))));
-    if (fabs(os) <= dmul(1.1920928955078125e-07, ms)) return true;
-    if (fabs(od) <= dmul(1.1920928955078125e-07, md)) return true;
-    if ((os < 0.0) != (od < 0.0)) ++flipped;
-  }
-  return flipped != 0 && flipped != 4;
 }
 
 // Projective map of the unit square (0,0),(1,0),(1,1),(0,1) onto the quad p0..p3, row-major 3x3.
@@ -135,35 +118,6 @@ __device__ __forceinline__ bool homography_from_maps(const double* S, const doub
   return ok;
 }
 
-// The four sampled correspondences of hypothesis (pair, hyp) as doubles.
-__device__ __forceinline__ void hypothesis_points(const float* __restrict__ src, const float* __restrict__ dst, uint32_t K,
-                                                  uint64_t seed, uint64_t pair, uint64_t hyp, double* sx, double* sy,
-                                                  double* dx, double* dy) {
-  uint32_t id[4];
-  sample4(seed, pair, hyp, K, id);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 s = reinterpret_cast<const float2*>(src)[id[j]];
-    const float2 d = reinterpret_cast<const float2*>(dst)[id[j]];
-    sx[j] = (double)s.x; sy[j] = (double)s.y; dx[j] = (double)d.x; dy[j] = (double)d.y;
-  }
-}
-
-// Same, reading the matches from the pair-packed shared-memory staging of the scoring kernel:
-// pts[2j] = (x0, x1, y0, y1), pts[2j+1] = (-x'0, -x'1, -y'0, -y'1) for matches 2j, 2j+1 (negation is exact).
-__device__ __forceinline__ void hypothesis_points_smem(const float4* pts, uint32_t K, uint64_t seed, uint64_t pair,
-                                                       uint64_t hyp, double* sx, double* sy, double* dx, double* dy) {
-  uint32_t id[4];
-  sample4(seed, pair, hyp, K, id);
-  const float* f = reinterpret_cast<const float*>(pts);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t base = (id[j] >> 1) * 8 + (id[j] & 1);
-    sx[j] = (double)f[base]; sy[j] = (double)f[base + 2];
-    dx[j] = (double)(-f[base + 4]); dy[j] = (double)(-f[base + 6]);
-  }
-}
-
 // Exact 4-point homography of a non-degenerate sample. Points are translated to the first sample point before the
 // closed-form solve (exact in FP64 for pixel-range FP32 input) and the translation is folded back in afterwards.
 __device__ bool hypothesis_solve(double* sx, double* sy, double* dx, double* dy, double* H) {
@@ -197,17 +151,86 @@ __device__ bool hypothesis_solve(double* sx, double* sy, double* dx, double* dy,
   return ok;
 }
 
-// Whole minimal-sample pipeline for one hypothesis.
-__device__ bool hypothesis_model(const float* __restrict__ src, const float* __restrict__ dst, uint32_t K,
-                                 uint64_t seed, uint64_t pair, uint64_t hyp, double* H) {
-  double sx[4], sy[4], dx[4], dy[4];
-  hypothesis_points(src, dst, K, seed, pair, hyp, sx, sy, dx, dy);
-  if (degenerate4(sx, sy, dx, dy)) return false;
-  return hypothesis_solve(sx, sy, dx, dy, H);
+
+// ---- HomographyEstimatorCallback::checkSubset for a 4-point sample (FP64, one rounding per operation) ----------------
+__device__ __forceinline__ bool cv_collinear_with_last(const double* x, const double* y) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double dx1 = dsub(x[j], x[3]), dy1 = dsub(y[j], y[3]);
+#pragma unroll
+    for (int k = 0; k < j; ++k) {
+      const double dx2 = dsub(x[k], x[3]), dy2 = dsub(y[k], y[3]);
+      const double lhs = fabs(dsub(dmul(dx2, dy1), dmul(dy2, dx1)));
+      const double rhs = dmul(1.1920928955078125e-07, dadd(dadd(dadd(fabs(dx1), fabs(dy1)), fabs(dx2)), fabs(dy2)));
+      if (lhs <= rhs) return true;
+    }
+  }
+  return false;
 }
 
-// Division-free inlier test in FP32 with explicit FMAs (mirrored by the oracle with fmaf()).
-__device__ __forceinline__ bool is_inlier(const float* h, float x, float y, float xp, float yp, float thr2) {
+// determinant of [[x0,y0,1],[x1,y1,1],[x2,y2,1]] in the operation order of cv::Matx33d's determinant
+__device__ __forceinline__ double cv_det3(double x0, double y0, double x1, double y1, double x2, double y2) {
+  const double m0 = dsub(y1, y2), m1 = dsub(x1, x2);
+  const double m2 = dsub(dmul(x1, y2), dmul(x2, y1));
+  return dadd(dsub(dmul(x0, m0), dmul(y0, m1)), m2);
+}
+
+__device__ __forceinline__ bool cv_check_subset(const double* sx, const double* sy, const double* dx, const double* dy) {
+  if (cv_collinear_with_last(sx, sy) || cv_collinear_with_last(dx, dy)) return false;
+  const int tt[4][3] = {{0, 1, 2}, {1, 2, 3}, {0, 2, 3}, {0, 1, 3}};
+  int negative = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = tt[i][0], b = tt[i][1], c = tt[i][2];
+    const double dA = cv_det3(sx[a], sy[a], sx[b], sy[b], sx[c], sy[c]);
+    const double dB = cv_det3(dx[a], dy[a], dx[b], dy[b], dx[c], dy[c]);
+    negative += (dmul(dA, dB) < 0.0) ? 1 : 0;
+  }
+  return negative == 0 || negative == 4;
+}
+
+// The four correspondences id[0..3] as doubles, from global memory ...
+__device__ __forceinline__ void sample_points(const float* __restrict__ src, const float* __restrict__ dst, const uint32_t* id,
+                                              double* sx, double* sy, double* dx, double* dy) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 s = __ldg(reinterpret_cast<const float2*>(src) + id[j]);
+    const float2 d = __ldg(reinterpret_cast<const float2*>(dst) + id[j]);
+    sx[j] = (double)s.x; sy[j] = (double)s.y; dx[j] = (double)d.x; dy[j] = (double)d.y;
+  }
+}
+
+// ... or from the pair-packed shared-memory staging of the scoring kernel:
+// pts[2j] = (x0, x1, y0, y1), pts[2j+1] = (-x'0, -x'1, -y'0, -y'1) for matches 2j, 2j+1 (negation is exact).
+__device__ __forceinline__ void sample_points_smem(const float4* pts, const uint32_t* id, double* sx, double* sy, double* dx,
+                                                   double* dy) {
+  const float* f = reinterpret_cast<const float*>(pts);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t base = (id[j] >> 1) * 8 + (id[j] & 1);
+    sx[j] = (double)f[base]; sy[j] = (double)f[base + 2];
+    dx[j] = (double)(-f[base + 4]); dy[j] = (double)(-f[base + 6]);
+  }
+}
+
+// Counter sampler: redraw (attempt = 0, 1, ...) until the subset check passes.  false after COUNTER_MAX_ATTEMPTS.
+template <bool SMEM>
+__device__ __forceinline__ bool counter_sample(const float4* pts, const float* __restrict__ src, const float* __restrict__ dst,
+                                               uint32_t K, uint64_t seed, uint64_t pair, uint64_t hyp, double* sx, double* sy,
+                                               double* dx, double* dy) {
+  for (uint32_t a = 0; a < COUNTER_MAX_ATTEMPTS; ++a) {
+    uint32_t id[4];
+    sample4(seed, pair, hyp, a, K, id);
+    if (SMEM) sample_points_smem(pts, id, sx, sy, dx, dy);
+    else sample_points(src, dst, id, sx, sy, dx, dy);
+    if (cv_check_subset(sx, sy, dx, dy)) return true;
+  }
+  return false;
+}
+
+// ---- inlier tests -----------------------------------------------------------------------------------------------------
+// Division-free test in FP32 with explicit FMAs (mirrored by the oracle with fmaf()).
+__device__ __forceinline__ bool fast_is_inlier(const float* h, float x, float y, float xp, float yp, float thr2) {
   const float w = __fmaf_rn(h[6], x, __fmaf_rn(h[7], y, h[8]));
   const float u = __fmaf_rn(h[0], x, __fmaf_rn(h[1], y, h[2]));
   const float v = __fmaf_rn(h[3], x, __fmaf_rn(h[4], y, h[5]));
@@ -218,19 +241,16 @@ __device__ __forceinline__ bool is_inlier(const float* h, float x, float y, floa
   return e <= lim;
 }
 
-// Same test, accumulating into `cnt` with one predicated add (the compiler's select + add costs an extra issue slot).
-__device__ __forceinline__ void inlier_count(const float* h, float x, float y, float xp, float yp, float thr2, int& cnt) {
-  const float w = __fmaf_rn(h[6], x, __fmaf_rn(h[7], y, h[8]));
-  const float u = __fmaf_rn(h[0], x, __fmaf_rn(h[1], y, h[2]));
-  const float v = __fmaf_rn(h[3], x, __fmaf_rn(h[4], y, h[5]));
-  const float du = __fmaf_rn(-xp, w, u);
-  const float dv = __fmaf_rn(-yp, w, v);
-  const float e = __fmaf_rn(du, du, __fmul_rn(dv, dv));
-  const float lim = __fmul_rn(__fmul_rn(thr2, w), w);
-  asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(e), "f"(lim));
+// OpenCV's HomographyEstimatorCallback::computeError: float32, a correctly rounded division, no contraction.
+__device__ __forceinline__ bool cv_is_inlier(const float* h, float x, float y, float xp, float yp, float thr2) {
+  const float ww = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(h[6], x), __fmul_rn(h[7], y)), 1.f));
+  const float px = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(h[0], x), __fmul_rn(h[1], y)), h[2]), ww);
+  const float py = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(h[3], x), __fmul_rn(h[4], y)), h[5]), ww);
+  const float ex = __fsub_rn(px, xp), ey = __fsub_rn(py, yp);
+  return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) <= thr2;
 }
 
-// ---- packed FP32 (sm_100 FFMA2 / FMUL2): two matches per instruction, each half rounded exactly like the scalar op ----
+// ---- packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2): two matches per instruction, each half rounded exactly like the scalar op
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
   f32x2 r;
@@ -248,11 +268,15 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
-// The inlier test of is_inlier() on TWO matches at once.  xy = (x0, x1, y0, y1), nq = (-x'0, -x'1, -y'0, -y'1);
-// h2[i] holds model coefficient i in both halves.  Same operations in the same order as the scalar test, so the
-// counts stay bit-identical to oracle/ransac_oracle.c.
-__device__ __forceinline__ void inlier_count2(const f32x2* h2, f32x2 thr2, float4 xy, float4 nq, int& cnt) {
+// fast_is_inlier() on TWO matches at once.  xy = (x0, x1, y0, y1), nq = (-x'0, -x'1, -y'0, -y'1); h2[i] holds model
+// coefficient i in both halves.  Same operations in the same order as the scalar test: counts stay bit-identical to the oracle.
+__device__ __forceinline__ void fast_count2(const f32x2* h2, f32x2 thr2, float4 xy, float4 nq, int& cnt) {
   const f32x2 X = pack2(xy.x, xy.y), Y = pack2(xy.z, xy.w), NXP = pack2(nq.x, nq.y), NYP = pack2(nq.z, nq.w);
   const f32x2 w = fma2(h2[6], X, fma2(h2[7], Y, h2[8]));
   const f32x2 u = fma2(h2[0], X, fma2(h2[1], Y, h2[2]));
@@ -268,7 +292,25 @@ __device__ __forceinline__ void inlier_count2(const f32x2* h2, f32x2 thr2, float
       : "+r"(cnt) : "f"(e0), "f"(l0), "f"(e1), "f"(l1));
 }
 
-// cv2's adaptive bound on the number of iterations (RANSACUpdateNumIters restated).
+// cv_is_inlier() on two matches at once (h2[8] holds 1.0f in both halves).
+__device__ __forceinline__ void cv_count2(const f32x2* h2, f32x2 thr2, float4 xy, float4 nq, int& cnt) {
+  const f32x2 X = pack2(xy.x, xy.y), Y = pack2(xy.z, xy.w), NXP = pack2(nq.x, nq.y), NYP = pack2(nq.z, nq.w);
+  const f32x2 den = add2(add2(mul2(h2[6], X), mul2(h2[7], Y)), h2[8]);
+  float d0, d1;
+  unpack2(den, d0, d1);
+  const f32x2 ww = pack2(__fdiv_rn(1.f, d0), __fdiv_rn(1.f, d1));
+  const f32x2 px = mul2(add2(add2(mul2(h2[0], X), mul2(h2[1], Y)), h2[2]), ww);
+  const f32x2 py = mul2(add2(add2(mul2(h2[3], X), mul2(h2[4], Y)), h2[5]), ww);
+  const f32x2 ex = add2(px, NXP), ey = add2(py, NYP);  // px - x' == px + (-x') in IEEE arithmetic
+  const f32x2 e = add2(mul2(ex, ex), mul2(ey, ey));
+  float e0, e1, l0, l1;
+  unpack2(e, e0, e1);
+  unpack2(thr2, l0, l1);
+  asm("{\n\t.reg .pred p, q;\n\tsetp.le.f32 p, %1, %2;\n\tsetp.le.f32 q, %3, %4;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t}"
+      : "+r"(cnt) : "f"(e0), "f"(l0), "f"(e1), "f"(l1));
+}
+
+// cv2's adaptive bound on the number of iterations (RANSACUpdateNumIters restated, modelPoints = 4).
 __device__ int update_num_iters(double conf, double outlier_ratio, int max_iters) {
   double p = fmin(fmax(conf, 0.0), 1.0);
   double ep = fmin(fmax(outlier_ratio, 0.0), 1.0);
@@ -282,19 +324,59 @@ __device__ int update_num_iters(double conf, double outlier_ratio, int max_iters
   return (int)llrint(num / denom);
 }
 
+// ---- cv2 sampler pre-pass: one THREAD per pair walks OpenCV's sequence; samples [npairs][nhyp] int4, x = -1: none -------
+__global__ void __launch_bounds__(64)
+ransac_sample_cv2_kernel(const float* __restrict__ src, const float* __restrict__ dst, const int64_t* __restrict__ pair_offsets,
+                         int64_t npairs, int nhyp, int4* __restrict__ samples) {
+  const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= npairs) return;
+  const int64_t m0 = pair_offsets[pair];
+  const uint32_t K = (uint32_t)(pair_offsets[pair + 1] - m0);
+  const float* s = src + m0 * 2;
+  const float* d = dst + m0 * 2;
+  int4* out = samples + pair * nhyp;
+  uint64_t state = 0xFFFFFFFFFFFFFFFFull;
+  int h = 0;
+  if (K >= 4) {
+    for (; h < nhyp; ++h) {
+      bool found = false;
+      uint32_t id[4];
+      for (int it = 0; it < CV_MAX_ATTEMPTS && !found; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          for (;;) {
+            const uint32_t v = cv_rng_next(state) % K;
+            bool dup = false;
+#pragma unroll
+            for (int c = 0; c < i; ++c) dup |= (id[c] == v);
+            if (!dup) { id[i] = v; break; }
+          }
+        }
+        double sx[4], sy[4], dx[4], dy[4];
+        sample_points(s, d, id, sx, sy, dx, dy);
+        found = cv_check_subset(sx, sy, dx, dy);
+      }
+      if (!found) break;  // OpenCV ends the loop when an iteration finds no subset
+      out[h] = make_int4((int)id[0], (int)id[1], (int)id[2], (int)id[3]);
+    }
+  }
+  for (; h < nhyp; ++h) out[h] = make_int4(-1, -1, -1, -1);
+}
+
 // grid.x = pairs. dynamic smem: float4 pts[chunk]; float models[nhyp][9] (compacted); int counts[nhyp]; int hyp_of[nhyp].
-//   A1  one LANE per hypothesis: sample + degeneracy test; survivors are compacted (ballot + one smem atomic per warp)
-//   A2  one LANE per surviving hypothesis: FP64 closed-form solve, FP32 model parked in shared memory
+//   A   one LANE per hypothesis: sample (redraw until the subset check passes | read the cv2 table) + FP64 closed-form
+//       solve; the models that exist are compacted (ballot + one smem atomic per warp), FP32 model parked in shared memory
 //   B   lane = hypothesis (model in 9 registers), the pair's matches stream through as broadcast LDS.128; work items
 //       are (32 hypotheses) x (RS_SEG matches) so all warps stay busy; the count lives in a register
-//   C   sequential replay of RANSAC's early exit over the counts
+//   C   sequential replay of RANSAC's early exit over the counts; the winner's FP64 model goes to best_H
 constexpr int RS_SEG = 256;
 
+template <bool CV>
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst,
                     const int64_t* __restrict__ pair_offsets, float thresh, int nhyp, double confidence,
-                    uint64_t seed, int64_t pair0, int chunk, int32_t* __restrict__ counts_out,
-                    int32_t* __restrict__ best_hyp, int32_t* __restrict__ best_count) {
+                    uint64_t seed, int64_t pair0, int chunk, const int4* __restrict__ samples,
+                    int32_t* __restrict__ counts_out, int32_t* __restrict__ best_hyp, double* __restrict__ best_H) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   float4* pts = reinterpret_cast<float4*>(rs_smem);
   float* models = reinterpret_cast<float*>(rs_smem + (size_t)chunk * sizeof(float4));
@@ -307,6 +389,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   const uint32_t K = (uint32_t)K64;
   const float* s = src + m0 * 2;
   const float* d = dst + m0 * 2;
+  const int4* smp = CV ? samples + pair * nhyp : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float thr2 = __fmul_rn(thresh, thresh);
   if (tid == 0) n_valid = 0;
@@ -327,45 +410,51 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       pts[2 * j + 1] = make_float4(-b0.x, -b1.x, -b0.y, -b1.y);
     }
   };
-  // When the whole pair fits (the common case) it is staged ONCE, before hypothesis generation, so the 8 scattered
-  // sample reads per hypothesis hit shared memory instead of L2.
+  // When the whole pair fits (the common case) it is staged ONCE, before hypothesis generation, so the scattered
+  // sample reads of every draw hit shared memory instead of L2.
   const bool resident = K64 <= chunk;
   if (resident) stage(0, (int)K64);
   __syncthreads();
 
-  // phase A1
+  // The points of hypothesis h (after redraws / from the cv2 table); false when the iteration has no sample.
+  auto hypothesis_points = [&](int h, double* sx, double* sy, double* dx, double* dy) -> bool {
+    if (K < 4) return false;
+    if (CV) {
+      const int4 q = __ldg(smp + h);
+      if (q.x < 0) return false;
+      const uint32_t id[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+      if (resident) sample_points_smem(pts, id, sx, sy, dx, dy);
+      else sample_points(s, d, id, sx, sy, dx, dy);
+      return true;
+    }
+    return resident ? counter_sample<true>(pts, s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy)
+                    : counter_sample<false>(pts, s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
+  };
+
+  // phase A
   const int rounds = (nhyp + RS_THREADS - 1) / RS_THREADS;
   for (int r = 0; r < rounds; ++r) {
     const int h = r * RS_THREADS + tid;
     bool ok = false;
-    if (h < nhyp && K >= 4) {
+    double H[9];
+    if (h < nhyp) {
       double sx[4], sy[4], dx[4], dy[4];
-      if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
-      else hypothesis_points(s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
-      ok = !degenerate4(sx, sy, dx, dy);
+      ok = hypothesis_points(h, sx, sy, dx, dy) && hypothesis_solve(sx, sy, dx, dy, H);
     }
     const unsigned b = __ballot_sync(0xffffffffu, ok);
     int base = 0;
     if (lane == 0 && b) base = atomicAdd(&n_valid, __popc(b));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (ok) hyp_of[base + __popc(b & ((1u << lane) - 1u))] = h;
+    if (ok) {
+      const int j = base + __popc(b & ((1u << lane) - 1u));
+      hyp_of[j] = h;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) models[j * 9 + i] = (float)H[i];
+    }
     if (h < nhyp) counts[h] = ok ? 0 : -1;
   }
   __syncthreads();
   const int nv = n_valid;
-
-  // phase A2
-  for (int j = tid; j < nv; j += RS_THREADS) {
-    const int h = hyp_of[j];
-    double sx[4], sy[4], dx[4], dy[4], H[9];
-    if (resident) hypothesis_points_smem(pts, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
-    else hypothesis_points(s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
-    const bool ok = hypothesis_solve(sx, sy, dx, dy, H);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) models[j * 9 + i] = ok ? (float)H[i] : 0.f;
-    if (!ok) { counts[h] = -1; hyp_of[j] = -1; }
-  }
-  __syncthreads();
 
   // phase B
   const int groups = (nv + 31) >> 5;
@@ -373,6 +462,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   for (int64_t c0 = 0; c0 < K64; c0 += chunk) {
     const int cn = (int)min((int64_t)chunk, K64 - c0);
     if (!resident) {
+      __syncthreads();
       stage(c0, cn);
       __syncthreads();
     }
@@ -391,11 +481,14 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       const int p0 = sg * (RS_SEG / 2), p1 = min(npair, p0 + RS_SEG / 2);
       int cnt = 0;
 #pragma unroll 4
-      for (int i = p0; i < p1; ++i) inlier_count2(h2, thr2x2, pts[2 * i], pts[2 * i + 1], cnt);
+      for (int i = p0; i < p1; ++i) {
+        if (CV) cv_count2(h2, thr2x2, pts[2 * i], pts[2 * i + 1], cnt);
+        else fast_count2(h2, thr2x2, pts[2 * i], pts[2 * i + 1], cnt);
+      }
       if (h >= 0 && cnt) atomicAdd(&counts[h], cnt);
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   if (counts_out) {
     for (int h = tid; h < nhyp; h += RS_THREADS) counts_out[pair * nhyp + h] = counts[h];
@@ -408,308 +501,415 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       const int c = counts[h];
       if (c > best_c) {
         best_c = c; best = h;
-        if (confidence > 0.0) niters = update_num_iters(confidence, (double)(K64 - c) / (double)K64, nhyp);
+        if (confidence > 0.0) niters = update_num_iters(confidence, (double)(K64 - c) / (double)K64, niters);
       }
     }
     best_hyp[pair] = best;
-    best_count[pair] = best >= 0 ? best_c : 0;
-  }
-}
-
-// ---- refinement ------------------------------------------------------------------------------------
-constexpr int RF_THREADS = 256;
-constexpr int RF_NSUM = 45;  // 36 (upper triangle of 8x8) + 8 (rhs) + 1 (cost)
-
-// Block-wide sum of NS doubles per thread; result valid in `out` (shared) for all threads after return.
-template <int NS>
-__device__ void block_sum(double (&v)[NS], double* scratch /* [RF_THREADS/32][NS] */, double* out /* [NS] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (best >= 0) {
+      double sx[4], sy[4], dx[4], dy[4], H[9];
+      (void)hypothesis_points(best, sx, sy, dx, dy);
+      (void)hypothesis_solve(sx, sy, dx, dy, H);
 #pragma unroll
-  for (int i = 0; i < NS; ++i) {
-    double x = v[i];
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) scratch[warp * NS + i] = x;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NS; i += blockDim.x) {
-    double x = 0.0;
-    for (int w = 0; w < RF_THREADS / 32; ++w) x += scratch[w * NS + i];
-    out[i] = x;
-  }
-  __syncthreads();
-}
-
-// Solve (A + lambda*diag(A)) x = b for the symmetric 8x8 A packed as the upper triangle (row-major) by
-// Cholesky. Returns false if the matrix is not positive definite.
-__device__ bool solve8_damped(const double* packed, const double* b, double lambda, double* x) {
-  double L[8][8];
-  int p = 0;
-  double A[8][8];
-  for (int i = 0; i < 8; ++i)
-    for (int j = i; j < 8; ++j) { A[i][j] = packed[p]; A[j][i] = packed[p]; ++p; }
-  for (int i = 0; i < 8; ++i) A[i][i] *= (1.0 + lambda);
-  for (int j = 0; j < 8; ++j) {
-    double sum = A[j][j];
-    for (int k = 0; k < j; ++k) sum -= L[j][k] * L[j][k];
-    if (!(sum > 0.0)) return false;
-    const double ljj = sqrt(sum);
-    L[j][j] = ljj;
-    for (int i = j + 1; i < 8; ++i) {
-      double s2 = A[i][j];
-      for (int k = 0; k < j; ++k) s2 -= L[i][k] * L[j][k];
-      L[i][j] = s2 / ljj;
+      for (int i = 0; i < 9; ++i) best_H[pair * 9 + i] = H[i];
     }
   }
-  double y[8];
-  for (int i = 0; i < 8; ++i) {
-    double s2 = b[i];
-    for (int k = 0; k < i; ++k) s2 -= L[i][k] * y[k];
-    y[i] = s2 / L[i][i];
-  }
-  for (int i = 7; i >= 0; --i) {
-    double s2 = y[i];
-    for (int k = i + 1; k < 8; ++k) s2 -= L[k][i] * x[k];
-    x[i] = s2 / L[i][i];
-  }
-  return true;
 }
 
-__device__ __forceinline__ void accumulate_rows(double (&acc)[RF_NSUM], const double* r1, double b1, const double* r2,
-                                                double b2) {
-  int p = 0;
+// ---- refinement: findHomography's post-processing, one warp per pair ---------------------------------------------------
+constexpr int RF_WARPS = 4;
+
+template <int N>
+__device__ __forceinline__ void warp_sum(double (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+
+// Cholesky factor (lower, in place, row-major NxN) of a symmetric positive definite matrix.  A pivot that is not safely
+// positive marks a direction the data do not determine: its reciprocal is set to 0, which removes the direction from the
+// solve (what the eigenvalue threshold of cv::solve(DECOMP_EIG) does to it).  rdiag receives 1 / L[j][j].
+template <int N>
+__device__ __forceinline__ void cholesky(double (&A)[N * N], double (&rdiag)[N], double tiny) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double sum = A[j * N + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) sum -= A[j * N + k] * A[j * N + k];
+    const bool ok = sum > tiny;
+    const double ljj = ok ? sqrt(sum) : 1.0;
+    const double r = ok ? 1.0 / ljj : 0.0;
+    A[j * N + j] = ljj;
+    rdiag[j] = r;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double s2 = A[i * N + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s2 -= A[i * N + k] * A[j * N + k];
+      A[i * N + j] = s2 * r;
+    }
+  }
+}
+
+// x = (L L^T)^-1 b
+template <int N>
+__device__ __forceinline__ void cholesky_solve(const double (&L)[N * N], const double (&rdiag)[N], const double (&b)[N],
+                                               double (&x)[N]) {
+  double y[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s2 = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s2 -= L[i * N + k] * y[k];
+    y[i] = s2 * rdiag[i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s2 = y[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) s2 -= L[k * N + i] * x[k];
+    x[i] = s2 * rdiag[i];
+  }
+}
+
+// d = (A + lambda * diag(D))^-1 v for the symmetric 8x8 A, through the Cholesky factor of the diagonally scaled matrix.
+__device__ __noinline__ void lm_solve(const double* A /*64*/, const double* D, const double* v, double lambda, double* d) {
+  double C[64], sc[8], b[8], z[8], rd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double aii = A[9 * i] + lambda * D[i];
+    sc[i] = aii > 0.0 ? rsqrt(aii) : 1.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const double a = A[8 * i + j] + (i == j ? lambda * D[i] : 0.0);
+      C[8 * i + j] = a * sc[i] * sc[j];
+    }
+    b[i] = v[i] * sc[i];
+  }
+  cholesky<8>(C, rd, 1e-14);
+  cholesky_solve<8>(C, rd, b, z);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = z[i] * sc[i];
+}
+
+// largest |diagonal entry| of A^-1 (LMSolver re-seeds lambda with its reciprocal)
+__device__ __noinline__ double lm_inverse_max_diag(const double* A /*64*/) {
+  double C[64], sc[8], rd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sc[i] = A[9 * i] > 0.0 ? rsqrt(A[9 * i]) : 1.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = i; j < 8; ++j) { acc[p] += r1[i] * r1[j] + r2[i] * r2[j]; ++p; }
+    for (int j = 0; j <= i; ++j) C[8 * i + j] = A[8 * i + j] * sc[i] * sc[j];
+  cholesky<8>(C, rd, 1e-14);
+  double maxval = DBL_EPSILON;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[36 + i] += r1[i] * b1 + r2[i] * b2;
+  for (int j = 0; j < 8; ++j) {
+    // column j of L^-1 by forward substitution; (C^-1)[j][j] = sum_i (L^-1)[i][j]^2
+    double col[8];
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < j) { col[i] = 0.0; continue; }
+      double s2 = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = j; k < i; ++k) s2 -= C[8 * i + k] * col[k];
+      col[i] = s2 * rd[i];
+      acc += col[i] * col[i];
+    }
+    maxval = fmax(maxval, fabs(acc * sc[j] * sc[j]));
+  }
+  return maxval;
 }
 
-// grid.x = pairs.
-__global__ void __launch_bounds__(RF_THREADS)
-ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ dst,
-                       const int64_t* __restrict__ pair_offsets, float thresh, uint64_t seed, int64_t pair0, int refine,
-                       const int32_t* __restrict__ best_hyp, double* __restrict__ Hout, uint8_t* __restrict__ mask,
-                       int32_t* __restrict__ ninl) {
-  __shared__ double sh_H[9];
-  __shared__ float sh_Hf[9];
-  __shared__ int sh_ok;
-  __shared__ double scratch[(RF_THREADS / 32) * RF_NSUM];
-  __shared__ double sums[RF_NSUM];
-  __shared__ double sh_h[8], sh_trial[8];
-  __shared__ int sh_flag;
-  __shared__ double sh_c1[1];
-  const int64_t pair = blockIdx.x;
+// Eigenvector of the smallest eigenvalue of the symmetric positive semi-definite 9x9 matrix M (what cv::eigen hands
+// runKernel as V[8]): inverse iteration on the Cholesky factor of M + mu I.
+__device__ __noinline__ void smallest_eigenvector9(const double* M /*81, lower triangle used*/, double* vec) {
+  double C[81], rd[9], x[9], y[9];
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) tr += M[10 * i];
+  const double mu = 1e-12 * tr;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) C[9 * i + j] = M[9 * i + j] + (i == j ? mu : 0.0);
+  cholesky<9>(C, rd, 0.0);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) x[i] = 1.0 - 0.07 * i;
+  for (int it = 0; it < 64; ++it) {
+    cholesky_solve<9>(C, rd, x, y);
+    double nn = 0.0, big = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { nn += y[i] * y[i]; if (fabs(y[i]) > fabs(big)) big = y[i]; }
+    const double inv = (big < 0.0 ? -1.0 : 1.0) / sqrt(nn);
+    double change = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double t = y[i] * inv;
+      change = fmax(change, fabs(t - x[i]));
+      x[i] = t;
+    }
+    if (!(change > 4e-16)) break;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) vec[i] = x[i];
+}
+
+// grid.x = ceil(npairs / RF_WARPS); warp = pair.  Every lane holds the same reduced sums and walks the (uniform) solver code.
+template <bool CV>
+__global__ void __launch_bounds__(RF_WARPS * 32)
+ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ dst, const int64_t* __restrict__ pair_offsets,
+                       int64_t npairs, float thresh, int refine, const int32_t* __restrict__ best_hyp,
+                       const double* __restrict__ best_H, int32_t* __restrict__ sel_ws, double* __restrict__ Hout,
+                       uint8_t* __restrict__ mask, int32_t* __restrict__ ninl) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * RF_WARPS + (threadIdx.x >> 5);
+  if (pair >= npairs) return;
   const int64_t m0 = pair_offsets[pair];
-  const int64_t K = pair_offsets[pair + 1] - m0;
+  const int K = (int)(pair_offsets[pair + 1] - m0);
   const float2* s = reinterpret_cast<const float2*>(src) + m0;
   const float2* d = reinterpret_cast<const float2*>(dst) + m0;
   uint8_t* mk = mask + m0;
-  const int tid = threadIdx.x;
-  const int bh = best_hyp[pair];
+  int32_t* sel = sel_ws + m0;
   const float thr2 = __fmul_rn(thresh, thresh);
-
-  if (tid == 0) {
-    double H[9];
-    bool ok = bh >= 0 && hypothesis_model(src + m0 * 2, dst + m0 * 2, (uint32_t)K, seed, (uint64_t)(pair + pair0), (uint64_t)bh, H);
-    sh_ok = ok ? 1 : 0;
-    for (int i = 0; i < 9; ++i) { sh_H[i] = ok ? H[i] : 0.0; sh_Hf[i] = ok ? (float)H[i] : 0.f; }
-  }
-  __syncthreads();
-  if (!sh_ok) {
-    for (int64_t i = tid; i < K; i += RF_THREADS) mk[i] = 0;
-    if (tid < 9) Hout[pair * 9 + tid] = nan("");
-    if (tid == 0) ninl[pair] = 0;
+  const int bh = best_hyp[pair];
+  if (bh < 0) {
+    for (int i = lane; i < K; i += 32) mk[i] = 0;
+    if (lane < 9) Hout[pair * 9 + lane] = nan("");
+    if (lane == 0) ninl[pair] = 0;
     return;
   }
+  double Hm[9];
   float hf[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) hf[i] = sh_Hf[i];
+  for (int i = 0; i < 9; ++i) { Hm[i] = best_H[pair * 9 + i]; hf[i] = (float)Hm[i]; }
 
-  // inlier mask of the winning minimal model (what cv2 returns as `mask`) + normalisation statistics
-  double st[9];
+  // inliers of the winning minimal model, compacted in increasing order
+  int n = 0;
+  for (int base = 0; base < K; base += 32) {
+    const int i = base + lane;
+    bool in = false;
+    if (i < K) {
+      const float2 a = s[i], b = d[i];
+      in = CV ? cv_is_inlier(hf, a.x, a.y, b.x, b.y, thr2) : fast_is_inlier(hf, a.x, a.y, b.x, b.y, thr2);
+      mk[i] = in ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if (in) sel[n + __popc(bal & ((1u << lane) - 1u))] = i;
+    n += __popc(bal);
+  }
+  __syncwarp();
+  bool refined = false;
+  double H[9];
+  if (refine && n >= 4) {
+    // ---- runKernel: normalised DLT (M = src, m = dst) ----
+    double c4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = lane; i < n; i += 32) {
+      const int r = sel[i];
+      const float2 a = s[r], b = d[r];
+      c4[0] += b.x; c4[1] += b.y; c4[2] += a.x; c4[3] += a.y;
+    }
+    warp_sum<4>(c4);
+    const double cmx = c4[0] / n, cmy = c4[1] / n, cMx = c4[2] / n, cMy = c4[3] / n;
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = lane; i < n; i += 32) {
+      const int r = sel[i];
+      const float2 a = s[r], b = d[r];
+      s4[0] += fabs(b.x - cmx); s4[1] += fabs(b.y - cmy); s4[2] += fabs(a.x - cMx); s4[3] += fabs(a.y - cMy);
+    }
+    warp_sum<4>(s4);
+    if (!(fabs(s4[0]) < DBL_EPSILON || fabs(s4[1]) < DBL_EPSILON || fabs(s4[2]) < DBL_EPSILON || fabs(s4[3]) < DBL_EPSILON)) {
+      const double smx = n / s4[0], smy = n / s4[1], sMx = n / s4[2], sMy = n / s4[3];
+      // LtL = [[PP, 0, -xPP], [0, PP, -yPP], [-xPP, -yPP, rPP]] with p = (X, Y, 1), r = x^2 + y^2
+      double q[24];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) st[i] = 0.0;
-  for (int64_t i = tid; i < K; i += RF_THREADS) {
-    const float2 a = s[i], b = d[i];
-    const bool in = is_inlier(hf, a.x, a.y, b.x, b.y, thr2);
-    mk[i] = in ? 1 : 0;
-    if (in) {
-      st[0] += 1.0;
-      st[1] += a.x; st[2] += a.y; st[3] += (double)a.x * a.x + (double)a.y * a.y;
-      st[4] += b.x; st[5] += b.y; st[6] += (double)b.x * b.x + (double)b.y * b.y;
+      for (int i = 0; i < 24; ++i) q[i] = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const int r = sel[i];
+        const float2 a = s[r], b = d[r];
+        const double x = (b.x - cmx) * smx, y = (b.y - cmy) * smy;
+        const double X = (a.x - cMx) * sMx, Y = (a.y - cMy) * sMy;
+        const double pp[6] = {X * X, X * Y, X, Y * Y, Y, 1.0};
+        const double rr = x * x + y * y;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { q[k] += pp[k]; q[6 + k] += x * pp[k]; q[12 + k] += y * pp[k]; q[18 + k] += rr * pp[k]; }
+      }
+      warp_sum<24>(q);
+      double L[81];
+      // symmetric 3x3 block from its 6 unique sums (XX XY X YY Y 1)
+      const int blk[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+#pragma unroll
+      for (int i = 0; i < 81; ++i) L[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int u = blk[3 * i + j];
+          L[9 * i + j] = q[u]; L[9 * (3 + i) + (3 + j)] = q[u];
+          L[9 * (6 + i) + j] = -q[6 + u]; L[9 * i + (6 + j)] = -q[6 + u];
+          L[9 * (6 + i) + (3 + j)] = -q[12 + u]; L[9 * (3 + i) + (6 + j)] = -q[12 + u];
+          L[9 * (6 + i) + (6 + j)] = q[18 + u];
+        }
+      double H0[9];
+      smallest_eigenvector9(L, H0);
+      // H = invHnorm * H0 * Hnorm2, invHnorm = [[1/smx,0,cmx],[0,1/smy,cmy],[0,0,1]], Hnorm2 = [[sMx,0,-cMx sMx],[0,sMy,-cMy sMy],[0,0,1]]
+      double T[9], R[9];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T[j] = H0[j] / smx + cmx * H0[6 + j];
+        T[3 + j] = H0[3 + j] / smy + cmy * H0[6 + j];
+        T[6 + j] = H0[6 + j];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        R[3 * i] = T[3 * i] * sMx;
+        R[3 * i + 1] = T[3 * i + 1] * sMy;
+        R[3 * i + 2] = T[3 * i + 2] - T[3 * i] * (cMx * sMx) - T[3 * i + 1] * (cMy * sMy);
+      }
+      double x8[8];
+      const double sc0 = 1.0 / R[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x8[i] = R[i] * sc0;
+
+      // ---- LMSolver(10 iterations, eps = FLT_EPSILON) on HomographyRefineCallback ----
+      // One pass over the inliers at parameters h: S = sum of squared residuals, max |residual|, and the unique sums of
+      // J^T J and J^T r:  acc[0..5] pp^T, [6..11] -xi p_a p_b, [12..17] -yi p_a p_b, [18..20] (xi^2+yi^2) p_a p_b (a,b<2),
+      // [21..28] J^T r, [29] S.
+      double A[64], v[8], D[8], S = 0.0, rinf = 0.0;
+      auto lm_pass = [&](const double* h, double* Ao, double* vo, double& So, double& rinfo) {
+        double acc[30];
+#pragma unroll
+        for (int i = 0; i < 30; ++i) acc[i] = 0.0;
+        double rmax = 0.0;
+        for (int i = lane; i < n; i += 32) {
+          const int r = sel[i];
+          const float2 a = s[r], b = d[r];
+          const double Mx = a.x, My = a.y;
+          double ww = h[6] * Mx + h[7] * My + 1.0;
+          ww = fabs(ww) > DBL_EPSILON ? 1.0 / ww : 0.0;
+          const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+          const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+          const double e0 = xi - b.x, e1 = yi - b.y;
+          const double p0 = Mx * ww, p1 = My * ww, p2 = ww;
+          const double pp[6] = {p0 * p0, p0 * p1, p0 * p2, p1 * p1, p1 * p2, p2 * p2};
+          const double pq[6] = {p0 * p0, p0 * p1, p1 * p0, p1 * p1, p2 * p0, p2 * p1};  // p_a p_b, a = 0..2, b = 0..1
+          const double rr = xi * xi + yi * yi;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { acc[k] += pp[k]; acc[6 + k] -= xi * pq[k]; acc[12 + k] -= yi * pq[k]; }
+          acc[18] += rr * pq[0]; acc[19] += rr * pq[1]; acc[20] += rr * pq[3];
+          acc[21] += p0 * e0; acc[22] += p1 * e0; acc[23] += p2 * e0;
+          acc[24] += p0 * e1; acc[25] += p1 * e1; acc[26] += p2 * e1;
+          const double g = xi * e0 + yi * e1;
+          acc[27] -= p0 * g; acc[28] -= p1 * g;
+          acc[29] += e0 * e0 + e1 * e1;
+          rmax = fmax(rmax, fmax(fabs(e0), fabs(e1)));
+        }
+        warp_sum<30>(acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+#pragma unroll
+        for (int i = 0; i < 64; ++i) Ao[i] = 0.0;
+        const int blk2[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { Ao[8 * i + j] = acc[blk2[3 * i + j]]; Ao[8 * (3 + i) + (3 + j)] = acc[blk2[3 * i + j]]; }
+        // pq index: (a, b) -> 0:(0,0) 1:(0,1) 2:(1,0) 3:(1,1) 4:(2,0) 5:(2,1)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            Ao[8 * a + (6 + b)] = acc[6 + 2 * a + b]; Ao[8 * (6 + b) + a] = acc[6 + 2 * a + b];
+            Ao[8 * (3 + a) + (6 + b)] = acc[12 + 2 * a + b]; Ao[8 * (6 + b) + (3 + a)] = acc[12 + 2 * a + b];
+          }
+        Ao[8 * 6 + 6] = acc[18]; Ao[8 * 6 + 7] = acc[19]; Ao[8 * 7 + 6] = acc[19]; Ao[8 * 7 + 7] = acc[20];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vo[i] = acc[21 + i];
+        So = acc[29];
+        rinfo = rmax;
+      };
+      lm_pass(x8, A, v, S, rinf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) D[i] = A[9 * i];
+      double lambda = 1.0, lc = 0.75;
+      for (int iter = 0;;) {
+        double dd[8], xd[8], Ad[64], vd[8], Sd, rinfd;
+        lm_solve(A, D, v, lambda, dd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xd[i] = x8[i] - dd[i];
+        lm_pass(xd, Ad, vd, Sd, rinfd);
+        double dS = 0.0, dinf = 0.0, tdv = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t += A[8 * i + j] * dd[j];
+          dS += dd[i] * (-t + 2.0 * v[i]);
+          tdv += dd[i] * v[i];
+          dinf = fmax(dinf, fabs(dd[i]));
+        }
+        const double Rr = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.0);
+        if (Rr > 0.75) {
+          lambda *= 0.5;
+          if (lambda < lc) lambda = 0.0;
+        } else if (Rr < 0.25) {
+          double nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1.0) + 2.0;
+          nu = fmin(fmax(nu, 2.0), 10.0);
+          if (lambda == 0.0) {
+            lambda = lc = 1.0 / lm_inverse_max_diag(A);
+            nu *= 0.5;
+          }
+          lambda *= nu;
+        }
+        if (Sd < S) {
+          S = Sd; rinf = rinfd;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { x8[i] = xd[i]; v[i] = vd[i]; }
+#pragma unroll
+          for (int i = 0; i < 64; ++i) A[i] = Ad[i];
+        }
+        ++iter;
+        if (!(iter < 10 && dinf >= (double)FLT_EPSILON && rinf >= (double)FLT_EPSILON)) break;
+      }
+      bool fin = true;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { H[i] = x8[i]; fin = fin && (fabs(x8[i]) <= DBL_MAX); }
+      H[8] = 1.0;
+      refined = fin;
     }
   }
-  block_sum<9>(st, scratch, sums);
-  const double n_in = sums[0];
-  if (tid == 0) ninl[pair] = (int)n_in;
-  if (!refine || n_in < 4.5) {
-    // with exactly 4 inliers the minimal model is already the least-squares optimum
-    if (tid < 9) Hout[pair * 9 + tid] = sh_H[tid];
+  if (!refined) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = Hm[i];
+  }
+  if (lane < 9) {
+    double hv = H[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) hv = lane == i ? H[i] : hv;
+    Hout[pair * 9 + lane] = hv;
+  }
+  if (!refined) {
+    if (lane == 0) ninl[pair] = n;
     return;
   }
-  // isotropic Hartley normalisation of both point sets (RMS distance sqrt(2))
-  const double csx = sums[1] / n_in, csy = sums[2] / n_in, cdx = sums[4] / n_in, cdy = sums[5] / n_in;
-  const double vs = fmax(sums[3] / n_in - (csx * csx + csy * csy), 1e-300);
-  const double vd = fmax(sums[6] / n_in - (cdx * cdx + cdy * cdy), 1e-300);
-  const double ss = sqrt(2.0 / vs), sd = sqrt(2.0 / vd);
-
-  // (1) linear least squares in the normalised frame with h8 = 1
-  double acc[RF_NSUM];
+  // OpenCV returns the inliers of the REFINED homography under computeError
 #pragma unroll
-  for (int i = 0; i < RF_NSUM; ++i) acc[i] = 0.0;
-  for (int64_t i = tid; i < K; i += RF_THREADS) {
-    if (!mk[i]) continue;
+  for (int i = 0; i < 9; ++i) hf[i] = (float)H[i];
+  int cnt = 0;
+  for (int i = lane; i < K; i += 32) {
     const float2 a = s[i], b = d[i];
-    const double x = ((double)a.x - csx) * ss, y = ((double)a.y - csy) * ss;
-    const double u = ((double)b.x - cdx) * sd, v = ((double)b.y - cdy) * sd;
-    const double r1[8] = {x, y, 1.0, 0.0, 0.0, 0.0, -x * u, -y * u};
-    const double r2[8] = {0.0, 0.0, 0.0, x, y, 1.0, -x * v, -y * v};
-    accumulate_rows(acc, r1, u, r2, v);
-  }
-  block_sum<RF_NSUM>(acc, scratch, sums);
-  if (tid == 0) {
-    double x[8];
-    bool ok = solve8_damped(sums, sums + 36, 0.0, x);
-    if (!ok) {
-      // fall back to the minimal model expressed in the normalised frame: Hn = Td * H * Ts^-1
-      const double* H = sh_H;
-      double G[9];
-      // Td * H : rows scaled/shifted
-      for (int j = 0; j < 3; ++j) {
-        G[j] = sd * (H[j] - cdx * H[6 + j]);
-        G[3 + j] = sd * (H[3 + j] - cdy * H[6 + j]);
-        G[6 + j] = H[6 + j];
-      }
-      // * Ts^-1 : Ts^-1 = [[1/ss,0,csx],[0,1/ss,csy],[0,0,1]]
-      double R[9];
-      for (int i = 0; i < 3; ++i) {
-        R[3 * i] = G[3 * i] / ss; R[3 * i + 1] = G[3 * i + 1] / ss;
-        R[3 * i + 2] = G[3 * i] * csx + G[3 * i + 1] * csy + G[3 * i + 2];
-      }
-      for (int i = 0; i < 8; ++i) x[i] = R[i] / R[8];
-    }
-    for (int i = 0; i < 8; ++i) sh_h[i] = x[i];
-  }
-  __syncthreads();
-
-  // (2) Levenberg-Marquardt on the reprojection error in the normalised destination frame
-  double lambda = 1e-3;
-  double cost = -1.0;
-  for (int iter = 0; iter < 30; ++iter) {
-    double h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = sh_h[i];
-#pragma unroll
-    for (int i = 0; i < RF_NSUM; ++i) acc[i] = 0.0;
-    for (int64_t i = tid; i < K; i += RF_THREADS) {
-      if (!mk[i]) continue;
-      const float2 a = s[i], b = d[i];
-      const double x = ((double)a.x - csx) * ss, y = ((double)a.y - csy) * ss;
-      const double u = ((double)b.x - cdx) * sd, v = ((double)b.y - cdy) * sd;
-      const double w = h[6] * x + h[7] * y + 1.0;
-      const double iw = fabs(w) > DBL_EPSILON ? 1.0 / w : 0.0;
-      const double pu = (h[0] * x + h[1] * y + h[2]) * iw;
-      const double pv = (h[3] * x + h[4] * y + h[5]) * iw;
-      const double ru = pu - u, rv = pv - v;
-      const double r1[8] = {x * iw, y * iw, iw, 0.0, 0.0, 0.0, -x * iw * pu, -y * iw * pu};
-      const double r2[8] = {0.0, 0.0, 0.0, x * iw, y * iw, iw, -x * iw * pv, -y * iw * pv};
-      accumulate_rows(acc, r1, -ru, r2, -rv);
-      acc[44] += ru * ru + rv * rv;
-    }
-    block_sum<RF_NSUM>(acc, scratch, sums);
-    cost = sums[44];
-    // inner loop: damped solves until the cost goes down
-    bool improved = false;
-    for (int attempt = 0; attempt < 12 && !improved; ++attempt) {
-      if (tid == 0) {
-        double dx[8];
-        const bool ok = solve8_damped(sums, sums + 36, lambda, dx);
-        sh_flag = ok ? 1 : 0;
-        for (int i = 0; i < 8; ++i) sh_trial[i] = sh_h[i] + (ok ? dx[i] : 0.0);
-      }
-      __syncthreads();
-      const bool ok = sh_flag != 0;
-      double ht[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ht[i] = sh_trial[i];
-      double c1[1] = {0.0};
-      if (ok) {
-        for (int64_t i = tid; i < K; i += RF_THREADS) {
-          if (!mk[i]) continue;
-          const float2 a = s[i], b = d[i];
-          const double x = ((double)a.x - csx) * ss, y = ((double)a.y - csy) * ss;
-          const double u = ((double)b.x - cdx) * sd, v = ((double)b.y - cdy) * sd;
-          const double w = ht[6] * x + ht[7] * y + 1.0;
-          const double iw = fabs(w) > DBL_EPSILON ? 1.0 / w : 0.0;
-          const double ru = (ht[0] * x + ht[1] * y + ht[2]) * iw - u;
-          const double rv = (ht[3] * x + ht[4] * y + ht[5]) * iw - v;
-          c1[0] += ru * ru + rv * rv;
-        }
-      }
-      block_sum<1>(c1, scratch, sh_c1);
-      if (ok && sh_c1[0] <= cost) {
-        improved = true;
-        lambda = fmax(lambda * 0.1, 1e-15);
-      } else {
-        lambda *= 10.0;
-      }
-      __syncthreads();
-    }
-    if (!improved) break;
-    // accept the step; stop when it no longer moves the parameters
-    double step = 0.0, scale = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      step = fmax(step, fabs(sh_trial[i] - sh_h[i]));
-      scale = fmax(scale, fabs(sh_h[i]));
-    }
-    __syncthreads();
-    if (tid < 8) sh_h[tid] = sh_trial[tid];
-    __syncthreads();
-    if (step <= 1e-13 * (1.0 + scale)) break;
-  }
-
-  // denormalise: H = Td^-1 * Hn * Ts, then H /= H[8]
-  if (tid == 0) {
-    double Hn[9];
-    for (int i = 0; i < 8; ++i) Hn[i] = sh_h[i];
-    Hn[8] = 1.0;
-    double G[9];  // Hn * Ts, Ts = [[ss,0,-ss*csx],[0,ss,-ss*csy],[0,0,1]]
-    for (int i = 0; i < 3; ++i) {
-      G[3 * i] = Hn[3 * i] * ss; G[3 * i + 1] = Hn[3 * i + 1] * ss;
-      G[3 * i + 2] = Hn[3 * i + 2] - ss * (Hn[3 * i] * csx + Hn[3 * i + 1] * csy);
-    }
-    double R[9];  // Td^-1 = [[1/sd,0,cdx],[0,1/sd,cdy],[0,0,1]]
-    for (int j = 0; j < 3; ++j) {
-      R[j] = G[j] / sd + cdx * G[6 + j];
-      R[3 + j] = G[3 + j] / sd + cdy * G[6 + j];
-      R[6 + j] = G[6 + j];
-    }
-    for (int i = 0; i < 9; ++i) {
-      const double hv = R[i] / R[8];
-      Hout[pair * 9 + i] = hv;
-      sh_Hf[i] = (float)hv;
-    }
-  }
-  __syncthreads();
-  // OpenCV returns the inliers of the REFINED homography (float32 reprojection error with division, the
-  // formula of its computeError); mirrored op for op by final_mask() in oracle/ransac_oracle.c.
-#pragma unroll
-  for (int i = 0; i < 9; ++i) hf[i] = sh_Hf[i];
-  double cnt[1] = {0.0};
-  for (int64_t i = tid; i < K; i += RF_THREADS) {
-    const float2 a = s[i], b = d[i];
-    const float ww = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(hf[6], a.x), __fmul_rn(hf[7], a.y)), 1.f));
-    const float px = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hf[0], a.x), __fmul_rn(hf[1], a.y)), hf[2]), ww);
-    const float py = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hf[3], a.x), __fmul_rn(hf[4], a.y)), hf[5]), ww);
-    const float dx = __fsub_rn(px, b.x), dy = __fsub_rn(py, b.y);
-    const bool in = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= thr2;
+    const bool in = cv_is_inlier(hf, a.x, a.y, b.x, b.y, thr2);
     mk[i] = in ? 1 : 0;
-    cnt[0] += in ? 1.0 : 0.0;
+    cnt += in ? 1 : 0;
   }
-  block_sum<1>(cnt, scratch, sh_c1);
-  if (tid == 0) ninl[pair] = (int)sh_c1[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) ninl[pair] = cnt;
 }
 
 static size_t ransac_smem_bytes(int nhyp, int chunk) {
@@ -728,15 +928,53 @@ static int ransac_pick_chunk(int nhyp) {
   return (int)c;
 }
 
+struct RansacWs {
+  int32_t* best_hyp;
+  double* best_H;
+  int32_t* sel;
+  int4* samples;
+  size_t bytes;
+};
+
+static RansacWs ransac_ws_layout(void* ws, int64_t total, int64_t npairs, int nhyp, int sampler, bool full) {
+  char* p = reinterpret_cast<char*>(ws);
+  size_t off = 0;
+  RansacWs w{};
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes > 0 ? bytes : 1, 256); return r; };
+  if (full) {
+    w.best_hyp = reinterpret_cast<int32_t*>(take((size_t)npairs * sizeof(int32_t)));
+    w.best_H = reinterpret_cast<double*>(take((size_t)npairs * 9 * sizeof(double)));
+    w.sel = reinterpret_cast<int32_t*>(take((size_t)total * sizeof(int32_t)));
+  }
+  if (sampler == HPUSM_RANSAC_SAMPLER_CV2) w.samples = reinterpret_cast<int4*>(take((size_t)npairs * nhyp * sizeof(int4)));
+  w.bytes = off > 0 ? off : 256;
+  return w;
+}
+
+static int launch_sampler(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs, int nhyp,
+                          int4* samples, cudaStream_t st) {
+  const int threads = npairs >= 64 * 148 ? 64 : 32;
+  const unsigned grid = (unsigned)((npairs + threads - 1) / threads);
+  HPUSM_LAUNCH(ransac_sample_cv2_kernel, grid, threads, 0, st, src, dst, pair_offsets, npairs, nhyp, samples);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
 static int launch_score(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                        float thresh, int nhyp, double confidence, uint64_t seed, int64_t pair0, int32_t* counts,
-                        int32_t* best_hyp, int32_t* best_count, cudaStream_t st) {
+                        float thresh, int nhyp, double confidence, int sampler, uint64_t seed, int64_t pair0,
+                        const int4* samples, int32_t* counts, int32_t* best_hyp, double* best_H, cudaStream_t st) {
   const int chunk = ransac_pick_chunk(nhyp);
   HPUSM_REQUIRE(chunk > 0, HPUSM_ERR_UNSUPPORTED, "ransac: %d hypotheses do not fit in shared memory", nhyp);
   const size_t smem = ransac_smem_bytes(nhyp, chunk);
-  HPUSM_CUDA_OK(cudaFuncSetAttribute(ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  HPUSM_LAUNCH_TIMED(ransac_score_kernel, (unsigned)npairs, RS_THREADS, smem, st, src, dst, pair_offsets, thresh, nhyp,
-               confidence, seed, pair0, chunk, counts, best_hyp, best_count);
+  if (sampler == HPUSM_RANSAC_SAMPLER_CV2) {
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(ransac_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HPUSM_LAUNCH_TIMED(ransac_score_kernel<true>, (unsigned)npairs, RS_THREADS, smem, st, src, dst, pair_offsets, thresh, nhyp,
+                       confidence, seed, pair0, chunk, samples, counts, best_hyp, best_H);
+  } else {
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(ransac_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HPUSM_LAUNCH_TIMED(ransac_score_kernel<false>, (unsigned)npairs, RS_THREADS, smem, st, src, dst, pair_offsets, thresh, nhyp,
+                       confidence, seed, pair0, chunk, samples, counts, best_hyp, best_H);
+  }
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }
@@ -747,60 +985,75 @@ using namespace hpusm;
 
 extern "C" {
 
-size_t hpusm_ransac_homography_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp) {
-  (void)total_matches; (void)nhyp;
-  return align_up((size_t)(npairs > 0 ? npairs : 1) * sizeof(int32_t), 256) * 2;
+size_t hpusm_ransac_homography_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp, int sampler) {
+  if (total_matches < 0 || npairs < 0 || nhyp <= 0) return 256;
+  return ransac_ws_layout(nullptr, total_matches, npairs, nhyp, sampler, true).bytes;
 }
 
-int hpusm_ransac_score_batch_at(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                                int64_t total_matches, float thresh, int nhyp, uint64_t seed, int64_t pair_index0,
-                                int32_t* counts, void* stream) {
+size_t hpusm_ransac_score_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp, int sampler) {
+  if (total_matches < 0 || npairs < 0 || nhyp <= 0) return 256;
+  return ransac_ws_layout(nullptr, total_matches, npairs, nhyp, sampler, false).bytes;
+}
+
+int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
+                             int64_t total_matches, float thresh, int nhyp, int sampler, uint64_t seed, int64_t pair_index0,
+                             int32_t* counts, void* ws, size_t ws_bytes, void* stream) {
   HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0 && pair_index0 >= 0, HPUSM_ERR_INVALID,
                 "hpusm_ransac_score_batch: bad sizes");
+  HPUSM_REQUIRE(sampler == HPUSM_RANSAC_SAMPLER_COUNTER || sampler == HPUSM_RANSAC_SAMPLER_CV2, HPUSM_ERR_INVALID,
+                "hpusm_ransac_score_batch: unknown sampler %d", sampler);
   if (npairs == 0) return HPUSM_OK;
   HPUSM_REQUIRE(pair_offsets && counts && ((src && dst) || total_matches == 0), HPUSM_ERR_INVALID,
                 "hpusm_ransac_score_batch: null pointer");
   HPUSM_REQUIRE(npairs < 0x40000000, HPUSM_ERR_UNSUPPORTED, "hpusm_ransac_score_batch: too many pairs for one call");
-  return launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, 0.0, seed, pair_index0, counts, nullptr, nullptr,
-                      as_stream(stream));
-}
-
-int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                             int64_t total_matches, float thresh, int nhyp, uint64_t seed, int32_t* counts,
-                             void* stream) {
-  return hpusm_ransac_score_batch_at(src, dst, pair_offsets, npairs, total_matches, thresh, nhyp, seed, 0, counts, stream);
-}
-
-int hpusm_ransac_homography_batch_at(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                                     int64_t total_matches, float thresh, int nhyp, double confidence, uint64_t seed,
-                                     int64_t pair_index0, int refine, double* H, uint8_t* mask, int32_t* ninl,
-                                     int32_t* best_hyp, void* ws, size_t ws_bytes, void* stream) {
-  HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0 && pair_index0 >= 0, HPUSM_ERR_INVALID,
-                "hpusm_ransac_homography_batch: bad sizes");
-  if (npairs == 0) return HPUSM_OK;
-  HPUSM_REQUIRE(pair_offsets && H && ninl && (mask || total_matches == 0) && ((src && dst) || total_matches == 0),
-                HPUSM_ERR_INVALID, "hpusm_ransac_homography_batch: null pointer");
-  HPUSM_REQUIRE(npairs < 0x40000000, HPUSM_ERR_UNSUPPORTED, "hpusm_ransac_homography_batch: too many pairs");
-  const size_t part = align_up((size_t)npairs * sizeof(int32_t), 256);
-  HPUSM_REQUIRE(ws && is_aligned(ws, 256) && ws_bytes >= 2 * part, HPUSM_ERR_WORKSPACE,
-                "hpusm_ransac_homography_batch: workspace needs %zu bytes, got %zu", 2 * part, ws_bytes);
   cudaStream_t st = as_stream(stream);
-  int32_t* bh = best_hyp ? best_hyp : reinterpret_cast<int32_t*>(ws);
-  int32_t* bc = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + part);
-  int rc = launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, confidence, seed, pair_index0, nullptr, bh, bc, st);
-  if (rc != HPUSM_OK) return rc;
-  HPUSM_LAUNCH(ransac_finalize_kernel, (unsigned)npairs, RF_THREADS, 0, st, src, dst, pair_offsets, thresh, seed,
-               pair_index0, refine, bh, H, mask, ninl);
-  HPUSM_CHECK_LAUNCH();
-  return HPUSM_OK;
+  RansacWs w{};
+  if (sampler == HPUSM_RANSAC_SAMPLER_CV2) {
+    w = ransac_ws_layout(ws, total_matches, npairs, nhyp, sampler, false);
+    HPUSM_REQUIRE(ws && is_aligned(ws, 256) && ws_bytes >= w.bytes, HPUSM_ERR_WORKSPACE,
+                  "hpusm_ransac_score_batch: workspace needs %zu bytes, got %zu", w.bytes, ws_bytes);
+    const int rc = launch_sampler(src, dst, pair_offsets, npairs, nhyp, w.samples, st);
+    if (rc != HPUSM_OK) return rc;
+  }
+  return launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, 0.0, sampler, seed, pair_index0, w.samples, counts, nullptr,
+                      nullptr, st);
 }
 
 int hpusm_ransac_homography_batch(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs,
-                                  int64_t total_matches, float thresh, int nhyp, double confidence, uint64_t seed,
-                                  int refine, double* H, uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
-                                  size_t ws_bytes, void* stream) {
-  return hpusm_ransac_homography_batch_at(src, dst, pair_offsets, npairs, total_matches, thresh, nhyp, confidence, seed, 0,
-                                          refine, H, mask, ninl, best_hyp, ws, ws_bytes, stream);
+                                  int64_t total_matches, float thresh, int nhyp, double confidence, int sampler,
+                                  uint64_t seed, int64_t pair_index0, int refine, double* H, uint8_t* mask, int32_t* ninl,
+                                  int32_t* best_hyp, void* ws, size_t ws_bytes, void* stream) {
+  HPUSM_REQUIRE(npairs >= 0 && total_matches >= 0 && nhyp > 0 && pair_index0 >= 0, HPUSM_ERR_INVALID,
+                "hpusm_ransac_homography_batch: bad sizes");
+  HPUSM_REQUIRE(sampler == HPUSM_RANSAC_SAMPLER_COUNTER || sampler == HPUSM_RANSAC_SAMPLER_CV2, HPUSM_ERR_INVALID,
+                "hpusm_ransac_homography_batch: unknown sampler %d", sampler);
+  if (npairs == 0) return HPUSM_OK;
+  HPUSM_REQUIRE(pair_offsets && H && ninl && (mask || total_matches == 0) && ((src && dst) || total_matches == 0),
+                HPUSM_ERR_INVALID, "hpusm_ransac_homography_batch: null pointer");
+  HPUSM_REQUIRE(npairs < 0x40000000 && total_matches < 0x7fffffff, HPUSM_ERR_UNSUPPORTED,
+                "hpusm_ransac_homography_batch: too many pairs / matches for one call");
+  const RansacWs w = ransac_ws_layout(ws, total_matches, npairs, nhyp, sampler, true);
+  HPUSM_REQUIRE(ws && is_aligned(ws, 256) && ws_bytes >= w.bytes, HPUSM_ERR_WORKSPACE,
+                "hpusm_ransac_homography_batch: workspace needs %zu bytes, got %zu", w.bytes, ws_bytes);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (sampler == HPUSM_RANSAC_SAMPLER_CV2) {
+    rc = launch_sampler(src, dst, pair_offsets, npairs, nhyp, w.samples, st);
+    if (rc != HPUSM_OK) return rc;
+  }
+  rc = launch_score(src, dst, pair_offsets, npairs, thresh, nhyp, confidence, sampler, seed, pair_index0, w.samples, nullptr,
+                    w.best_hyp, w.best_H, st);
+  if (rc != HPUSM_OK) return rc;
+  const unsigned grid = (unsigned)((npairs + RF_WARPS - 1) / RF_WARPS);
+  if (sampler == HPUSM_RANSAC_SAMPLER_CV2)
+    HPUSM_LAUNCH(ransac_finalize_kernel<true>, grid, RF_WARPS * 32, 0, st, src, dst, pair_offsets, npairs, thresh, refine,
+                 w.best_hyp, w.best_H, w.sel, H, mask, ninl);
+  else
+    HPUSM_LAUNCH(ransac_finalize_kernel<false>, grid, RF_WARPS * 32, 0, st, src, dst, pair_offsets, npairs, thresh, refine,
+                 w.best_hyp, w.best_H, w.sel, H, mask, ninl);
+  HPUSM_CHECK_LAUNCH();
+  if (best_hyp) HPUSM_CUDA_OK(cudaMemcpyAsync(best_hyp, w.best_hyp, (size_t)npairs * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return HPUSM_OK;
 }
 
 }  // extern "C"

@@ -19,6 +19,22 @@ class DMatch(object):
         self.queryIdx, self.trainIdx, self.imgIdx, self.distance = int(queryIdx), int(trainIdx), 0, float(distance)
 
 
+def _pad_binary(desc):
+    """Binary descriptors zero-padded to the kernel's row widths (32 or 64 bytes): AKAZE's default MLDB descriptor is
+    61 bytes wide.  Zero bytes on both sides leave every Hamming distance unchanged."""
+    desc = np.ascontiguousarray(desc, dtype=np.uint8)
+    if desc.ndim != 2:
+        raise ValueError("knnMatch: descriptors must be a 2-D uint8 array")
+    w = desc.shape[1]
+    if w in (32, 64):
+        return desc
+    if w > 64:
+        raise ValueError("knnMatch: binary descriptors wider than 64 bytes are not supported (got %d)" % w)
+    out = np.zeros((desc.shape[0], 32 if w < 32 else 64), np.uint8)
+    out[:, :w] = desc
+    return out
+
+
 class BFMatcher(object):
     """Duck-type of cv2.BFMatcher(norm) (crossCheck off) as features.match_and_draw uses it."""
 
@@ -28,7 +44,8 @@ class BFMatcher(object):
 
     def knn2(self, queryDescriptors, trainDescriptors):
         if self.normType == NORM_HAMMING:
-            idx, dist = engine.knn2_hamming(up(queryDescriptors, np.uint8), up(trainDescriptors, np.uint8))
+            q, t = _pad_binary(queryDescriptors), _pad_binary(trainDescriptors)
+            idx, dist = engine.knn2_hamming(up(q, np.uint8), up(t, np.uint8))
         else:
             idx, dist = engine.knn2_l2(up(queryDescriptors, np.float32), up(trainDescriptors, np.float32))
         self.last = (idx, dist)
@@ -48,8 +65,12 @@ class BFMatcher(object):
 
 
 def init_feature(name):
-    """(detector, matcher) as features.py:10-43.  Detection stays with OpenCV (out of the path's scope); the
-    brute-force matcher is ours.  FLANN variants are not part of the replaced path."""
+    """(detector, matcher) as features.py:10-43.  Detection stays with OpenCV (out of the path's scope); the matcher
+    is ours.  The '-flann' names (every driver script of the reference passes 'orb-flann': urbanscene/main.py:15,
+    jochen_deel.py:14, dataset/dataset_urbanscene.py:11) get the same exact brute-force GPU matcher: FLANN's KD-tree / LSH
+    index only approximates the k=2 neighbours that this matcher returns exactly, and match_and_draw consumes both through
+    the same knnMatch contract.  Set HPUSM_FLANN=cv2 to get the reference's own cv2.FlannBasedMatcher instead."""
+    import os
     import cv2
     chunks = name.split('-')
     if chunks[0] == 'sift':
@@ -71,7 +92,14 @@ def init_feature(name):
     else:
         return None, None
     if 'flann' in chunks:
-        raise NotImplementedError("FLANN matchers are outside the replaced path; use the brute-force names")
+        if os.environ.get("HPUSM_FLANN", "").lower() == "cv2":  # the reference's approximate matcher, features.py:30-40
+            search_params = dict(checks=50)
+            if norm == NORM_L2:
+                flann_params = dict(algorithm=thresholds.FLANN_INDEX_KDTREE, trees=5)
+            else:
+                flann_params = dict(algorithm=thresholds.FLANN_INDEX_LSH, table_number=6, key_size=12, multi_probe_level=1)
+            return detector, cv2.FlannBasedMatcher(flann_params, search_params)
+        logging.info("init_feature(%r): FLANN requested, using the exact GPU brute-force matcher", name)
     return detector, BFMatcher(norm)
 
 
@@ -91,16 +119,36 @@ def filter_matches(kp1, kp2, matches, ratio=thresholds.FILTER_RATIO):
     return p1, p2, list(zip(mkp1, mkp2))
 
 
-def find_homography_ransac(src, dst, thresh=5.0, maxIters=2000, confidence=0.995, seed=0):
-    """cv2.findHomography(src, dst, cv2.RANSAC, thresh) -> (H float64 (3,3) or None, mask uint8 (K,1))."""
+def find_homography_ransac(src, dst, thresh=5.0, maxIters=2000, confidence=0.995, seed=0, sampler="cv2"):
+    """cv2.findHomography(src, dst, cv2.RANSAC, thresh) -> (H float64 (3,3) or None, mask uint8 (K,1)).
+
+    The default sampler replays OpenCV's own (fixed-seed) sample sequence on the GPU, so H and mask are the ones
+    cv2.findHomography returns; sampler="counter" draws from the seeded counter-based table instead."""
     src = np.float32(src).reshape(-1, 2)
     dst = np.float32(dst).reshape(-1, 2)
-    offs = torch.tensor([0, len(src)], dtype=torch.int64, device=up(src, np.float32).device)
-    H, mask, ninl, best = engine.ransac_homography_batch(up(src, np.float32), up(dst, np.float32), offs, thresh, maxIters,
-                                                         confidence, seed)
+    dsrc = up(src, np.float32)
+    offs = torch.tensor([0, len(src)], dtype=torch.int64, device=dsrc.device)
+    H, mask, ninl, best = engine.ransac_homography_batch(dsrc, up(dst, np.float32), offs, thresh, maxIters, confidence, seed,
+                                                         sampler=sampler)
     if int(down(best)[0]) < 0:
         return None, None
     return down(H)[0], down(mask).reshape(-1, 1)
+
+
+def find_homography_both_ways(p_a, p_b, thresh=5.0, maxIters=2000, confidence=0.995, seed=0, sampler="cv2"):
+    """The two calls of match_and_draw (features.py:66 and :69) as ONE batch of two pairs: (H, mask, H2, mask2)."""
+    a = np.float32(p_a).reshape(-1, 2)
+    b = np.float32(p_b).reshape(-1, 2)
+    k = len(a)
+    src = up(np.concatenate([a, b]), np.float32)
+    dst = up(np.concatenate([b, a]), np.float32)
+    offs = torch.tensor([0, k, 2 * k], dtype=torch.int64, device=src.device)
+    H, mask, ninl, best = engine.ransac_homography_batch(src, dst, offs, thresh, maxIters, confidence, seed, sampler=sampler)
+    best, H, mask = down(best), down(H), down(mask)
+    out = []
+    for p in range(2):
+        out += [None, None] if best[p] < 0 else [H[p], mask[p * k:(p + 1) * k].reshape(-1, 1)]
+    return tuple(out)
 
 
 def _kp_array(kps):
@@ -129,8 +177,7 @@ def match_and_draw(win, matcher, desc_model, desc_input, kp_model, kp_input, mod
         raw_matches = matcher.knnMatch(desc_model, trainDescriptors=desc_input, k=2)
         p_model, p_input, kp_pairs = filter_matches(kp_model, kp_input, raw_matches)
     if len(p_model) >= thresholds.MIN_MATCH_COUNT:
-        H, mask = find_homography_ransac(p_model, p_input, 5.0)
-        H2, mask2 = find_homography_ransac(p_input, p_model, 5.0)
+        H, mask, H2, mask2 = find_homography_both_ways(p_model, p_input, 5.0)
         if H is None or H2 is None:
             return (None, None, None, None, None, None)
         logging.debug('%d / %d  inliers/matched' % (np.sum(mask), len(mask)))

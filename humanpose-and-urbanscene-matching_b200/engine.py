@@ -216,43 +216,62 @@ def validate_homography_batch(H):
 
 
 # ---- K3: RANSAC ----------------------------------------------------------------------------------------
+SAMPLER_COUNTER = 0  # counter-based sample table keyed on (seed, pair, iteration, attempt): parallel draws
+SAMPLER_CV2 = 1      # OpenCV's own fixed-seed sample sequence: the result is cv2.findHomography's
+
+
+def _sampler(sampler):
+    if sampler in (SAMPLER_COUNTER, "counter"):
+        return SAMPLER_COUNTER
+    if sampler in (SAMPLER_CV2, "cv2"):
+        return SAMPLER_CV2
+    raise ValueError("sampler must be 'counter' or 'cv2', got %r" % (sampler,))
+
+
 def ransac_homography_batch(src, dst, pair_offsets, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, refine=True,
-                            pair_index0=0):
+                            pair_index0=0, sampler=SAMPLER_COUNTER):
     """cv2.findHomography(src, dst, RANSAC, thresh) per pair (features.py:66,:69).
 
-    Returns (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32, best_hyp [npairs] i32).  `pair_index0`: the
-    index of this call's first pair in the sample table (a slice of a larger batch draws the larger batch's samples)."""
+    Returns (H [npairs,3,3] f64, mask [total] u8, ninl [npairs] i32, best_hyp [npairs] i32).  `sampler`: 'cv2' replays
+    OpenCV's own sample sequence (mask and H are cv2.findHomography's), 'counter' draws from the seeded counter-based
+    table; `pair_index0`: the index of this call's first pair in that table (a slice of a larger batch draws the larger
+    batch's samples)."""
     src = _cuda(src, torch.float32, "src")
     dst = _cuda(dst, torch.float32, "dst")
     pair_offsets = _cuda(pair_offsets, torch.int64, "pair_offsets")
     total = src.shape[0]
     npairs = pair_offsets.numel() - 1
     dev = src.device
+    sampler = _sampler(sampler)
     with torch.cuda.device(dev):
         H = torch.empty((npairs, 3, 3), dtype=torch.float64, device=dev)
         mask = torch.empty((total,), dtype=torch.uint8, device=dev)
         ninl = torch.empty((npairs,), dtype=torch.int32, device=dev)
         best = torch.empty((npairs,), dtype=torch.int32, device=dev)
-        ws = _workspace(lib.hpusm_ransac_homography_workspace_bytes(total, npairs, nhyp), dev)
-        check(lib.hpusm_ransac_homography_batch_at(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
-                                                   int(nhyp), float(confidence), int(seed), int(pair_index0),
-                                                   1 if refine else 0, _ptr(H), _ptr(mask), _ptr(ninl), _ptr(best),
-                                                   _ptr(ws), ws.numel(), _stream(dev)))
+        ws = _workspace(lib.hpusm_ransac_homography_workspace_bytes(total, npairs, nhyp, sampler), dev)
+        check(lib.hpusm_ransac_homography_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
+                                                int(nhyp), float(confidence), sampler, int(seed), int(pair_index0),
+                                                1 if refine else 0, _ptr(H), _ptr(mask), _ptr(ninl), _ptr(best),
+                                                _ptr(ws), ws.numel(), _stream(dev)))
     return H, mask, ninl, best
 
 
-def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, out=None, pair_index0=0):
-    """Inlier count of every hypothesis of every pair: counts [npairs, nhyp] i32 (-1 = degenerate sample)."""
+def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, out=None, pair_index0=0,
+                       sampler=SAMPLER_COUNTER):
+    """Inlier count of every iteration's model of every pair: counts [npairs, nhyp] i32 (-1 = no acceptable sample)."""
     src = _cuda(src, torch.float32, "src")
     dst = _cuda(dst, torch.float32, "dst")
     pair_offsets = _cuda(pair_offsets, torch.int64, "pair_offsets")
     total = src.shape[0]
     npairs = pair_offsets.numel() - 1
     dev = src.device
+    sampler = _sampler(sampler)
     with torch.cuda.device(dev):
         counts = out if out is not None else torch.empty((npairs, nhyp), dtype=torch.int32, device=dev)
-        check(lib.hpusm_ransac_score_batch_at(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
-                                              int(nhyp), int(seed), int(pair_index0), _ptr(counts), _stream(dev)))
+        ws = _workspace(lib.hpusm_ransac_score_workspace_bytes(total, npairs, nhyp, sampler), dev)
+        check(lib.hpusm_ransac_score_batch(_ptr(src), _ptr(dst), _ptr(pair_offsets), npairs, total, float(thresh),
+                                           int(nhyp), sampler, int(seed), int(pair_index0), _ptr(counts), _ptr(ws),
+                                           ws.numel(), _stream(dev)))
     return counts
 
 

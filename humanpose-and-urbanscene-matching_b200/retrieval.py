@@ -57,11 +57,15 @@ def knn2_sharded(q, t_shard, row_offset, kind="l2", ratio=0.8, knn_fn=None, merg
     merge_fn = merge_fn or engine.knn2_merge
     ratio_fn = ratio_fn or engine.ratio_filter
     idx, d = knn_fn(q, t_shard)
-    gi, gd = allgather(globalize(idx, row_offset)), allgather(d)
-    if gi.shape[0] > 1:
-        idx, d = merge_fn(gi, gd)
-    else:
-        idx, d = gi[0], gd[0]
+    idx = globalize(idx, row_offset)
+    rank, n = world()
+    if n > 1:
+        # ONE all-gather: (idx, dist) packed as 4 x 32 bit per query (the distance travels as its bit pattern)
+        bits = torch.int32 if d.dtype in (torch.float32, torch.int32) else None
+        if bits is None:
+            raise TypeError("knn2_sharded: distances must be 32-bit, got %s" % d.dtype)
+        g = allgather(torch.cat([idx.to(torch.int32), d.contiguous().view(torch.int32)], dim=1))  # [n, nq, 4]
+        idx, d = merge_fn(g[:, :, :2].contiguous(), g[:, :, 2:].contiguous().view(d.dtype))
     keep, count = ratio_fn(idx, d, ratio)
     return idx, d, keep, count
 
@@ -84,8 +88,14 @@ class StreamedL2Matcher:
     until the next call.
     """
 
-    def __init__(self, nq, nt, d, device, q_chunk=None, t_first=1 << 17, t_chunk=1 << 20, mode=None):
+    def __init__(self, nq, nt, d, device, q_chunk=None, t_first=1 << 17, t_chunk=1 << 20, mode=None, query_slices=False):
         self.nq, self.nt, self.d, self.device = int(nq), int(nt), int(d), torch.device(device)
+        # query_slices: every rank is handed only ITS rows shard_range(nq, rank, world) of the (replicated) query array;
+        # the slices are exchanged by one all-gather over NVLink, so a query row crosses PCIe once per node, not once per rank
+        self.query_slices = bool(query_slices)
+        rank, nranks = world()
+        self.q_per = -(-self.nq // nranks) if self.query_slices else self.nq
+        self.q_lo, self.q_hi = shard_range(self.nq, rank, nranks) if self.query_slices else (0, self.nq)
         if q_chunk is None:
             # a query chunk = 7 full waves of the persistent kernel's 256-query units: chunks that are not a multiple of
             # (SM count x 256) rows leave the last wave partly empty (measured: 134 ms with 131072-row chunks, 124 ms so)
@@ -94,7 +104,9 @@ class StreamedL2Matcher:
         self.q_bounds = self._bounds(self.nq, 0, q_chunk)
         self.t_bounds = self._bounds(self.nt, t_first, t_chunk)
         dev = self.device
-        self.dq = torch.empty((self.nq, self.d), dtype=torch.float32, device=dev)
+        nrows = self.q_per * nranks if self.query_slices else self.nq
+        self.dq = torch.empty((nrows, self.d), dtype=torch.float32, device=dev)
+        self.dq_slice = torch.empty((self.q_per, self.d), dtype=torch.float32, device=dev) if self.query_slices else None
         self.dt = torch.empty((self.nt, self.d), dtype=torch.float32, device=dev)
         qmax = max([b - a for a, b in self.q_bounds] or [0])
         tmax = max([b - a for a, b in self.t_bounds] or [0])
@@ -105,7 +117,7 @@ class StreamedL2Matcher:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.q_ready = [torch.cuda.Event() for _ in self.q_bounds]
         self.t_ready = [torch.cuda.Event() for _ in self.t_bounds]
-        self.h2d_bytes = (self.nq + self.nt) * self.d * 4
+        self.h2d_bytes = ((self.q_hi - self.q_lo) + self.nt) * self.d * 4
 
     @staticmethod
     def _bounds(n, first, chunk):
@@ -124,8 +136,8 @@ class StreamedL2Matcher:
         return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
 
     def __call__(self, hq, ht):
-        if tuple(hq.shape) != (self.nq, self.d) or tuple(ht.shape) != (self.nt, self.d):
-            raise ValueError("StreamedL2Matcher was built for [%d,%d] x [%d,%d]" % (self.nq, self.d, self.nt, self.d))
+        if tuple(hq.shape) != (self.q_hi - self.q_lo, self.d) or tuple(ht.shape) != (self.nt, self.d):
+            raise ValueError("StreamedL2Matcher was built for [%d,%d] x [%d,%d]" % (self.q_hi - self.q_lo, self.d, self.nt, self.d))
         if hq.is_cuda or ht.is_cuda:
             raise ValueError("StreamedL2Matcher takes HOST tensors; use engine.knn2_l2 for device tensors")
         if self.nq == 0 or self.nt == 0:
@@ -135,9 +147,14 @@ class StreamedL2Matcher:
         cs.wait_stream(cur)  # the previous call's kernels no longer read the device copies
         nqc, ntc = len(self.q_bounds), len(self.t_bounds)
         order = [("q", 0), ("t", 0)] + [("q", i) for i in range(1, nqc)] + [("t", j) for j in range(1, ntc)]
+        if self.query_slices:
+            order = [("qs", 0)] + [("t", j) for j in range(ntc)]
         with torch.cuda.stream(cs):
             for kind, k in order:
-                if kind == "q":
+                if kind == "qs":
+                    self.dq_slice[:self.q_hi - self.q_lo].copy_(hq, non_blocking=True)
+                    self.q_ready[0].record(cs)
+                elif kind == "q":
                     a, b = self.q_bounds[k]
                     self.dq[a:b].copy_(hq[a:b], non_blocking=True)
                     self.q_ready[k].record(cs)
@@ -145,10 +162,13 @@ class StreamedL2Matcher:
                     a, b = self.t_bounds[k]
                     self.dt[a:b].copy_(ht[a:b], non_blocking=True)
                     self.t_ready[k].record(cs)
+        if self.query_slices:
+            cur.wait_event(self.q_ready[0])
+            dist.all_gather_into_tensor(self.dq, self.dq_slice)  # rank r's rows land at [r * q_per, (r + 1) * q_per)
         for j, (ta, tb) in enumerate(self.t_bounds):
             cur.wait_event(self.t_ready[j])
             for i, (qa, qb) in enumerate(self.q_bounds):
-                if j == 0:
+                if j == 0 and not self.query_slices:
                     cur.wait_event(self.q_ready[i])
                 pi, pd = self.part_idx[j, qa:qb], self.part_dist[j, qa:qb]
                 engine.knn2_l2(self.dq[qa:qb], self.dt[ta:tb], mode=self.mode, out=(pi, pd), workspace=self.ws)
@@ -222,11 +242,13 @@ class StreamedHomographyBatch:
     buffers, valid until the next call).
     """
 
-    def __init__(self, pair_offsets, device, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, pairs_per_chunk=512):
+    def __init__(self, pair_offsets, device, thresh=5.0, nhyp=2000, confidence=0.995, seed=0, pairs_per_chunk=512,
+                 sampler="counter"):
         self.device = torch.device(device)
         offs = torch.as_tensor(pair_offsets, dtype=torch.int64).cpu()
         self.npairs, self.total = int(offs.numel() - 1), int(offs[-1])
         self.args = (float(thresh), int(nhyp), float(confidence), int(seed))
+        self.sampler = sampler
         step = max(int(pairs_per_chunk), 1)
         self.chunks = []
         for p0 in range(0, self.npairs, step):
@@ -259,7 +281,7 @@ class StreamedHomographyBatch:
         for c, (p0, p1, r0, r1, local) in enumerate(self.chunks):
             cur.wait_event(self.ready[c])
             H, mask, ninl, _ = engine.ransac_homography_batch(self.src[r0:r1], self.dst[r0:r1], local, thresh, nhyp, conf,
-                                                              seed=seed, pair_index0=p0)
+                                                              seed=seed, pair_index0=p0, sampler=self.sampler)
             self.H[p0:p1], self.mask[r0:r1], self.ninl[p0:p1] = H, mask, ninl
         return self.H, self.mask, self.ninl
 
@@ -310,7 +332,7 @@ def pose_topk_sharded(query, db_shard, row_offset, k=16, match_fn=None, topk_fn=
 
 
 def scene_retrieval(query_desc, query_kp, db_desc, db_kp, seg_offsets, ratio=0.8, min_match=16, thresh=5.0, nhyp=2000,
-                    confidence=0.995, seed=0, query_pose=None, db_poses=None, query_size=None):
+                    confidence=0.995, seed=0, query_pose=None, db_poses=None, query_size=None, sampler="counter"):
     """One query image against an image database, the whole of features.match_and_draw + validate_homography per
     database image (features.py:57-105,:177-211) without leaving the device: segmented Hamming kNN-2 + ratio ->
     per-image match lists -> batched RANSAC in both directions -> homography sanity flags.
@@ -323,8 +345,8 @@ def scene_retrieval(query_desc, query_kp, db_desc, db_kp, seg_offsets, ratio=0.8
     to be compared with thresholds.AFFINE_TRANS_WHOLE_DISTANCE (matching.py:75)."""
     score, best = engine.knn2_hamming_segmented(query_desc, db_desc, seg_offsets, ratio, want_best_idx=True)
     offs, src, dst, sel = engine.segment_matches(best, score, query_kp, db_kp, min_match)
-    H, mask, ninl, _ = engine.ransac_homography_batch(src, dst, offs, thresh, nhyp, confidence, seed)
-    H2, _, _, _ = engine.ransac_homography_batch(dst, src, offs, thresh, nhyp, confidence, seed)
+    H, mask, ninl, _ = engine.ransac_homography_batch(src, dst, offs, thresh, nhyp, confidence, seed, sampler=sampler)
+    H2, _, _, _ = engine.ransac_homography_batch(dst, src, offs, thresh, nhyp, confidence, seed, sampler=sampler)
     valid = engine.validate_homography_batch(H)
     out = {"n_matches": score, "n_inliers": ninl, "H": H, "H2": H2, "valid": valid, "pair_offsets": offs, "src": src,
            "dst": dst, "mask": mask, "sel": sel}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HPUSM_ABI_VERSION 100
+#define HPUSM_ABI_VERSION 200
 
 #define HPUSM_OK 0
 #define HPUSM_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported width) */
@@ -153,39 +153,41 @@ int hpusm_validate_homography_batch(const double* H, int64_t n, uint8_t* valid, 
  * Replaces cv2.findHomography(src, dst, cv2.RANSAC, thresh) (features.py:66 and :69), batched over
  * image pairs.  Pair p owns matches [pair_offsets[p], pair_offsets[p+1]).
  *   src, dst [total][2] float32; pair_offsets [npairs+1] int64 (device).
- *   nhyp      hypotheses per pair (cv2 maxIters; reference default 2000).
- *   confidence  > 0: reproduce the sequential early-exit of RANSAC exactly (hypothesis h is considered
+ *   nhyp      RANSAC iterations per pair (cv2 maxIters; reference default 2000).  As in OpenCV every iteration redraws
+ *             its 4-point sample until HomographyEstimatorCallback::checkSubset accepts it, so every iteration scores a model.
+ *   confidence  > 0: reproduce the sequential early-exit of RANSAC exactly (iteration h is considered
  *               only while h < the adaptive iteration bound, cv2 default 0.995); <= 0: use all nhyp.
- *   seed      keys the counter-based sample table (seed, pair, hypothesis) shared with the oracle.
+ *   sampler   HPUSM_RANSAC_SAMPLER_CV2: OpenCV's own fixed-seed sample sequence (its RNG cannot be seeded from Python and
+ *               ignores cv2.setRNGSeed) replayed by a sequential per-pair pre-pass, and OpenCV's float32 computeError as
+ *               the inlier test: mask and H are those of cv2.findHomography (identical masks, H to 1e-4 and better; pinned
+ *               on 13 real image pairs and 1000 synthetic ones, tests/golden/ransac_*.npz).  `seed`/`pair_index0` are unused.
+ *             HPUSM_RANSAC_SAMPLER_COUNTER: counter-based sample table keyed on (seed, pair_index0 + p, iteration, attempt),
+ *               drawn by all lanes in parallel, division-free inlier test; shared bit for bit with oracle/ransac_oracle.c.
+ *               A batch cut into chunks or sharded over GPUs passes its first pair's global index as pair_index0 and
+ *               draws exactly the samples of the one-call run.
  *   H    [npairs][9] float64 row-major, H[8] == 1; all NaN when no model with >= 4 inliers exists.
  *   mask [total] uint8 inlier flags: with refine != 0 the inliers of the REFINED homography under cv2's float32
  *               reprojection error (what cv2 4.x returns); otherwise those of the winning minimal-sample model.
- *   ninl [npairs] int32 = number of set mask entries; best_hyp [npairs] int32 (optional, may be NULL) winning index.
- *   refine != 0: least-squares DLT on the inliers followed by Levenberg-Marquardt on the reprojection
- *               error (cv2 does both); refine == 0 returns the winning minimal-sample model.
+ *   ninl [npairs] int32 = number of set mask entries; best_hyp [npairs] int32 (optional, may be NULL) winning iteration.
+ *   refine != 0: findHomography's post-processing -- runKernel's normalised DLT on the inliers of the winning model, then
+ *               LMSolver's <= 10 Levenberg-Marquardt iterations on the reprojection error; refine == 0 returns the winning
+ *               minimal-sample model.
  * ------------------------------------------------------------------------------------------------ */
-size_t hpusm_ransac_homography_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp);
+#define HPUSM_RANSAC_SAMPLER_COUNTER 0
+#define HPUSM_RANSAC_SAMPLER_CV2 1
+size_t hpusm_ransac_homography_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp, int sampler);
 int hpusm_ransac_homography_batch(const float* src, const float* dst, const int64_t* pair_offsets,
                                   int64_t npairs, int64_t total_matches, float thresh, int nhyp,
-                                  double confidence, uint64_t seed, int refine, double* H,
-                                  uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
+                                  double confidence, int sampler, uint64_t seed, int64_t pair_index0, int refine,
+                                  double* H, uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
                                   size_t ws_bytes, void* stream);
-/* Hypothesis scoring only (the C4 benchmark kernel): counts [npairs][nhyp] int32 inlier counts,
- * -1 for a degenerate sample. */
+/* Scoring only (the C4 benchmark kernel): counts [npairs][nhyp] int32 inlier count of every iteration's model,
+ * -1 where an iteration found no acceptable sample (degenerate input).  ws is only needed by the cv2 sampler. */
+size_t hpusm_ransac_score_workspace_bytes(int64_t total_matches, int64_t npairs, int nhyp, int sampler);
 int hpusm_ransac_score_batch(const float* src, const float* dst, const int64_t* pair_offsets,
-                             int64_t npairs, int64_t total_matches, float thresh, int nhyp,
-                             uint64_t seed, int32_t* counts, void* stream);
-
-/* The same two calls for a SLICE of a larger batch: pair p of this call is pair `pair_index0 + p` of the sample table, so a
- * batch cut into chunks (pipelined uploads) or sharded over GPUs draws exactly the samples of the one-call run. */
-int hpusm_ransac_homography_batch_at(const float* src, const float* dst, const int64_t* pair_offsets,
-                                     int64_t npairs, int64_t total_matches, float thresh, int nhyp,
-                                     double confidence, uint64_t seed, int64_t pair_index0, int refine, double* H,
-                                     uint8_t* mask, int32_t* ninl, int32_t* best_hyp, void* ws,
-                                     size_t ws_bytes, void* stream);
-int hpusm_ransac_score_batch_at(const float* src, const float* dst, const int64_t* pair_offsets,
-                                int64_t npairs, int64_t total_matches, float thresh, int nhyp,
-                                uint64_t seed, int64_t pair_index0, int32_t* counts, void* stream);
+                             int64_t npairs, int64_t total_matches, float thresh, int nhyp, int sampler,
+                             uint64_t seed, int64_t pair_index0, int32_t* counts, void* ws, size_t ws_bytes,
+                             void* stream);
 
 /* Projective transform of points, replaces cv2.perspectiveTransform (features.py:77,
  * transformation.py:38): pts [n][2] float32, H [9] float64 (device) -> out [n][2] float32. */

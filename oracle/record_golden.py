@@ -226,6 +226,38 @@ def record_ransac_synth_cv2():
          pair_offsets=np.array(offs, np.int64))
 
 
+def record_validate_homography():
+    """features.validate_homography (features.py:177-211) on 1000 matrices: random similarity/projective ones around every
+    threshold (determinant sign, row norms 0.1 / 4, perspective norm 0.002), exactly singular blocks, and edge values."""
+    rng = np.random.default_rng(77)
+    Hs = []
+    for k in range(1000):
+        kind = k % 8
+        th = rng.uniform(-np.pi, np.pi)
+        s1, s2 = rng.uniform(0.05, 5.0, 2) if kind != 1 else rng.choice([0.1, 4.0, 0.0999999, 4.0000001, 0.1000001, 3.9999999], 2)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        A = np.diag([s1, s2]) @ R
+        if kind == 2:
+            A[1] = -A[1]                                     # orientation reversing
+        if kind == 3:
+            A[1] = A[0] * rng.uniform(0.5, 2.0)              # singular top-left block (determinant ~ 0 of either sign)
+        H = np.eye(3)
+        H[:2, :2] = A
+        H[:2, 2] = rng.uniform(-300, 300, 2)
+        pn = rng.choice([0.0, 0.002, 0.0019999, 0.0020001, rng.uniform(0, 0.004)])
+        ph = rng.uniform(-np.pi, np.pi)
+        H[2, :2] = pn * np.array([np.cos(ph), np.sin(ph)])
+        if kind == 4:
+            H[:2, :2] = np.array([[1.0, 2.0], [2.0, 4.0]]) * rng.uniform(0.2, 0.9)  # exactly rank one
+        if kind == 5:
+            H[:2, :2] = rng.uniform(-4.5, 4.5, (2, 2))
+        Hs.append(H)
+    Hs = np.stack(Hs)
+    valid = np.array([bool(ref_features.validate_homography(H)) for H in Hs])
+    assert 50 < valid.sum() < 950
+    save("validate_homography.npz", H=Hs, valid=valid)
+
+
 def load_fixture_poses():
     poses, names = [], []
     for f in sorted(glob.glob(os.path.join(REF, "json_data", "*.json"))):
@@ -517,7 +549,7 @@ if __name__ == "__main__":
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
                record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra,
                record_scene_pair_orb_extra, record_multi_person_match, record_scene_score_single, record_ransac_real_pairs,
-               record_ransac_synth_cv2):
+               record_ransac_synth_cv2, record_validate_homography):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

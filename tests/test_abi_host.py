@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(hpusm):
 
 def test_version_and_error_string(hpusm):
     lib = hpusm._lib.lib
-    assert lib.hpusm_version() == 100
+    assert lib.hpusm_version() == 200
     rc = lib.hpusm_knn2_hamming(None, 4, None, 4, 48, None, None, None, 0, None)  # unsupported width, no GPU needed
     assert rc == hpusm._lib.ERR_UNSUPPORTED
     assert "48" in hpusm._lib.last_error()
@@ -121,10 +121,30 @@ assert common.parse_JSON_multi_person.__module__.startswith("_hpusm_reference") 
 poses = common.parse_JSON_multi_person("/root/reference/json_data/duo1.json")
 assert poses[0].shape == (18, 2)
 assert hasattr(ft, "explore_match")                                                   # GUI helper of the reference
+det, m = ft.init_feature("orb-flann")        # the name every driver script of the reference uses (urbanscene/main.py:15)
+assert type(m).__name__ == "BFMatcher" and m.normType == ft.NORM_HAMMING and det is not None
+det, m = ft.init_feature("sift-flann")
+assert type(m).__name__ == "BFMatcher" and m.normType == ft.NORM_L2
+import os
+os.environ["HPUSM_FLANN"] = "cv2"
+det, m = ft.init_feature("orb-flann")
+assert "Flann" in type(m).__name__
 print("OK")
 ''' % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_binary_descriptor_padding():
+    """AKAZE's 61-byte descriptors are zero-padded to the kernel's 64-byte rows (Hamming distances unchanged)."""
+    import importlib
+    ft = importlib.import_module("humanpose-and-urbanscene-matching_b200.dropin.urbanscene.features")
+    d = np.random.default_rng(0).integers(0, 256, (7, 61), dtype=np.uint8)
+    p = ft._pad_binary(d)
+    assert p.shape == (7, 64) and np.array_equal(p[:, :61], d) and not p[:, 61:].any()
+    assert ft._pad_binary(d[:, :32]) .shape == (7, 32) and ft._pad_binary(d[:, :20]).shape == (7, 32)
+    with pytest.raises(ValueError):
+        ft._pad_binary(np.zeros((2, 65), np.uint8))
 
 
 def test_public_python_surface_is_complete():

@@ -90,11 +90,11 @@ def test_c4_ransac_100k_pairs_properties(hpusm, cuda_device):
     src, dst = src.reshape(-1, 2).contiguous(), dst.reshape(-1, 2).contiguous()
     offs = torch.arange(0, npairs + 1, device=cuda_device, dtype=torch.int64) * K
     counts = hpusm.ransac_score_batch(src, dst, offs, 5.0, nhyp, seed=4)
-    # (1) counts are inlier counts in [0, K] for accepted samples (an ill-conditioned 4-point model can miss even its
-    #     own sample in the float32 test, as in cv2), -1 for rejected ones; most accepted samples do fit their points
-    valid = counts >= 0
-    assert (counts >= -1).all() and (counts <= K).all() and valid.any(dim=1).all()
-    assert (counts[valid] >= 4).float().mean() > 0.99
+    # (1) every iteration scores a model (samples are redrawn until OpenCV's subset check passes): counts are inlier
+    #     counts in [0, K]; an ill-conditioned 4-point model can miss even its own sample in the float32 test, as in
+    #     cv2, but nearly all models do fit their points
+    assert (counts >= 0).all() and (counts <= K).all()
+    assert (counts >= 4).float().mean() > 0.99
     # (2) the best hypothesis of every pair explains (almost) the planted 30 % and no more than inliers + chance hits
     best = counts.max(dim=1).values
     n_inl = inl.sum(dim=1)

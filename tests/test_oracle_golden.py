@@ -297,3 +297,12 @@ def test_scene_score_single_matches_reference():
         a, b = int(offs[c]), int(offs[c + 1])
         got = pose_oracle.scene_score_single(g["src"][a:b], g["dst"][a:b], g["H2"][c], g["model_pose"][c], g["input_pose"][c])
         np.testing.assert_allclose(got, g["result"][c], rtol=1e-7, atol=1e-10)
+
+
+def test_dropin_validate_homography_matches_reference():
+    """The drop-in's host-side validate_homography (nine scalar operations) against the reference's on 1000 matrices."""
+    import importlib
+    ft = importlib.import_module("humanpose-and-urbanscene-matching_b200.dropin.urbanscene.features")
+    g = load_golden("validate_homography.npz")
+    got = np.array([bool(ft.validate_homography(H)) for H in g["H"]])
+    np.testing.assert_array_equal(got, g["valid"])
