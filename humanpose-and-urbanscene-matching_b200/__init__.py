@@ -6,6 +6,7 @@ csrc/        hand-written CUDA kernels + the C ABI  -> libhpusm.so (see include/
 _lib.py      ctypes binding of the C ABI (fails loudly when the library or a GPU is missing)
 engine.py    batched entry points over torch CUDA tensors (buffer carriers only)
 retrieval.py query-vs-database drivers, sharded over ranks with torch.distributed
+posedb.py / imagedb.py  packed pose / image-descriptor databases streamed from disk to HBM
 dropin/      modules with the reference's own names and signatures (urbanscene.features, ...)
 
 The directory name carries hyphens, so import it with
@@ -14,7 +15,7 @@ module at the repository root.
 """
 from . import _lib  # noqa: F401
 from . import synth  # noqa: F401
-from . import engine, retrieval, posedb, dropin  # noqa: F401
+from . import engine, retrieval, posedb, imagedb, dropin  # noqa: F401
 from .engine import (  # noqa: F401
     knn2_hamming,
     knn2_hamming_segmented,

@@ -42,6 +42,7 @@ _u64 = ctypes.c_uint64
 # name -> (restype, argtypes); mirrors include/hpusm.h one to one
 SIGNATURES = {
     "hpusm_version": (_i32, []),
+    "hpusm_async_status": (_i32, []),
     "hpusm_last_error": (ctypes.c_char_p, []),
     "hpusm_device_count": (_i32, []),
     "hpusm_launch_count": (_i64, []),
@@ -70,7 +71,8 @@ SIGNATURES = {
     "hpusm_perspective_transform": (_i32, [_p, _i64, _p, _p, _p]),
     "hpusm_affine_lsq_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p]),
     "hpusm_procrustes_batch": (_i32, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
-    "hpusm_pose_match_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "hpusm_pose_match_workspace_bytes": (_sz, [_i64]),
+    "hpusm_pose_match_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "hpusm_pose_match_batch_f64": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "hpusm_pose_match_pairs": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "hpusm_scene_score_batch": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _f64, _f64, _u64, _p, _p, _p, _p]),
@@ -78,8 +80,11 @@ SIGNATURES = {
     "hpusm_pose_topk_workspace_bytes": (_sz, [_i64, _i32]),
     "hpusm_pose_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "hpusm_pose_topk_merge": (_i32, [_p, _p, _i64, _i32, _p, _p, _p]),
+    "hpusm_orb_workspace_bytes": (_sz, [_i32, _i32, _i32, _f64]),
+    "hpusm_orb_compute": (_i32, [_p, _i32, _i32, _i64, _i32, _f64, _p, _p, _i64, _p, _p, _sz, _p]),
     "hpusm_microbench_popc": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_lop3": (_i32, [_i64, _i32, _i64, _p, _p]),
+    "hpusm_microbench_ffma": (_i32, [_i32, _i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_minmax": (_i32, [_i32, _i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_mma": (_i32, [_i32, _i32, _p]),
 }

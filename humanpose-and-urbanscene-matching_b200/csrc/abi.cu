@@ -22,17 +22,18 @@ void set_error(const char* fmt, ...) {
 static std::atomic<int> g_profile{0};
 static std::mutex g_profile_mu;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events;
-static cudaEvent_t g_profile_open = nullptr;
+static thread_local cudaEvent_t g_profile_open = nullptr;  // begin/end are paired on the launching thread
 
 void profile_mark(cudaStream_t st, bool begin) {
   if (!g_profile.load(std::memory_order_relaxed)) return;
-  std::lock_guard<std::mutex> lock(g_profile_mu);
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, st);
   if (begin) {
+    if (g_profile_open) cudaEventDestroy(g_profile_open);
     g_profile_open = e;
   } else if (g_profile_open) {
+    std::lock_guard<std::mutex> lock(g_profile_mu);
     g_profile_events.emplace_back(g_profile_open, e);
     g_profile_open = nullptr;
   } else {
@@ -41,15 +42,72 @@ void profile_mark(cudaStream_t st, bool begin) {
 }
 
 int sm_count() {
-  static int cached[64] = {0};
+  static std::atomic<int> cached[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (cached[dev] == 0) {
-    int n = 0;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    cached[dev] = n;
+    cached[dev].store(n, std::memory_order_relaxed);
   }
-  return cached[dev];
+  return n;
+}
+
+// FP32 pipe: every thread issues `iters` fused multiply-adds in 8 independent chains; PACKED = fma.rn.f32x2 (FFMA2, two
+// FMAs per instruction), else scalar FFMA.  The measured denominator of the RANSAC scoring kernel's roofline.
+template <bool PACKED>
+__global__ void ffma_microbench_kernel(int64_t iters, uint32_t* sink) {
+  const float s0 = 1.0f + 1e-7f * threadIdx.x, m = 0.999999f;
+  if (PACKED) {
+    unsigned long long a[8], mm, cc;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(m));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(1e-9f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(a[i]) : "f"(s0 + i), "f"(s0 - i));
+    for (int64_t k = 0; k < iters; k += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(mm), "l"(cc));
+    }
+    unsigned long long r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= a[i];
+    if (r == 0x123456789abcdefull) sink[0] = 1;
+  } else {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = s0 + i;
+    for (int64_t k = 0; k < iters; k += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(m), "f"(1e-9f));
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += a[i];
+    if (r == 123.456f) sink[0] = 1;
+  }
+}
+
+// ---- asynchronous error word (pinned, mapped) ------------------------------------------------------------------------
+static std::mutex g_async_mu;
+static volatile int* g_async_host = nullptr;
+
+__global__ void async_report_kernel(const int* __restrict__ device_flag, int code, volatile int* host_word) {
+  if (*device_flag != 0) *host_word = code;
+}
+
+int async_report(const int* device_flag, int code, cudaStream_t st) {
+  {
+    std::lock_guard<std::mutex> lock(g_async_mu);
+    if (!g_async_host) {
+      int* p = nullptr;
+      HPUSM_CUDA_OK(cudaHostAlloc(&p, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+      *p = 0;
+      g_async_host = p;
+    }
+  }
+  HPUSM_LAUNCH(async_report_kernel, 1, 1, 0, st, device_flag, code, g_async_host);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
 }
 
 // Each thread keeps 8 independent POPC chains so the pipe, not the dependency, is the limit.
@@ -116,6 +174,16 @@ extern "C" {
 
 int hpusm_version(void) { return HPUSM_ABI_VERSION; }
 
+int hpusm_async_status(void) {
+  std::lock_guard<std::mutex> lock(hpusm::g_async_mu);
+  if (!hpusm::g_async_host) return HPUSM_OK;
+  const int code = *hpusm::g_async_host;
+  *hpusm::g_async_host = 0;
+  if (code != 0) hpusm::set_error("an asynchronous entry point rejected its input on the device (code %d): e.g. HPUSM_L2_TC_I8 "
+                                  "on descriptors that are not integers in [0,255]", code);
+  return code;
+}
+
 const char* hpusm_last_error(void) { return t_error; }
 
 int hpusm_device_count(void) {
@@ -172,6 +240,16 @@ int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* 
   HPUSM_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,
                 "hpusm_microbench_lop3: bad arguments");
   HPUSM_LAUNCH(lop3_microbench_kernel, (unsigned)blocks, threads, 0, as_stream(stream), iters, sink);
+  HPUSM_CHECK_LAUNCH();
+  return HPUSM_OK;
+}
+
+int hpusm_microbench_ffma(int packed, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream) {
+  HPUSM_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, HPUSM_ERR_INVALID,
+                "hpusm_microbench_ffma: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (packed) { HPUSM_LAUNCH(ffma_microbench_kernel<true>, (unsigned)blocks, threads, 0, st, iters, sink); }
+  else { HPUSM_LAUNCH(ffma_microbench_kernel<false>, (unsigned)blocks, threads, 0, st, iters, sink); }
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

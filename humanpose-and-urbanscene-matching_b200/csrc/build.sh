@@ -11,7 +11,9 @@ PIDS=()
 for f in *.cu; do
   o="build/${f%.cu}.o"
   mkdir -p build
-  if [[ ! -f "$o" || "$f" -nt "$o" || common.cuh -nt "$o" || tc_ptx.cuh -nt "$o" || l2_internal.cuh -nt "$o" || ../../include/hpusm.h -nt "$o" ]]; then
+  stale=0
+  for h in *.cuh *.inc ../../include/hpusm.h; do [[ "$h" -nt "$o" ]] && stale=1; done
+  if [[ ! -f "$o" || "$f" -nt "$o" || $stale -eq 1 ]]; then
     echo "nvcc $f"
     "$NVCC" "${FLAGS[@]}" ${HPUSM_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
     PIDS+=($!)

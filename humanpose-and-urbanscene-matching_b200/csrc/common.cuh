@@ -64,6 +64,10 @@ inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintp
 
 int sm_count();  // SMs of the current device (148 on B200), cached
 
+// Asynchronous error reporting: enqueues a one-thread kernel that, if *device_flag != 0, stores `code` into a pinned host
+// word; hpusm_async_status() returns and clears it.  Lets an entry point stay asynchronous where it used to read a flag back.
+int async_report(const int* device_flag, int code, cudaStream_t st);
+
 // ---- device helpers -------------------------------------------------------------------------------
 
 // A (distance, index) candidate pair list of length 2 kept sorted lexicographically.

@@ -256,13 +256,13 @@ int l2_simt_candidates(const float* q, int64_t nq, const float* t, int64_t nt, i
   const int64_t rows = row_list ? n_list : nq;
   if (rows == 0) return HPUSM_OK;
   const size_t smem = l2_simt_smem_bytes(d);
-  static bool attr_done[64] = {false};
+  static std::atomic<bool> attr_done[64];
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+  if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
     HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_simt_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)l2_simt_smem_bytes(512)));
-    attr_done[dev] = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   const int64_t tiles = (rows + SIMT_TQ - 1) / SIMT_TQ;
   const int64_t rows_per_split = nt == 0 ? 1 : (nt + splits - 1) / splits;

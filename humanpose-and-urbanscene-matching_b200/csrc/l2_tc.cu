@@ -62,8 +62,9 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 
 // ---- operand preparation --------------------------------------------------------------------------------
 // One warp per row: float32 -> bf16 operand row of 144 columns and the exactness check.  A value passes when it is
-// an integer with |v| <= 256: then bf16 holds v and 2v exactly and every partial sum of the contraction is an
-// integer of magnitude <= 2^24.  flag[0] |= 1 otherwise.
+// an integer in [0, 256]: then bf16 holds v and 2v exactly, every partial sum of the contraction is an integer of
+// magnitude <= 2^24, and s = 2 q.t - ||t||^2 >= -||t||^2 > -2^24 stays above the key of the padding rows (mixed-sign
+// integers could push s below it and lose a real neighbour to a padding row: they take the split engine).  flag[0] |= 1 otherwise.
 //   query side    (is_db == 0): [2q | 1 1 1 0 ...]
 //   database side (is_db == 1): [t | -p0 -p1 -p2 0 ...], ||t||^2 = p0 + p1 + p2 (bytes 0, 1, 2 of the integer norm);
 //                               rows n..n_pad are padding that can never be selected (s = -(2^24 - 1)).
@@ -81,7 +82,7 @@ l2_tc_prep_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int is_
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      bad |= !(fabsf(f[i]) <= 256.f) || f[i] != rintf(f[i]);
+      bad |= !(f[i] >= 0.f && f[i] <= 256.f) || f[i] != rintf(f[i]);
       s = fmaf(f[i], f[i], s);
     }
   }
@@ -471,13 +472,13 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
     if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, TC_KA, 16, CU_TENSOR_MAP_SWIZZLE_32B, 128);
     if (rc != HPUSM_OK) return rc;
   }
-  static bool attr_done[64] = {false};
+  static std::atomic<bool> attr_done[64];
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+  if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
     HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_done[dev] = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   const int q_blocks = (int)((nq + TC_QB - 1) / TC_QB);
   int64_t rows_per_split = (nt + L.splits_tc - 1) / L.splits_tc;
@@ -512,6 +513,11 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   HPUSM_CHECK_LAUNCH();
   *resolved_mode = HPUSM_L2_TC_INT;
   *fallback_rows = 0;
+  if (mode == HPUSM_L2_TC_INT) {
+    // explicit mode: the range check gates the sweep on the device (every idx stays -1) and is reported asynchronously
+    rc = async_report(flag, HPUSM_ERR_UNSUPPORTED, st);
+    if (rc != HPUSM_OK) return rc;
+  }
   return l2_rerank_finalize(q, nq, t, d, part, L.nparts, 2, nullptr, 0, idx, dist, st);
 }
 

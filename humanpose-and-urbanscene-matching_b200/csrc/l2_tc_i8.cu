@@ -207,7 +207,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtensorMap map_t,
                   const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt, int q_blocks, int splits,
                   int64_t rows_per_split, const uint32_t* __restrict__ par, int32_t* __restrict__ part_idx,
-                  long long* __restrict__ trace) {
+                  long long* __restrict__ trace, const int* __restrict__ gate) {
+  // explicit HPUSM_L2_TC_I8 is fully asynchronous: the prep kernels' eligibility flag is consumed HERE instead of being
+  // read back by the host; ineligible data leave the candidate lists empty (every idx -1) and the error is reported
+  // through hpusm_async_status().  Uniform over the grid, before any barrier or tensor-memory allocation.
+  if (gate && *gate != 0) return;
   extern __shared__ uint8_t i8_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem;                          // [stages][16 KB | 4 KB]
@@ -491,27 +495,27 @@ int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_
   HPUSM_CHECK_LAUNCH();
   HPUSM_LAUNCH(l2_i8_prep_kernel, (unsigned)((L.nt_pad + 7) / 8), 256, 0, st, t, nt, L.nt_pad, 1, tb, par, flag);
   HPUSM_CHECK_LAUNCH();
-  // the one host read of the engine: do the descriptors fit u8 operands?
-  int h_flag = 0;
-  HPUSM_CUDA_OK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  HPUSM_CUDA_OK(cudaStreamSynchronize(st));
-  *eligible = h_flag == 0;
-  if (h_flag != 0) {
-    HPUSM_REQUIRE(!require, HPUSM_ERR_UNSUPPORTED,
-                  "HPUSM_L2_TC_I8 needs integer descriptors in [0,255] with squared norms up to %d", 2 * I8_HB);
-    return HPUSM_OK;
+  *eligible = 1;
+  if (!require) {
+    // HPUSM_L2_AUTO: the one host read of the engine -- do the descriptors fit u8 operands?  (The explicit mode never
+    // synchronises: the flag gates the sweep on the device and surfaces through hpusm_async_status().)
+    int h_flag = 0;
+    HPUSM_CUDA_OK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HPUSM_CUDA_OK(cudaStreamSynchronize(st));
+    *eligible = h_flag == 0;
+    if (h_flag != 0) return HPUSM_OK;
   }
   HPUSM_CUDA_OK(cudaMemsetAsync(part, 0xff, (size_t)L.splits * I8_CGS * nq * 2 * sizeof(int32_t), st));
   CUtensorMap map_t, map_ta;
   int rc = tc_make_map(&map_t, tb, L.nt_pad, I8_KA, 128, CU_TENSOR_MAP_SWIZZLE_128B, I8_TN, 1);
   if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, I8_KA, 32, CU_TENSOR_MAP_SWIZZLE_32B, I8_TN, 1);
   if (rc != HPUSM_OK) return rc;
-  static bool attr_done[64] = {false};
+  static std::atomic<bool> attr_done[64];
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+  if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
     HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
-    attr_done[dev] = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   const int q_blocks = (int)((nq + I8_QB - 1) / I8_QB);
   int64_t rows_per_split = (nt + L.splits - 1) / L.splits;
@@ -524,8 +528,12 @@ int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_
   if (trace_path) { HPUSM_CUDA_OK(cudaMalloc(&trace, 8192 * 8)); HPUSM_CUDA_OK(cudaMemset(trace, 0, 8192 * 8)); }
 #endif
   HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
-                     rows_per_split, par, part, trace);
+                     rows_per_split, par, part, trace, require ? flag : nullptr);
   HPUSM_CHECK_LAUNCH();
+  if (require) {
+    int rc2 = async_report(flag, HPUSM_ERR_UNSUPPORTED, st);
+    if (rc2 != HPUSM_OK) return rc2;
+  }
 #ifdef I8_TRACE
   if (trace) {
     static long long h[8192];

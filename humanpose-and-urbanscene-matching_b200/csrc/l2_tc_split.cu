@@ -410,12 +410,12 @@ int l2_tc_split_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int
   if (rc == HPUSM_OK) rc = tc_make_map(&map_t, tb, L.nt_pad, SP_K, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc == HPUSM_OK) rc = tc_make_map(&map_ta, tb, L.nt_pad, SP_K, 16, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != HPUSM_OK) return rc;
-  static bool attr_done[64] = {false};
+  static std::atomic<bool> attr_done[64];
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+  if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
     HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    attr_done[dev] = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   const int q_blocks = (int)((nq + SP_QB - 1) / SP_QB);
   int64_t rows_per_split = (nt + L.splits - 1) / L.splits;

@@ -16,6 +16,7 @@
 #include <float.h>
 #include <math.h>
 #include "common.cuh"
+#include "pose_fast.cuh"
 
 namespace hpusm {
 
@@ -474,24 +475,11 @@ constexpr int PM_THREADS = 128;
 #ifndef HPUSM_POSE_MIN_BLOCKS
 #define HPUSM_POSE_MIN_BLOCKS 4  // 128 registers: measured 1.39 ms per 10 M poses vs 1.59 ms at 2 blocks (233 registers)
 #endif
+// One database pose through the exact FP64 decision.
 template <typename T>
-__global__ void __launch_bounds__(PM_THREADS, HPUSM_POSE_MIN_BLOCKS)
-pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, int64_t n, int query_is_model,
-                        PoseParams prm, uint8_t* __restrict__ match, float* __restrict__ score,
-                        double* __restrict__ detail) {
-  __shared__ T sq[NJ * 2];
-  __shared__ unsigned sq_undetected;
-  if (threadIdx.x < NJ * 2) sq[threadIdx.x] = query[threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned u = 0;
-    for (int j = 0; j < NJ; ++j) if (sq[2 * j] == T(0) && sq[2 * j + 1] == T(0)) u |= 1u << j;
-    sq_undetected = u;
-  }
-  __syncthreads();
-  const int64_t p = (int64_t)blockIdx.x * PM_THREADS + threadIdx.x;
-  if (p >= n) return;
-
+__device__ __forceinline__ void pose_exact_one(const T* sq, unsigned sq_undetected, const T* __restrict__ db, int64_t p,
+                                               int query_is_model, const PoseParams& prm, uint8_t* __restrict__ match,
+                                               float* __restrict__ score, double* __restrict__ detail) {
   T pr[NJ * 2];
   load_pose<T>(db + p * (NJ * 2), pr);
   // common.handle_undetected_points: a joint missing on either side is (0,0) on both
@@ -507,6 +495,81 @@ pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, i
     pose_decide_slow<T>(sq, db + p * (NJ * 2), und, query_is_model, &prm, match + p, score + p, det);
   else
     pose_decide<T, false, false>(sq, pr, und, s_q, s_p, query_is_model, prm, match + p, score + p, nullptr);
+}
+
+// Exact FP64 decision for every database pose (list == nullptr: thread = pose) or for the poses the FP32 fast path
+// could not certify (list / list_count: grid-stride over the list).
+template <typename T>
+__global__ void __launch_bounds__(PM_THREADS, HPUSM_POSE_MIN_BLOCKS)
+pose_match_batch_kernel(const T* __restrict__ query, const T* __restrict__ db, int64_t n, int query_is_model,
+                        PoseParams prm, uint8_t* __restrict__ match, float* __restrict__ score,
+                        double* __restrict__ detail, const int32_t* __restrict__ list, const int32_t* __restrict__ list_count) {
+  __shared__ T sq[NJ * 2];
+  __shared__ unsigned sq_undetected;
+  if (threadIdx.x < NJ * 2) sq[threadIdx.x] = query[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned u = 0;
+    for (int j = 0; j < NJ; ++j) if (sq[2 * j] == T(0) && sq[2 * j + 1] == T(0)) u |= 1u << j;
+    sq_undetected = u;
+  }
+  __syncthreads();
+  if (list) {
+    const int64_t cnt = *list_count;
+    for (int64_t i = (int64_t)blockIdx.x * PM_THREADS + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * PM_THREADS)
+      pose_exact_one<T>(sq, sq_undetected, db, (int64_t)list[i], query_is_model, prm, match, score, detail);
+    return;
+  }
+  const int64_t p = (int64_t)blockIdx.x * PM_THREADS + threadIdx.x;
+  if (p >= n) return;
+  pose_exact_one<T>(sq, sq_undetected, db, p, query_is_model, prm, match, score, detail);
+}
+
+// ---- FP32 fast path (pose_fast.cuh) ----------------------------------------------------------------------------------
+__global__ void pose_query_prep_kernel(const float* __restrict__ query, PoseQueryPrep* __restrict__ prep) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    PoseQueryPrep pq;
+    pose_query_prep(query, pq);
+    *prep = pq;
+  }
+}
+
+constexpr int PF_THREADS = 128;
+
+// thread = database pose.  A pose the FP32 evaluation cannot certify goes to `list` (one atomic per warp) for the exact kernel.
+template <bool QIM>
+__global__ void __launch_bounds__(PF_THREADS)
+pose_match_fast_kernel(const PoseQueryPrep* __restrict__ prep, const float* __restrict__ db, int64_t n, PoseFastParams prm,
+                       uint8_t* __restrict__ match, float* __restrict__ score, int32_t* __restrict__ list,
+                       int32_t* __restrict__ list_count) {
+  __shared__ PoseQueryPrep pq;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(prep);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&pq);
+    for (int i = threadIdx.x; i < (int)(sizeof(PoseQueryPrep) / 4); i += PF_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
+  bool defer = false;
+  if (p < n) {
+    float pr[NJ * 2], px[NJ], py[NJ];
+    load_pose<float>(db + p * (NJ * 2), pr);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { px[j] = pr[2 * j]; py[j] = pr[2 * j + 1]; }
+    uint8_t m = 0;
+    float sc = 0.f;
+    const bool certain = pq.usable && pose_fast_decide<float, QIM>(pq, px, py, prm, PF_DIST_BAND, PF_ROT_BAND, m, sc);
+    if (certain) { match[p] = m; score[p] = sc; }
+    defer = !certain;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, defer);
+  if (bal) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(list_count, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (defer) list[base + __popc(bal & ((1u << lane) - 1u))] = (int32_t)p;
+  }
 }
 
 // Arbitrary (model, input) pose pairs in one launch: the candidate stage of multi_person.match
@@ -821,8 +884,29 @@ static void pose_params(const double* thresholds, PoseParams& prm) {
   prm.tan_legs = prm.legs_use_tan ? tan(a_l) : 0.0;
 }
 
+struct PoseWs {
+  PoseQueryPrep* prep;
+  int32_t* count;
+  int32_t* list;
+  size_t bytes;
+};
+
+static PoseWs pose_ws_layout(void* ws, int64_t n) {
+  char* p = reinterpret_cast<char*>(ws);
+  PoseWs w{};
+  size_t off = 0;
+  w.prep = reinterpret_cast<PoseQueryPrep*>(p); off += align_up(sizeof(PoseQueryPrep), 256);
+  w.count = reinterpret_cast<int32_t*>(p ? p + off : nullptr); off += 256;
+  w.list = reinterpret_cast<int32_t*>(p ? p + off : nullptr); off += align_up((size_t)(n > 0 ? n : 1) * sizeof(int32_t), 256);
+  w.bytes = off;
+  return w;
+}
+
+size_t hpusm_pose_match_workspace_bytes(int64_t n) { return pose_ws_layout(nullptr, n).bytes; }
+
 int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int query_is_model,
-                           const double* thresholds, uint8_t* match, float* score, double* detail, void* stream) {
+                           const double* thresholds, uint8_t* match, float* score, double* detail, void* ws,
+                           size_t ws_bytes, void* stream) {
   HPUSM_REQUIRE(n >= 0, HPUSM_ERR_INVALID, "hpusm_pose_match_batch: negative size");
   if (n == 0) return HPUSM_OK;
   HPUSM_REQUIRE(query && db && thresholds && match && score, HPUSM_ERR_INVALID,
@@ -830,8 +914,32 @@ int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int q
   HPUSM_REQUIRE(is_aligned(db, 16), HPUSM_ERR_INVALID, "hpusm_pose_match_batch: db must be 16-byte aligned");
   PoseParams prm;
   pose_params(thresholds, prm);
-  HPUSM_LAUNCH_TIMED(pose_match_batch_kernel<float>, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
-                     as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+  cudaStream_t st = as_stream(stream);
+  // The FP32 fast path needs the tangent form of both rotation tests, no per-part detail, and 32-bit list indices;
+  // everything else (and whatever the fast path cannot certify) is the exact FP64 kernel's.
+  const bool fast = !detail && prm.torso_use_tan && prm.legs_use_tan && n < 0x7fffffff && ws != nullptr;
+  if (!fast) {
+    HPUSM_LAUNCH_TIMED(pose_match_batch_kernel<float>, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0, st, query,
+                       db, n, query_is_model, prm, match, score, detail, nullptr, nullptr);
+    HPUSM_CHECK_LAUNCH();
+    return HPUSM_OK;
+  }
+  const PoseWs w = pose_ws_layout(ws, n);
+  HPUSM_REQUIRE(is_aligned(ws, 256) && ws_bytes >= w.bytes, HPUSM_ERR_WORKSPACE,
+                "hpusm_pose_match_batch: workspace needs %zu bytes, got %zu", w.bytes, ws_bytes);
+  PoseFastParams fp;
+  fp.d_torso = prm.d_torso; fp.tan_torso = prm.tan_torso; fp.d_legs = prm.d_legs; fp.tan_legs = prm.tan_legs;
+  fp.d_shoulder = prm.d_shoulder;
+  HPUSM_CUDA_OK(cudaMemsetAsync(w.count, 0, sizeof(int32_t), st));
+  HPUSM_LAUNCH(pose_query_prep_kernel, 1, 32, 0, st, query, w.prep);
+  const unsigned grid = (unsigned)((n + PF_THREADS - 1) / PF_THREADS);
+  if (query_is_model)
+    HPUSM_LAUNCH_TIMED(pose_match_fast_kernel<true>, grid, PF_THREADS, 0, st, w.prep, db, n, fp, match, score, w.list, w.count);
+  else
+    HPUSM_LAUNCH_TIMED(pose_match_fast_kernel<false>, grid, PF_THREADS, 0, st, w.prep, db, n, fp, match, score, w.list, w.count);
+  const unsigned lgrid = (unsigned)min((int64_t)sm_count() * 4, (n + PM_THREADS - 1) / PM_THREADS);
+  HPUSM_LAUNCH(pose_match_batch_kernel<float>, lgrid, PM_THREADS, 0, st, query, db, n, query_is_model, prm, match, score,
+               nullptr, w.list, w.count);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }
@@ -846,7 +954,7 @@ int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n,
   PoseParams prm;
   pose_params(thresholds, prm);
   HPUSM_LAUNCH_TIMED(pose_match_batch_kernel<double>, (unsigned)((n + PM_THREADS - 1) / PM_THREADS), PM_THREADS, 0,
-                     as_stream(stream), query, db, n, query_is_model, prm, match, score, detail);
+                     as_stream(stream), query, db, n, query_is_model, prm, match, score, detail, nullptr, nullptr);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

@@ -363,6 +363,100 @@ ransac_sample_cv2_kernel(const float* __restrict__ src, const float* __restrict_
   for (; h < nhyp; ++h) out[h] = make_int4(-1, -1, -1, -1);
 }
 
+// The same sequence with one WARP per pair, for small batches (the drop-in's two calls per image pair), where the
+// thread-per-pair walk is a chain of ~10^4 dependent attempts.  OpenCV's generator itself is cheap; what an attempt costs
+// is fetching its four matches and the subset check.  So every lane walks the generator redundantly through the next 128
+// draws, keeps the four that belong to ITS attempt (lane l = attempt l of the batch, assuming no duplicate redraws
+// before it), and checks that attempt; the lanes below the first one that saw a duplicate are exactly OpenCV's next
+// attempts, and the ones among them whose subset passes are its next iterations, in order.  The attempt with the
+// duplicate is then replayed the sequential way (uniformly by all lanes) and the next batch starts behind it.
+__global__ void __launch_bounds__(128)
+ransac_sample_cv2_warp_kernel(const float* __restrict__ src, const float* __restrict__ dst,
+                              const int64_t* __restrict__ pair_offsets, int64_t npairs, int nhyp, int4* __restrict__ samples) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= npairs) return;
+  const int64_t m0 = pair_offsets[pair];
+  const uint32_t K = (uint32_t)(pair_offsets[pair + 1] - m0);
+  const float* s = src + m0 * 2;
+  const float* d = dst + m0 * 2;
+  int4* out = samples + pair * nhyp;
+  uint64_t state = 0xFFFFFFFFFFFFFFFFull;  // uniform over the warp
+  int h = 0, fails = 0;                     // iterations written; attempts since the last accepted subset
+  bool dead = K < 4;
+  while (h < nhyp && !dead) {
+    // 128 draws; lane l keeps draws 4l .. 4l+3 and the generator state in front of them
+    uint64_t st = state, my_state = state;
+    uint32_t id[4] = {0, 0, 0, 0};
+    for (int a = 0; a < 32; ++a) {
+      if (a == lane) my_state = st;
+      const uint32_t v0 = cv_rng_next(st), v1 = cv_rng_next(st), v2 = cv_rng_next(st), v3 = cv_rng_next(st);
+      if (a == lane) { id[0] = v0; id[1] = v1; id[2] = v2; id[3] = v3; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) id[i] %= K;
+    const bool dup = id[0] == id[1] || id[0] == id[2] || id[0] == id[3] || id[1] == id[2] || id[1] == id[3] || id[2] == id[3];
+    bool ok = false;
+    if (!dup) {
+      double sx[4], sy[4], dx[4], dy[4];
+      sample_points(s, d, id, sx, sy, dx, dy);
+      ok = cv_check_subset(sx, sy, dx, dy);
+    }
+    const unsigned dupmask = __ballot_sync(0xffffffffu, dup);
+    const int first_dup = dupmask ? __ffs(dupmask) - 1 : 32;
+    const unsigned valid = first_dup == 32 ? 0xffffffffu : ((1u << first_dup) - 1u);
+    const unsigned acc = __ballot_sync(0xffffffffu, ok) & valid;
+    // OpenCV gives up on an iteration after CV_MAX_ATTEMPTS failed attempts: find where, if at all, inside this batch
+    // (attempt a of the batch is the (fails + a - last accepted before a)-th of its iteration)
+    int limit = 32;  // first attempt of the batch that would be attempt number CV_MAX_ATTEMPTS + 1 of its iteration
+    {
+      const unsigned below = acc & ((1u << lane) - 1u);
+      const int since = below ? lane - (32 - __clz(below)) : fails + lane;  // failed attempts of this iteration before mine
+      const unsigned over = __ballot_sync(0xffffffffu, since >= CV_MAX_ATTEMPTS) & valid;
+      if (over) limit = __ffs(over) - 1;
+    }
+    const unsigned live = limit == 32 ? 0xffffffffu : ((1u << limit) - 1u);
+    const unsigned acc_live = acc & live;
+    if ((acc_live >> lane) & 1u) {
+      const int hh = h + __popc(acc_live & ((1u << lane) - 1u));
+      if (hh < nhyp) out[hh] = make_int4((int)id[0], (int)id[1], (int)id[2], (int)id[3]);
+    }
+    h += __popc(acc_live);
+    if (limit < 32 && limit <= first_dup) { dead = true; break; }
+    const int consumed = first_dup;  // whole attempts of the batch that were OpenCV's attempts
+    {
+      const unsigned upto = acc_live & valid;
+      fails = upto ? consumed - (32 - __clz(upto)) : fails + consumed;
+    }
+    if (first_dup == 32) { state = st; continue; }
+    // the attempt with the duplicate, replayed the sequential way from the state in front of it
+    state = __shfl_sync(0xffffffffu, my_state, first_dup);
+    if (h >= nhyp) break;
+    if (fails >= CV_MAX_ATTEMPTS) { dead = true; break; }
+    uint32_t q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      for (;;) {
+        const uint32_t v = cv_rng_next(state) % K;
+        bool dd = false;
+#pragma unroll
+        for (int c = 0; c < i; ++c) dd |= (q[c] == v);
+        if (!dd) { q[i] = v; break; }
+      }
+    }
+    double sx[4], sy[4], dx[4], dy[4];
+    sample_points(s, d, q, sx, sy, dx, dy);
+    if (cv_check_subset(sx, sy, dx, dy)) {
+      if (lane == 0) out[h] = make_int4((int)q[0], (int)q[1], (int)q[2], (int)q[3]);
+      ++h;
+      fails = 0;
+    } else {
+      ++fails;
+    }
+  }
+  for (int i = h + lane; i < nhyp; i += 32) out[i] = make_int4(-1, -1, -1, -1);
+}
+
 // grid.x = pairs. dynamic smem: float4 pts[chunk]; float models[nhyp][9] (compacted); int counts[nhyp]; int hyp_of[nhyp].
 //   A   one LANE per hypothesis: sample (redraw until the subset check passes | read the cv2 table) + FP64 closed-form
 //       solve; the models that exist are compacted (ballot + one smem atomic per warp), FP32 model parked in shared memory
@@ -953,9 +1047,15 @@ static RansacWs ransac_ws_layout(void* ws, int64_t total, int64_t npairs, int nh
 
 static int launch_sampler(const float* src, const float* dst, const int64_t* pair_offsets, int64_t npairs, int nhyp,
                           int4* samples, cudaStream_t st) {
-  const int threads = npairs >= 64 * 148 ? 64 : 32;
-  const unsigned grid = (unsigned)((npairs + threads - 1) / threads);
-  HPUSM_LAUNCH(ransac_sample_cv2_kernel, grid, threads, 0, st, src, dst, pair_offsets, npairs, nhyp, samples);
+  if (npairs < 4 * (int64_t)sm_count()) {
+    // few pairs: one warp per pair tests 32 attempts at a time (a thread per pair would walk ~10^4 dependent attempts)
+    HPUSM_LAUNCH(ransac_sample_cv2_warp_kernel, (unsigned)((npairs + 3) / 4), 128, 0, st, src, dst, pair_offsets, npairs, nhyp,
+                 samples);
+  } else {
+    const int threads = npairs >= 64 * 148 ? 64 : 32;
+    const unsigned grid = (unsigned)((npairs + threads - 1) / threads);
+    HPUSM_LAUNCH(ransac_sample_cv2_kernel, grid, threads, 0, st, src, dst, pair_offsets, npairs, nhyp, samples);
+  }
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }

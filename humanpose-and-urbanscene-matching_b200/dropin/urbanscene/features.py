@@ -64,6 +64,41 @@ class BFMatcher(object):
         return out
 
 
+class OrbGpu(object):
+    """The reference's ORB (features.py:19-20) with detection on OpenCV and DESCRIPTION on the GPU: `detectAndCompute`
+    returns the keypoints of cv2's detector and descriptors that are bit-identical to cv2's (hpusm_orb_compute:
+    INTER_LINEAR_EXACT pyramid, ORB's 7x7 Gaussian, rotated rBRIEF tests).  `last_descriptors` keeps the device tensor of
+    the last call so a caller that goes on to match (BFMatcher.knn2) can skip the upload."""
+
+    def __init__(self, cv_detector):
+        self.cv = cv_detector
+        self.last_descriptors = None
+
+    def detect(self, image, mask=None):
+        return self.cv.detect(image, mask)
+
+    def compute(self, image, keypoints):
+        if len(keypoints) == 0:
+            self.last_descriptors = None
+            return keypoints, None
+        pts = np.float32([kp.pt for kp in keypoints])
+        octs = np.int32([kp.octave for kp in keypoints])
+        angs = np.float32([kp.angle for kp in keypoints])
+        lxy, cs = engine.orb_keypoint_params(pts, octs, angs)
+        img = np.ascontiguousarray(image)
+        if img.ndim != 2 or img.dtype != np.uint8:
+            raise ValueError("OrbGpu: grayscale uint8 images only (the reference reads them with cv2.imread(path, 0))")
+        desc = engine.orb_compute(up(img, np.uint8), up(lxy, np.int32), up(cs, np.float32))
+        self.last_descriptors = desc
+        return keypoints, down(desc)
+
+    def detectAndCompute(self, image, mask=None):
+        return self.compute(image, self.detect(image, mask))
+
+    def __getattr__(self, name):  # everything else (getters, setters) is the OpenCV detector's
+        return getattr(self.cv, name)
+
+
 def init_feature(name):
     """(detector, matcher) as features.py:10-43.  Detection stays with OpenCV (out of the path's scope); the matcher
     is ours.  The '-flann' names (every driver script of the reference passes 'orb-flann': urbanscene/main.py:15,
@@ -82,6 +117,8 @@ def init_feature(name):
     elif chunks[0] == 'orb':
         detector = cv2.ORB_create(nfeatures=100000, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
                                   scoreType=cv2.ORB_FAST_SCORE, patchSize=31)
+        if os.environ.get("HPUSM_ORB", "gpu").lower() != "cv2":
+            detector = OrbGpu(detector)  # same keypoints, same descriptors bit for bit; description on the GPU
         norm = NORM_HAMMING
     elif chunks[0] == 'akaze':
         detector = cv2.AKAZE_create()

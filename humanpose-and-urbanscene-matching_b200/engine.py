@@ -7,6 +7,7 @@ an error, and a failing library call raises ``HpusmError``.
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -41,6 +42,12 @@ def _stream(dev):
 def _workspace(nbytes, dev):
     # torch's caching allocator hands out 512-byte aligned blocks; the ABI asks for 256
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def async_status():
+    """HPUSM_OK (0) or the error code an asynchronous entry point recorded on the device since the last call (explicit
+    L2_TC_I8 / L2_TC_INT on data outside their value range: every idx of that call is -1).  Call after synchronising."""
+    return int(lib.hpusm_async_status())
 
 
 def launch_count():
@@ -275,6 +282,48 @@ def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, ou
     return counts
 
 
+# ---- ORB description (the step in front of K2) --------------------------------------------------------------
+ORB_LEVELS, ORB_SCALE = 8, 1.2  # features.py:19-20
+
+
+def orb_keypoint_params(pts, octaves, angles, scale_factor=ORB_SCALE):
+    """Host-side per-keypoint inputs of hpusm_orb_compute from cv2.KeyPoint fields: (kp_lxy [n,3] int32, kp_cs [n,2] f32).
+    float32 arithmetic as in OpenCV's computeOrbDescriptors: scale = 1.f / (float)pow(scaleFactor, octave), centre =
+    cvRound(pt * scale), (cos, sin) of angle * (float)(pi/180)."""
+    pts = np.asarray(pts, np.float32).reshape(-1, 2)
+    octaves = np.asarray(octaves, np.int32).reshape(-1)
+    f32 = np.float32
+    level_scale = np.power(np.float64(scale_factor), octaves.astype(np.float64)).astype(np.float32)
+    inv = f32(1.0) / level_scale
+    lxy = np.empty((len(pts), 3), np.int32)
+    lxy[:, 0] = octaves
+    lxy[:, 1] = np.rint(pts[:, 0] * inv).astype(np.int32)
+    lxy[:, 2] = np.rint(pts[:, 1] * inv).astype(np.int32)
+    ang = (np.asarray(angles, np.float32).reshape(-1) * f32(np.pi / 180.0)).astype(np.float64)
+    cs = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)
+    return lxy, cs
+
+
+def orb_compute(img, kp_lxy, kp_cs, nlevels=ORB_LEVELS, scale_factor=ORB_SCALE, workspace=None):
+    """cv2.ORB.compute on the device: img [h,w] uint8 CUDA tensor, keypoint parameters from orb_keypoint_params (CUDA
+    tensors).  Returns desc [n,32] uint8 on the device (bit-identical to cv2's), ready for knn2_hamming."""
+    img = _cuda(img, torch.uint8, "img")
+    kp_lxy = _cuda(kp_lxy, torch.int32, "kp_lxy")
+    kp_cs = _cuda(kp_cs, torch.float32, "kp_cs")
+    if img.dim() != 2:
+        raise ValueError("img must be [height, width] uint8")
+    h, w = img.shape
+    n = kp_lxy.shape[0]
+    dev = img.device
+    with torch.cuda.device(dev):
+        desc = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+        need = lib.hpusm_orb_workspace_bytes(w, h, int(nlevels), float(scale_factor))
+        ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
+        check(lib.hpusm_orb_compute(_ptr(img), w, h, w, int(nlevels), float(scale_factor), _ptr(kp_lxy), _ptr(kp_cs), n,
+                                    _ptr(desc), _ptr(ws), ws.numel(), _stream(dev)))
+    return desc
+
+
 def perspective_transform(pts, H):
     """cv2.perspectiveTransform(pts, H) (features.py:77, transformation.py:38)."""
     pts = _cuda(pts, torch.float32, "pts")
@@ -318,9 +367,12 @@ def procrustes_batch(X, Y, scaling=True, reflection="best"):
     return d, Z, tform
 
 
-def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THRESHOLDS, want_detail=False, out=None):
+def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THRESHOLDS, want_detail=False, out=None,
+                     exact=False, workspace=None):
     """single_person.match_single of one query against a pose database (single_person.py:80-189).
 
+    float32 databases are swept by the FP32 fast path with the exact FP64 kernel behind it for every pose it cannot
+    certify (same decisions as the FP64 kernel, scores within 2e-6); `exact=True` runs the FP64 kernel on every pose.
     Returns (match [n] u8, score [n] f32[, detail [n, POSE_DETAIL] f64])."""
     f64 = db.dtype == torch.float64
     query = _cuda(query, torch.float64 if f64 else torch.float32, "query")
@@ -337,9 +389,18 @@ def pose_match_batch(query, db, query_is_model=True, thresholds=DEFAULT_POSE_THR
         else:
             match, score = out
         detail = torch.empty((n, POSE_DETAIL), dtype=torch.float64, device=dev) if want_detail else None
-        fn = lib.hpusm_pose_match_batch_f64 if f64 else lib.hpusm_pose_match_batch
-        check(fn(_ptr(query), _ptr(db), n, 1 if query_is_model else 0,
-                 ctypes.cast(thr, ctypes.c_void_p), _ptr(match), _ptr(score), _ptr(detail), _stream(dev)))
+        if f64:
+            check(lib.hpusm_pose_match_batch_f64(_ptr(query), _ptr(db), n, 1 if query_is_model else 0,
+                                                 ctypes.cast(thr, ctypes.c_void_p), _ptr(match), _ptr(score), _ptr(detail),
+                                                 _stream(dev)))
+        else:
+            ws = None
+            if not exact and not want_detail:
+                need = lib.hpusm_pose_match_workspace_bytes(n)
+                ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
+            check(lib.hpusm_pose_match_batch(_ptr(query), _ptr(db), n, 1 if query_is_model else 0,
+                                             ctypes.cast(thr, ctypes.c_void_p), _ptr(match), _ptr(score), _ptr(detail),
+                                             _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev)))
     return (match, score, detail) if want_detail else (match, score)
 
 
@@ -438,8 +499,14 @@ def microbench_mma(kind, rounds, device):
 
 
 def microbench_popc(blocks, threads, iters, device, op="popc"):
-    """op: "popc" | "lop3" | "imax3" | "fmax3" | "imax" | "fmax" -- every thread issues `iters` of that instruction."""
+    """op: "popc" | "lop3" | "imax3" | "fmax3" | "imax" | "fmax" | "ffma" | "ffma2" -- every thread issues `iters` of
+    that instruction."""
     sink = torch.zeros((1,), dtype=torch.int32, device=device)
+    if op in ("ffma", "ffma2"):
+        with torch.cuda.device(device):
+            check(lib.hpusm_microbench_ffma(1 if op == "ffma2" else 0, int(blocks), int(threads), int(iters), _ptr(sink),
+                                            _stream(device)))
+        return
     minmax = {"imax3": 0, "fmax3": 1, "imax": 2, "fmax": 3}
     with torch.cuda.device(device):
         if op in minmax:

@@ -332,7 +332,8 @@ def pose_topk_sharded(query, db_shard, row_offset, k=16, match_fn=None, topk_fn=
 
 
 def scene_retrieval(query_desc, query_kp, db_desc, db_kp, seg_offsets, ratio=0.8, min_match=16, thresh=5.0, nhyp=2000,
-                    confidence=0.995, seed=0, query_pose=None, db_poses=None, query_size=None, sampler="counter"):
+                    confidence=0.995, seed=0, query_pose=None, db_poses=None, query_size=None, sampler="counter",
+                    image_index0=0):
     """One query image against an image database, the whole of features.match_and_draw + validate_homography per
     database image (features.py:57-105,:177-211) without leaving the device: segmented Hamming kNN-2 + ratio ->
     per-image match lists -> batched RANSAC in both directions -> homography sanity flags.
@@ -342,11 +343,15 @@ def scene_retrieval(query_desc, query_kp, db_desc, db_kp, seg_offsets, ratio=0.8
     [18,2], `db_poses` [nimg,18,2] (float64) and `query_size` = (width, height) of the query image the scene score of
     urban_scene.match_scene_multi (perspective correction + affine fit of pose and 5 background matches,
     urban_scene.py:80-145) is added as `score`: +inf where the homography is missing or fails validate_homography,
-    to be compared with thresholds.AFFINE_TRANS_WHOLE_DISTANCE (matching.py:75)."""
+    to be compared with thresholds.AFFINE_TRANS_WHOLE_DISTANCE (matching.py:75).
+    `image_index0`: index of this call's first image in the whole database (a database streamed in runs of images draws
+    the RANSAC samples of the one-call run: the sample table is keyed on the image's global index)."""
     score, best = engine.knn2_hamming_segmented(query_desc, db_desc, seg_offsets, ratio, want_best_idx=True)
     offs, src, dst, sel = engine.segment_matches(best, score, query_kp, db_kp, min_match)
-    H, mask, ninl, _ = engine.ransac_homography_batch(src, dst, offs, thresh, nhyp, confidence, seed, sampler=sampler)
-    H2, _, _, _ = engine.ransac_homography_batch(dst, src, offs, thresh, nhyp, confidence, seed, sampler=sampler)
+    H, mask, ninl, _ = engine.ransac_homography_batch(src, dst, offs, thresh, nhyp, confidence, seed, sampler=sampler,
+                                                      pair_index0=image_index0)
+    H2, _, _, _ = engine.ransac_homography_batch(dst, src, offs, thresh, nhyp, confidence, seed, sampler=sampler,
+                                                 pair_index0=image_index0)
     valid = engine.validate_homography_batch(H)
     out = {"n_matches": score, "n_inliers": ninl, "H": H, "H2": H2, "valid": valid, "pair_offsets": offs, "src": src,
            "dst": dst, "mask": mask, "sel": sel}

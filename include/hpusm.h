@@ -40,11 +40,13 @@ extern "C" {
 #define HPUSM_L2_AUTO 0   /* tensor-core path; engine chosen from the data (u8 integer MMA, else bf16 exact-int, else
                              hi/lo split); reads a 4-byte flag back per decision, i.e. synchronises the stream      */
 #define HPUSM_L2_SIMT 1   /* exact FP32 CUDA-core brute force (cross-check / tiny inputs)             */
-#define HPUSM_L2_TC_INT 2 /* tcgen05, bf16 operands, caller asserts integer values in [0,256]         */
+#define HPUSM_L2_TC_INT 2 /* tcgen05, bf16 operands, integer values in [0,256] (checked on the device: a violation leaves
+                             every idx at -1 and is reported by hpusm_async_status())                                   */
 #define HPUSM_L2_TC_SPLIT 3 /* tcgen05, hi/lo bf16 split (general float), top-4 + verified FP32 re-rank; synchronises
                                the stream once (count of rows sent to the exact fallback)                          */
 #define HPUSM_L2_TC_I8 4  /* tcgen05 kind::i8, u8 operands, s32 accumulation: integer values in [0,255] and squared
-                             norms below 4,000,000 (checked on the device; HPUSM_ERR_UNSUPPORTED otherwise)         */
+                             norms below 4,000,000.  Fully asynchronous: the range check runs on the device and gates
+                             the sweep there; a violation leaves every idx at -1 and is reported by hpusm_async_status() */
 
 int hpusm_version(void);
 const char* hpusm_last_error(void);
@@ -52,6 +54,10 @@ const char* hpusm_last_error(void);
 int hpusm_device_count(void);
 /* Running count of kernels this library launched from the calling process (for bench `gpu_launches`). */
 int64_t hpusm_launch_count(void);
+/* Entry points that stay asynchronous where a data-dependent precondition can only be checked on the device (explicit
+ * HPUSM_L2_TC_I8) record a violation in a pinned host word instead of reading a flag back.  Call after synchronising the
+ * stream: returns HPUSM_OK or the recorded HPUSM_ERR_* code (and clears it); the affected call's outputs are all idx -1. */
+int hpusm_async_status(void);
 
 /* Event bracketing of the dominant kernel of each path (the kNN sweep, the RANSAC scoring kernel, the pose
  * kernel), for roofline accounting: while enabled every such launch is bracketed by two CUDA events on its
@@ -93,9 +99,9 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
  *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512.
  *   The tensor-core engines are built for d == 128 (SIFT); HPUSM_L2_AUTO takes the exact FP32 engine for other
  *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 return HPUSM_ERR_UNSUPPORTED there.
- *   HPUSM_L2_TC_INT trusts the caller that every value is an integer with |v| <= 256;
+ *   HPUSM_L2_TC_INT / HPUSM_L2_TC_I8 never synchronise: their value-range check runs on the device (see hpusm_async_status);
  *   HPUSM_L2_AUTO checks the value range on the device: integers in [0,255] (what OpenCV SIFT emits) run on the u8
- *   integer tensor pipe, other integers with |v| <= 256 on the bf16 engine, anything else on the split engine, whose
+ *   integer tensor pipe, integers in [0,256] on the bf16 engine, anything else (mixed signs included) on the split engine, whose
  *   answer is the exact FP32 one as well (candidate lists are proven complete or the row is redone by the FP32 engine).
  *   idx  [nq][2] int32 as above.
  *   dist [nq][2] float32 = sqrtf( sum_k (q_k - t_k)^2 ), the sum taken in FP32 in increasing k with
@@ -226,12 +232,18 @@ int hpusm_procrustes_batch(const double* X, const double* Y, int64_t n, int npts
  *   match [n] uint8, score [n] float32 (= error_score, single_person.py:184).
  *   detail (optional, NULL to skip) [n][DETAIL] float64: torso/legs/face max distance, shoulder
  *   distance, rot torso, rot legs, then the three 3x3 A matrices and the (22,2) transformed input,
- *   HPUSM_POSE_DETAIL doubles per pose. */
+ *   HPUSM_POSE_DETAIL doubles per pose.
+ *   ws (optional): hpusm_pose_match_workspace_bytes(n).  With a workspace (and detail == NULL, rotation thresholds
+ *   below 86 degrees) the database is swept by an FP32 fast path that certifies its own decisions: a pose whose
+ *   comparisons fall inside the FP32 error bands, whose part fits are ill conditioned or which needs one of the
+ *   reference's corner cases is redone by the exact FP64 kernel, so `match` is the FP64 answer for every pose and
+ *   `score` agrees with it to 2e-6.  ws == NULL: the exact FP64 kernel for every pose. */
 #define HPUSM_POSE_JOINTS 18
 #define HPUSM_POSE_DETAIL (8 + 27 + 44)
+size_t hpusm_pose_match_workspace_bytes(int64_t n);
 int hpusm_pose_match_batch(const float* query, const float* db, int64_t n, int query_is_model,
                            const double* thresholds, uint8_t* match, float* score, double* detail,
-                           void* stream);
+                           void* ws, size_t ws_bytes, void* stream);
 
 /* Same with float64 poses (the reference's own dtype); used by the drop-in single_person.match_single. */
 int hpusm_pose_match_batch_f64(const double* query, const double* db, int64_t n, int query_is_model,
@@ -276,11 +288,28 @@ int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t
 int hpusm_pose_topk_merge(const float* cand_score, const int64_t* cand_index, int64_t count, int k, float* top_score,
                           int64_t* top_index, void* stream);
 
+/* --------------------------------------------------------------------------------------------------
+ * ORB description (the step in front of K2): cv2.ORB.compute for given keypoints, bit for bit.
+ * Replaces the description half of detector.detectAndCompute (urbanscene/urban_scene.py:31-32) for the reference's ORB
+ * (features.py:19-20: scaleFactor 1.2, 8 levels, WTA_K 2, patchSize 31); detection stays with OpenCV.
+ *   img [height][pitch] uint8 grayscale (device).  The smoothed pyramid is built in `ws`
+ *   (hpusm_orb_workspace_bytes): level L = INTER_LINEAR_EXACT resize of level L-1, each level through ORB's 7x7 Gaussian.
+ *   kp_lxy [n][3] int32: octave, and the keypoint centre in that level, (cvRound(pt.x * s), cvRound(pt.y * s)) with
+ *   s = 1.f / (float)pow(scale_factor, octave); kp_cs [n][2] float32: cos and sin of angle * pi/180 (computed on the host,
+ *   where the keypoints come from).  desc [n][32] uint8 stays on the device and feeds hpusm_knn2_hamming directly. */
+size_t hpusm_orb_workspace_bytes(int width, int height, int nlevels, double scale_factor);
+int hpusm_orb_compute(const uint8_t* img, int width, int height, int64_t pitch, int nlevels, double scale_factor,
+                      const int32_t* kp_lxy, const float* kp_cs, int64_t n, uint8_t* desc, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* Integer-pipe micro-benchmarks: every thread issues `iters` POPC.32 (resp. LOP3) in 8 independent chains; returns
  * nothing useful in `sink`.  bench.py uses them as the measured denominators of the Hamming roofline. */
 int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
 /* Same for LOP3 on the ALU pipe (the Hamming kernel issues 16 LOP3 + 4 POPC per 256-bit pair). */
 int hpusm_microbench_lop3(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
+/* FP32 pipe: every thread issues `iters` fused multiply-adds in 8 independent chains; packed != 0: fma.rn.f32x2 (two FMAs
+ * per instruction).  bench.py uses it as the measured denominator of the RANSAC scoring roofline. */
+int hpusm_microbench_ffma(int packed, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
 /* Issue rate of the max-scan instructions the fused top-2 epilogues of K1 are made of.
  * op 0: 3-input s32 max, 1: 3-input f32 max, 2: 2-input s32 max, 3: 2-input f32 max. */
 int hpusm_microbench_minmax(int op, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);

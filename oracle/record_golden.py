@@ -258,6 +258,52 @@ def record_validate_homography():
     save("validate_homography.npz", H=Hs, valid=valid)
 
 
+def _reference_orb():
+    detector, _ = ref_features.init_feature("orb")  # features.py:19-20: nfeatures=100000, 1.2, 8 levels, WTA_K=2, FAST score
+    return detector
+
+
+def record_orb_pattern():
+    """OpenCV's 256-pair ORB test pattern, read off the binary: one keypoint at angle 0 on a black image with a single
+    pixel of value 11 (the 7x7 Gaussian leaves exactly one pixel of value 1) sets the bits whose SECOND point is that
+    pixel; white image / pixel 244 gives the FIRST points.  Saved as [256, 4] = (x0, y0, x1, y1)."""
+    orb = _reference_orb()
+    A = np.full((256, 2), 99, np.int32)
+    B = np.full((256, 2), 99, np.int32)
+    for py in range(-20, 21):
+        for px in range(-20, 21):
+            for inv in (False, True):
+                im = np.full((200, 200), 255, np.uint8) if inv else np.zeros((200, 200), np.uint8)
+                im[100 + py, 100 + px] = 244 if inv else 11
+                _, d = orb.compute(im, [cv2.KeyPoint(100.0, 100.0, 31.0, 0.0, 1.0, 0, -1)])
+                for i in np.nonzero(np.unpackbits(d[0], bitorder="little"))[0]:
+                    tgt = A if inv else B
+                    assert tgt[i, 0] == 99
+                    tgt[i] = (px, py)
+    assert (A != 99).all() and (B != 99).all()
+    np.save(os.path.join(OUT, "orb_pattern.npy"), np.concatenate([A, B], 1).astype(np.int8))
+    print("orb_pattern.npy", np.abs(A).max(), np.abs(B).max())
+
+
+ORB_FIXTURES = ["pisa7.jpg", "taj1.jpg", "pisa2.jpg"]
+
+
+def record_orb_descriptors():
+    """detector.detectAndCompute (urban_scene.py:31-32) with the reference's ORB on three img/ fixtures: the grayscale image
+    (the GPU box has no /root/reference), every keypoint's (pt, octave, angle) and its descriptor."""
+    orb = _reference_orb()
+    arrays = {}
+    for k, name in enumerate(ORB_FIXTURES):
+        img = cv2.imread(os.path.join(REF, "img", name), 0)
+        kp, desc = orb.detectAndCompute(img, None)
+        kp2, desc2 = orb.compute(img, kp)
+        assert np.array_equal(desc, desc2) and len(kp2) == len(kp)
+        arrays.update({"img_%d" % k: img, "pt_%d" % k: np.float32([q.pt for q in kp]),
+                       "octave_%d" % k: np.int32([q.octave for q in kp]), "angle_%d" % k: np.float32([q.angle for q in kp]),
+                       "desc_%d" % k: desc})
+    save("orb_descriptors.npz", names=np.array(ORB_FIXTURES), **arrays)
+
+
 def load_fixture_poses():
     poses, names = [], []
     for f in sorted(glob.glob(os.path.join(REF, "json_data", "*.json"))):
@@ -549,7 +595,8 @@ if __name__ == "__main__":
     for fn in (lambda: record_scene_pair("pisa1_pisa2", "pisa1.jpg", "pisa2.jpg"), record_knn_synthetic, record_ransac_cv2,
                record_pose, record_multi_person, record_json_parser, record_scene_score, record_scene_pairs_sift_extra,
                record_scene_pair_orb_extra, record_multi_person_match, record_scene_score_single, record_ransac_real_pairs,
-               record_ransac_synth_cv2, record_validate_homography):
+               record_ransac_synth_cv2, record_validate_homography, record_orb_pattern,
+               record_orb_descriptors):
         name = getattr(fn, "__name__", "record_scene_pair")
         if not only or name in only or (name == "<lambda>" and "record_scene_pair" in only):
             fn()

@@ -135,6 +135,25 @@ print("OK")
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
 
 
+def test_packed_image_database_round_trip(hpusm, tmp_path):
+    """imagedb.pack_arrays / ImageDB: ragged images, an image without keypoints, 61-byte rows padded to 64."""
+    rng = np.random.default_rng(2)
+    counts = [5, 0, 17, 1]
+    descs = [rng.integers(0, 256, (c, 61), dtype=np.uint8) if c else None for c in counts]
+    kps = [rng.uniform(0, 500, (c, 2)).astype(np.float32) for c in counts]
+    path = str(tmp_path / "img.hpusm")
+    assert hpusm.imagedb.pack_arrays(descs, kps, path, names=["a", "b", "c", "d"], sizes=[(10, 20)] * 4) == (4, 23)
+    db = hpusm.imagedb.ImageDB(path)
+    assert len(db) == 4 and db.n_rows == 23 and db.width == 64 and db.names == ["a", "b", "c", "d"]
+    np.testing.assert_array_equal(db.seg_offsets, [0, 5, 5, 22, 23])
+    d2, k2 = db.image(2)
+    np.testing.assert_array_equal(d2[:, :61], descs[2])
+    assert not d2[:, 61:].any()
+    np.testing.assert_array_equal(k2, kps[2])
+    assert db.image(1)[0].shape == (0, 64) and tuple(db.sizes[3]) == (10, 20)
+    assert [c[:2] for c in db.chunks(3)] == [(0, 3), (3, 4)]
+
+
 def test_binary_descriptor_padding():
     """AKAZE's 61-byte descriptors are zero-padded to the kernel's 64-byte rows (Hamming distances unchanged)."""
     import importlib

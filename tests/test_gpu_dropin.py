@@ -141,6 +141,26 @@ def test_bfmatcher_akaze_width_and_flann_names(mods):
     assert isinstance(matcher, ft.BFMatcher) and matcher.normType == ft.NORM_HAMMING
 
 
+def test_orb_detector_dropin_equals_cv2(mods):
+    """init_feature('orb-flann') (the name the reference's drivers pass) hands out a detector whose detectAndCompute gives
+    cv2's keypoints and, from the GPU, cv2's descriptors bit for bit (urban_scene.py:31-32)."""
+    cv2 = pytest.importorskip("cv2")
+    ft = mods["urbanscene.features"]
+    detector, matcher = ft.init_feature("orb-flann")
+    assert isinstance(detector, ft.OrbGpu)
+    ref = cv2.ORB_create(nfeatures=100000, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                         scoreType=cv2.ORB_FAST_SCORE, patchSize=31)
+    g = load_golden("orb_descriptors.npz")
+    for k in (0, 1):
+        img = g["img_%d" % k]
+        kp, desc = detector.detectAndCompute(img, None)
+        kp_ref, desc_ref = ref.detectAndCompute(img, None)
+        assert [q.pt for q in kp] == [q.pt for q in kp_ref]
+        np.testing.assert_array_equal(desc, desc_ref)
+        np.testing.assert_array_equal(desc, g["desc_%d" % k])
+    assert detector.getNLevels() == 8  # attribute access falls through to the OpenCV detector
+
+
 def test_transformation_functions(mods):
     tr = mods["urbanscene.transformation"]
     g = load_golden("perspective_transform.npz")

@@ -4,11 +4,13 @@ recorded from the reference.  Needs a B200: run with `-m gpu`.
 Bars (BASELINE.json north_star): match indices bit-exact for Hamming and for L2 after the FP32 re-rank
 (ties within 1e-5 relative distance tolerated for general floats); homographies / transforms within 1e-4;
 inlier sets identical under the shared hypothesis seed."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden
+from conftest import load_golden, ROOT
 from oracle import knn_oracle, pose_oracle, ransac_oracle
 
 pytestmark = pytest.mark.gpu
@@ -228,12 +230,15 @@ def test_l2_i8_fuzz_against_fp32_engine(hpusm, cuda_device):
 
 def test_l2_auto_engine_selection(hpusm, cuda_device):
     """HPUSM_L2_AUTO: u8 engine for integers in [0,255] with bounded norms, bf16 exact-int engine for other integers
-    with |v| <= 256, split engine for the rest; HPUSM_L2_TC_I8 on data it cannot hold is an error, not a wrong answer."""
+    in [0,256], split engine for the rest (mixed signs included).  The explicit integer engines never synchronise: on
+    data they cannot hold the device-side check leaves every idx at -1 and hpusm_async_status() reports it after the
+    next synchronisation -- an error, not a wrong answer."""
     rng = np.random.default_rng(11)
     E = hpusm.engine
     cases = [
         (rng.integers(0, 256, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_I8),
-        (rng.integers(-9, 10, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_INT),      # negative query values
+        (rng.integers(-9, 10, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_SPLIT),    # negative query values
+        (rng.integers(0, 257, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_INT),      # a value of 256
         (rng.integers(0, 100, (300, 128)), rng.integers(200, 256, (900, 128)), E.L2_TC_INT),    # ||t||^2 > 4e6
         (rng.integers(0, 100, (300, 128)) + 0.5, rng.integers(0, 100, (900, 128)), E.L2_TC_SPLIT),
     ]
@@ -247,9 +252,17 @@ def test_l2_auto_engine_selection(hpusm, cuda_device):
         else:
             np.testing.assert_array_equal(idx.cpu().numpy(), ri)
             np.testing.assert_array_equal(dist.cpu().numpy(), rd)
-        if want != E.L2_TC_I8:
-            with pytest.raises(Exception, match="TC_I8"):
-                hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=E.L2_TC_I8)
+        assert E.async_status() == 0
+        for explicit in (E.L2_TC_I8, E.L2_TC_INT):
+            ii, dd = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=explicit)
+            torch.cuda.synchronize()
+            holds = want == E.L2_TC_I8 or (want == E.L2_TC_INT and explicit == E.L2_TC_INT)
+            if holds:
+                assert E.async_status() == 0
+                np.testing.assert_array_equal(ii.cpu().numpy(), ri)
+            else:
+                assert E.async_status() == -4 and E.async_status() == 0   # HPUSM_ERR_UNSUPPORTED, reported once
+                assert bool((ii == -1).all())
 
 
 @pytest.mark.parametrize("mode", L2_MODES)
@@ -338,6 +351,57 @@ def test_l2_auto_equals_simt_at_scale(hpusm, cuda_device):
     ib, db_ = hpusm.knn2_l2(q, t, mode=hpusm.engine.L2_SIMT)
     assert torch.equal(ia, ib) and torch.equal(da, db_)
     assert (ia[:1000, 0].cpu() == torch.arange(5000, 6000)).all()
+
+
+# ---- ORB description (the step in front of K2) -----------------------------------------------------------------------------
+def test_orb_compute_is_cv2_orb_compute(hpusm, cuda_device):
+    """hpusm_orb_compute against the reference detector's own descriptors (cv2.ORB.compute, features.py:19-20) on three
+    img/ fixtures: every bit of every descriptor on all 8 pyramid levels; the smoothed pyramid against the oracle; and
+    the descriptors feed knn2_hamming without leaving the device."""
+    from oracle import orb_oracle
+    g = load_golden("orb_descriptors.npz")
+    assert np.array_equal(np.load(os.path.join(ROOT, "tests", "golden", "orb_pattern.npy")).astype(np.int8),
+                          np.loadtxt(os.path.join(ROOT, "humanpose-and-urbanscene-matching_b200", "csrc", "orb_pattern.inc"),
+                                     delimiter=",", comments="//", usecols=range(4 * 4)).reshape(256, 4).astype(np.int8))
+    descs = []
+    for k, name in enumerate(g["names"]):
+        img, pt, octave, angle, want = g["img_%d" % k], g["pt_%d" % k], g["octave_%d" % k], g["angle_%d" % k], g["desc_%d" % k]
+        lxy, cs = hpusm.engine.orb_keypoint_params(pt, octave, angle)
+        ocx, ocy, oa, ob = orb_oracle.keypoint_params(pt, octave, angle)
+        assert np.array_equal(lxy[:, 1], ocx) and np.array_equal(lxy[:, 2], ocy) and np.array_equal(cs[:, 0], oa)
+        desc = hpusm.engine.orb_compute(dev(img, cuda_device), dev(lxy, cuda_device), dev(cs, cuda_device))
+        np.testing.assert_array_equal(desc.cpu().numpy(), want, err_msg=str(name))
+        descs.append(desc)
+    assert sum(len(d) for d in descs) > 10000
+    idx, dist = hpusm.knn2_hamming(descs[2], descs[0])         # pisa2 vs pisa7, straight from the descriptor kernel
+    ri, rd = knn_oracle.knn2_hamming(g["desc_2"], g["desc_0"])
+    np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+    np.testing.assert_array_equal(dist.cpu().numpy(), rd)
+
+
+def test_orb_compute_odd_shapes(hpusm, cuda_device):
+    """Images whose sizes are not multiples of the kernels' tiles, keypoints on every level incl. close to the border
+    margin OpenCV keeps (31 px): the device descriptors equal the oracle's."""
+    from oracle import orb_oracle
+    rng = np.random.default_rng(8)
+    for (h, w) in ((97, 131), (240, 333), (480, 641)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        img = (0.5 * img + 0.5 * np.roll(img, 3, 1)).astype(np.uint8)
+        pts, octs = [], []
+        for level in range(8):
+            lw, lh = orb_oracle.level_size(w, h, level)
+            if lw <= 64 or lh <= 64:
+                continue
+            s = float(orb_oracle.level_scale(level))
+            m = 40
+            xs = rng.uniform(31, lw - 32, m) * s
+            ys = rng.uniform(31, lh - 32, m) * s
+            pts.append(np.stack([xs, ys], 1)); octs.append(np.full(m, level))
+        pts, octs = np.concatenate(pts).astype(np.float32), np.concatenate(octs).astype(np.int32)
+        angs = rng.uniform(0, 360, len(pts)).astype(np.float32)
+        lxy, cs = hpusm.engine.orb_keypoint_params(pts, octs, angs)
+        desc = hpusm.engine.orb_compute(dev(img, cuda_device), dev(lxy, cuda_device), dev(cs, cuda_device))
+        np.testing.assert_array_equal(desc.cpu().numpy(), orb_oracle.compute(img, pts, octs, angs))
 
 
 # ---- K3 RANSAC --------------------------------------------------------------------------------------------
@@ -553,6 +617,38 @@ def test_pose_match_single_reference(hpusm, cuda_device):
     assert n_tight > 600 and n_ref > 600 and n_flip <= 2
 
 
+@pytest.mark.parametrize("qim", [True, False])
+def test_pose_fast_path_equals_exact_kernel(hpusm, cuda_device, qim):
+    """hpusm_pose_match_batch with a workspace (FP32 fast path + exact FP64 kernel for what it cannot certify) against the
+    exact FP64 kernel on every pose: identical decisions on all 1 M poses (missing joints, noise levels 0-15 px), scores
+    within 2e-6; and against the oracle on a slice.  Includes the reference's corner cases (no joints, zero extent,
+    negative coordinates), which the fast path must hand over."""
+    db = hpusm.synth.pose_database(hpusm.synth.CANONICAL_POSE, 1_000_000, seed=21)
+    db[0] = 0
+    db[1, :, 0] = 100.0
+    db[2, 3] = [-5.0, 40.0]
+    db[3, 2:] = 0
+    q = hpusm.synth.CANONICAL_POSE.astype(np.float32)
+    dq, ddb = dev(q, cuda_device), dev(db, cuda_device)
+    m_fast, s_fast = hpusm.pose_match_batch(dq, ddb, qim)
+    m_exact, s_exact = hpusm.pose_match_batch(dq, ddb, qim, exact=True)
+    assert torch.equal(m_fast, m_exact)
+    ok = torch.isfinite(s_exact)
+    assert torch.equal(torch.isfinite(s_fast), ok)
+    assert float((s_fast[ok] - s_exact[ok]).abs().max()) < 2e-6
+    k = 3000
+    rm, rs = pose_oracle.match_single_batch(q.astype(np.float64), db[:k].astype(np.float64), qim)
+    np.testing.assert_array_equal(m_fast[:k].cpu().numpy().astype(bool), rm)
+    np.testing.assert_allclose(s_fast[:k].cpu().numpy(), rs, rtol=1e-5, atol=2e-6, equal_nan=True)
+    # a query with a negative coordinate or an undetected joint: same contract
+    for qq in (np.where(np.arange(18)[:, None] == 6, 0.0, q).astype(np.float32), (q - np.float32([300, 0])).astype(np.float32)):
+        a = hpusm.pose_match_batch(dev(qq, cuda_device), ddb[:200000], qim)
+        b = hpusm.pose_match_batch(dev(qq, cuda_device), ddb[:200000], qim, exact=True)
+        assert torch.equal(a[0], b[0])
+        fin = torch.isfinite(b[1])
+        assert float((a[1][fin] - b[1][fin]).abs().max()) < 2e-6
+
+
 def test_pose_topk(hpusm, cuda_device):
     rng = np.random.default_rng(4)
     n = 200000
@@ -649,6 +745,27 @@ def test_scene_retrieval_fused_stage(hpusm, cuda_device):
     assert got["valid"][planted[0]] == 1 and got["valid"][planted[1]] == 1
     assert got["n_inliers"][planted[0]] >= 100 and got["n_inliers"][planted[2]] == 0
     assert np.isnan(got["H"][planted[2]]).all()
+
+
+@pytest.mark.parametrize("sampler", ["counter", "cv2"])
+def test_imagedb_streamed_retrieval_equals_resident(hpusm, cuda_device, tmp_path, sampler):
+    """Packed image database (descriptors + keypoints) streamed from disk in runs of whole images through
+    scene_retrieval == one resident scene_retrieval call over the whole database, bit for bit."""
+    q_desc, q_kp, db_desc, db_kp, offs, planted = _scene_database(hpusm)
+    nimg = len(offs) - 1
+    path = str(tmp_path / "images.hpusm")
+    descs = [db_desc[offs[i]:offs[i + 1]] for i in range(nimg)]
+    kps = [db_kp[offs[i]:offs[i + 1]] for i in range(nimg)]
+    assert hpusm.imagedb.pack_arrays(descs, kps, path) == (nimg, int(offs[-1]))
+    idb = hpusm.imagedb.ImageDB(path)
+    got = idb.retrieve(q_desc, q_kp, device=cuda_device, images_per_chunk=3, nhyp=500, seed=5, sampler=sampler)
+    want = hpusm.retrieval.scene_retrieval(dev(q_desc, cuda_device), dev(q_kp, cuda_device), dev(db_desc, cuda_device),
+                                           dev(db_kp, cuda_device), dev(offs, cuda_device), nhyp=500, seed=5, sampler=sampler)
+    for key in ("n_matches", "n_inliers", "valid"):
+        np.testing.assert_array_equal(got[key], want[key].cpu().numpy(), err_msg=key)
+    for key in ("H", "H2"):
+        np.testing.assert_array_equal(np.nan_to_num(got[key], nan=-7.0), np.nan_to_num(want[key].cpu().numpy(), nan=-7.0), err_msg=key)
+    assert got["valid"][planted[0]] == 1 and got["valid"][planted[1]] == 1
 
 
 def test_posedb_streaming_search(hpusm, cuda_device, tmp_path):

@@ -306,3 +306,41 @@ def test_dropin_validate_homography_matches_reference():
     g = load_golden("validate_homography.npz")
     got = np.array([bool(ft.validate_homography(H)) for H in g["H"]])
     np.testing.assert_array_equal(got, g["valid"])
+
+
+def _orb_fixtures():
+    g = load_golden("orb_descriptors.npz")
+    for k, name in enumerate(g["names"]):
+        yield str(name), g["img_%d" % k], g["pt_%d" % k], g["octave_%d" % k], g["angle_%d" % k], g["desc_%d" % k]
+
+
+def test_orb_oracle_reproduces_cv2_descriptors():
+    """oracle/orb_oracle.py (pyramid by INTER_LINEAR_EXACT, 7x7 float Gaussian with OpenCV's FMA order, rotated 256-pair
+    pattern) against the reference detector's own descriptors on three img/ fixtures: every bit of every descriptor."""
+    from oracle import orb_oracle
+    total = 0
+    for name, img, pt, octave, angle, desc in _orb_fixtures():
+        sel = np.arange(0, len(pt), 3) if len(pt) > 4000 else np.arange(len(pt))
+        mine = orb_oracle.compute(img, pt[sel], octave[sel], angle[sel])
+        np.testing.assert_array_equal(mine, desc[sel], err_msg=name)
+        total += len(sel)
+    assert total > 5000
+
+
+def test_orb_oracle_building_blocks_match_cv2():
+    """The restated resize and blur against the cv2 functions themselves (only when cv2 is importable: same image here
+    and on the GPU box)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import orb_oracle
+    for name, img, *_ in _orb_fixtures():
+        h, w = img.shape
+        prev = img
+        for level in range(1, 8):
+            dw, dh = orb_oracle.level_size(w, h, level)
+            want = cv2.resize(prev, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)
+            np.testing.assert_array_equal(orb_oracle.resize_linear_exact(prev, dw, dh), want)
+            prev = want
+        k = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+        np.testing.assert_array_equal(k.ravel()[:4], orb_oracle.GAUSS7)
+        want = cv2.sepFilter2D(img, -1, k, k, borderType=cv2.BORDER_REFLECT_101)
+        np.testing.assert_array_equal(orb_oracle.gaussian_blur7(img), want)
