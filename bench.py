@@ -34,6 +34,15 @@ PKG = "humanpose-and-urbanscene-matching_b200"
 FLOP_PER_PAIR = 256.0  # 2*D, D = 128: norms, top-2 and re-rank are not counted
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %6.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -50,6 +59,8 @@ def parse_args():
     ap.add_argument("--nt", type=int, default=1 << 20, help="database rows PER GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline", default=None, choices=["sift", "orb", "ransac", "pose"],
+                    help="internal: print the CPU baseline of one workload (a fresh process, no CUDA) and exit")
     ap.add_argument("--images", type=int, default=10000, help="orb: database images (2048 descriptors each)")
     ap.add_argument("--pairs", type=int, default=100000, help="ransac: image pairs (2000 matches x 1024 hypotheses each)")
     ap.add_argument("--poses", type=int, default=10_000_000, help="pose: database poses")
@@ -88,15 +99,30 @@ def sift_like_torch(n, seed, device, d=128):
 
 
 def make_workload(nq, nt, rank, device, planted=0.1):
+    """This rank's database shard `t` and the query set `q`, IDENTICAL on every rank (queries are replicated): each rank
+    plants noisy copies of rows of its own shard, and the planted rows of all ranks are exchanged and applied in rank
+    order, so every rank holds the same queries (round 1 planted per rank and the ranks matched slightly different
+    query sets -- found by the on-hardware parity check below)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     t = sift_like_torch(nt, 1000 + rank, device)
     q = sift_like_torch(nq, 7, device)
-    k = int(planted * nq) // max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    k = int(planted * nq) // max(1, world)
     if k:
         g = torch.Generator(device=device).manual_seed(99 + rank)
         qi = torch.randperm(nq, generator=g, device=device)[:k]
         ti = torch.randint(0, nt, (k,), generator=g, device=device)
         noise = torch.round(torch.randn((k, 128), generator=g, device=device) * 4.0)
-        q[qi] = torch.clamp(t[ti] + noise, 0, 255)
+        rows = torch.clamp(t[ti] + noise, 0, 255)
+        if world > 1:
+            import torch.distributed as dist
+            all_qi = torch.empty((world * k,), dtype=qi.dtype, device=device)
+            all_rows = torch.empty((world * k, 128), dtype=rows.dtype, device=device)
+            dist.all_gather_into_tensor(all_qi, qi.contiguous())
+            dist.all_gather_into_tensor(all_rows, rows.contiguous())
+            for r in range(world):
+                q[all_qi[r * k:(r + 1) * k]] = all_rows[r * k:(r + 1) * k]
+        else:
+            q[qi] = rows
     return q, t
 
 
@@ -134,18 +160,19 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows[self.first:] or self.rows[-1:]:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None,
+                "power_w_max": max(pw) if pw else None}
 
 
 # ---- reference CPU path (cv2.BFMatcher.knnMatch + the ratio loop of features.filter_matches) --------------------
@@ -331,10 +358,12 @@ def i8_sustained_peak(hp, device, seconds=2.0):
 
 
 def run_sift(args, rank, world, device, hp):
+    log("sift: weak-scaling pass (resident + end to end)")
     weak = sift_pass(args, rank, world, device, hp, args.nt, rank * args.nt, "weak")
     strong = weak
     if world > 1:
         a, b = hp.retrieval.shard_range(args.nt, rank, world, align=128)
+        log("sift: strong-scaling pass")
         strong = sift_pass(args, rank, world, device, hp, b - a, a, "strong")
     if rank != 0:
         return None
@@ -353,6 +382,7 @@ def run_sift(args, rank, world, device, hp):
     peak_source = "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"
     if mode == "tcgen05-i8-exact-int":
         # MEASURED_PEAKS.json has no INT8 line: the denominator is this GPU's own sustained kind::i8 issue rate, measured now
+        log("sift: sustained kind::i8 issue rate (roofline denominator)")
         peak_tf, peak_clocks = i8_sustained_peak(hp, device)
         peak_source = ("hpusm_microbench_mma(kind::i8) sustained for 2 s in this run: every SM issuing back-to-back 128x256x32 "
                        "u8 MMAs and nothing else (clocks under that load in roofline.peak_clocks)")
@@ -529,28 +559,8 @@ def run_orb(args, rank, world, device, hp):
                        "hbm_GBps_algorithmic": (db.numel() + query.numel()) / (k_ms * 1e-3) / 1e9}
     out["clocks"] = r["clocks"]
     if not args.no_cpu_baseline and world == 1:
-        import cv2
-        cores = cpu_threads()
-        nim = 64
-        qn, dn = hq.numpy(), hdb.numpy()[:nim * per]
-        m = cv2.BFMatcher(cv2.NORM_HAMMING)
-        t0 = time.perf_counter()
-        for i in range(nim):
-            raw = m.knnMatch(qn, trainDescriptors=dn[i * per:(i + 1) * per], k=2)
-            sum(1 for x in raw if len(x) == 2 and x[0].distance < x[1].distance * 0.8)
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": per * per * nim / dt, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                               "sample": "%d database images, cv2.BFMatcher(NORM_HAMMING).knnMatch k=2 + ratio loop per image, %.1f s" % (nim, dt)}
+        out["cpu_baseline"] = cpu_baseline_subprocess("orb")
     return out
-
-
-def _cv2_ransac_pairs(job):
-    import cv2
-    src, dst = job
-    cv2.setNumThreads(1)
-    for s, d in zip(src, dst):
-        cv2.findHomography(s.reshape(-1, 1, 2), d.reshape(-1, 1, 2), cv2.RANSAC, 5.0, maxIters=1024, confidence=1 - 1e-9)
-    return len(src)
 
 
 def run_ransac(args, rank, world, device, hp):
@@ -638,24 +648,8 @@ def run_ransac(args, rank, world, device, hp):
                        "hbm_GBps_algorithmic": src.numel() * 8 / (k_ms * 1e-3) / 1e9, "reprojections_per_s": evals / (k_ms * 1e-3)}
     out["clocks"] = r["clocks"]
     if not args.no_cpu_baseline and world == 1:
-        import multiprocessing as mpx
-        cores = os.cpu_count() or 1
-        npair = 16 * cores
-        sn, dn = hs.numpy()[:npair * K].reshape(npair, K, 2), hd.numpy()[:npair * K].reshape(npair, K, 2)
-        jobs = [(sn[i::cores], dn[i::cores]) for i in range(cores)]
-        with mpx.get_context("fork").Pool(cores) as pool:
-            t0 = time.perf_counter()
-            pool.map(_cv2_ransac_pairs, jobs)
-            dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": npair * nhyp / dt, "unit": "hyps/s", "cores": cores, "kind": "reference",
-                               "sample": "%d pairs, cv2.findHomography(RANSAC, 5.0, maxIters=1024, confidence=1-1e-9) in a %d-process pool, %.1f s" % (npair, cores, dt)}
+        out["cpu_baseline"] = cpu_baseline_subprocess("ransac")
     return out
-
-
-def _pose_chunk(job):
-    from oracle import pose_oracle
-    q, db = job
-    return pose_oracle.match_single_batch(q, db)[0].sum()
 
 
 def run_pose(args, rank, world, device, hp):
@@ -719,25 +713,115 @@ def run_pose(args, rank, world, device, hp):
                        "kernel_launches": int(r["kernel_n"]), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk else "fallback 6650 GB/s"}
     out["clocks"] = r["clocks"]
     if not args.no_cpu_baseline and world == 1:
-        import multiprocessing as mpx
-        cores = os.cpu_count() or 1
-        ns = 1500 * cores
-        qn, dn = query.cpu().numpy().astype(np.float64), hdb.numpy()[:ns].astype(np.float64)
+        out["cpu_baseline"] = cpu_baseline_subprocess("pose")
+    return out
+
+
+# ---- CPU baselines: the reference's own CPU path, each in a FRESH process -------------------------------------------
+# (A process that has initialised CUDA, started OpenCV's thread pool and an nvidia-smi reader thread must not fork worker
+# pools: the children inherit locked mutexes and hang.  The baselines therefore run in a clean interpreter, with a
+# hard timeout, and only report a number.)
+def cpu_baseline_subprocess(workload, extra=(), timeout=240):
+    log("cpu baseline of %s in a fresh process" % workload)
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-baseline", workload] + list(extra)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        if res.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": "cpu baseline exited %d: %s" % (res.returncode, res.stderr[-300:])}
+    except subprocess.TimeoutExpired:
+        return {"error": "cpu baseline timed out after %d s" % timeout}
+
+
+def _cv2_ransac_pairs(job):
+    import cv2
+    src, dst = job
+    cv2.setNumThreads(1)
+    for s, d in zip(src, dst):
+        cv2.findHomography(s.reshape(-1, 1, 2), d.reshape(-1, 1, 2), cv2.RANSAC, 5.0, maxIters=1024, confidence=1 - 1e-9)
+    return len(src)
+
+
+def _pose_chunk(job):
+    from oracle import pose_oracle
+    q, db = job
+    return pose_oracle.match_single_batch(q, db)[0].sum()
+
+
+def run_cpu_baseline(args):
+    """`bench.py --cpu-baseline W`: times the reference's CPU implementation of workload W on a bounded sample, all host cores."""
+    synth = load_synth()
+    cores = os.cpu_count() or 1
+    w = args.cpu_baseline
+    if w == "sift":
+        threads = cpu_threads()
+        ns = pick_cpu_sample(args.nt, args.cpu_sample)
+        qn, tn = synth.sift_like(ns, args.nt, seed=7, planted=0.1)
+        if args.descriptors == "float":
+            qn, tn = qn * np.float32(1.0137), tn * np.float32(1.0137)
+        reference_step(qn[:max(16, ns // 8)], tn)
+        t0 = time.perf_counter()
+        reference_step(qn, tn)
+        dt = time.perf_counter() - t0
+        return {"value": ns * args.nt / dt, "unit": "pairs/s", "cores": threads, "kind": "reference",
+                "sample": "%d queries x %d db rows, cv2.BFMatcher(NORM_L2).knnMatch k=2 + ratio loop "
+                          "(features.py:59,:45-55), %.1f s" % (ns, args.nt, dt)}
+    if w == "orb":
+        import cv2
+        threads = cpu_threads()
+        per, nim = 2048, 1024
+        rng = np.random.default_rng(1)
+        qn = rng.integers(0, 256, (per, 32), dtype=np.uint8)
+        dn = rng.integers(0, 256, (nim * per, 32), dtype=np.uint8)
+        m = cv2.BFMatcher(cv2.NORM_HAMMING)
+        m.knnMatch(qn, trainDescriptors=dn[:per], k=2)
+        t0 = time.perf_counter()
+        for i in range(nim):
+            raw = m.knnMatch(qn, trainDescriptors=dn[i * per:(i + 1) * per], k=2)
+            sum(1 for x in raw if len(x) == 2 and x[0].distance < x[1].distance * 0.8)
+        dt = time.perf_counter() - t0
+        return {"value": per * per * nim / dt, "unit": "pairs/s", "cores": threads, "kind": "reference",
+                "sample": "%d database images x 2048 descriptors, cv2.BFMatcher(NORM_HAMMING).knnMatch k=2 + ratio loop per image, %.1f s" % (nim, dt)}
+    import multiprocessing as mpx
+    if w == "ransac":
+        K, nhyp, npair = 2000, 1024, 96 * cores
+        src, dst, _ = synth.ransac_batch(npair, K, 0.3, seed=2)
+        sn, dn = src.reshape(npair, K, 2), dst.reshape(npair, K, 2)
+        jobs = [(sn[i::cores], dn[i::cores]) for i in range(cores)]
+        with mpx.get_context("fork").Pool(cores) as pool:
+            t0 = time.perf_counter()
+            pool.map(_cv2_ransac_pairs, jobs)
+            dt = time.perf_counter() - t0
+        return {"value": npair * nhyp / dt, "unit": "hyps/s", "cores": cores, "kind": "reference",
+                "sample": "%d pairs x 2000 matches, cv2.findHomography(RANSAC, 5.0, maxIters=1024, confidence=1-1e-9: every "
+                          "iteration scores a model) in a %d-process pool, %.1f s" % (npair, cores, dt)}
+    if w == "pose":
+        ns = 15000 * cores
+        qn = synth.CANONICAL_POSE.astype(np.float64)
+        dn = synth.pose_database(synth.CANONICAL_POSE, ns, seed=3).astype(np.float64)
         jobs = [(qn, dn[i::cores]) for i in range(cores)]
         with mpx.get_context("fork").Pool(cores) as pool:
             t0 = time.perf_counter()
             pool.map(_pose_chunk, jobs)
             dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": ns / dt, "unit": "poses/s", "cores": cores, "kind": "port",
-                               "sample": "%d poses, oracle/pose_oracle.match_single (NumPy restatement of single_person.py:80-189) in a %d-process pool, %.1f s" % (ns, cores, dt)}
-    return out
+        return {"value": ns / dt, "unit": "poses/s", "cores": cores, "kind": "port",
+                "sample": "%d poses, oracle/pose_oracle.match_single (NumPy restatement of single_person.py:80-189) in a "
+                          "%d-process pool, %.1f s" % (ns, cores, dt)}
+    raise SystemExit("unknown --cpu-baseline workload %r" % w)
 
 
 def main():
     args = parse_args()
+    # a wedged run must fail loudly, not sit on the GPU box until somebody's limit kills it
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("HPUSM_BENCH_WATCHDOG_S", "1500")), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_baseline:
+        print(json.dumps(run_cpu_baseline(args)), flush=True)
+        return
     if args.impl == "reference":
         out = run_reference(args, rank)
         if out is not None:
@@ -757,20 +841,14 @@ def main():
     else:
         out = run_sift(args, rank, world, device, hp)
         if rank == 0 and not args.no_cpu_baseline and world == 1:
-            cores = cpu_threads()
-            ns = pick_cpu_sample(args.nt, args.cpu_sample)
-            qn, tn = hp.synth.sift_like(ns, args.nt, seed=7, planted=0.1)
-            reference_step(qn[:max(16, ns // 8)], tn)
-            t0 = time.perf_counter()
-            reference_step(qn, tn)
-            dt = time.perf_counter() - t0
-            out["cpu_baseline"] = {"value": ns * args.nt / dt, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                                   "sample": "%d queries x %d db rows, cv2.BFMatcher(NORM_L2).knnMatch k=2 + ratio loop "
-                                             "(features.py:59,:45-55), %.1f s" % (ns, args.nt, dt)}
+            log("sift: cpu baseline")
+            out["cpu_baseline"] = cpu_baseline_subprocess("sift", ["--nt", str(args.nt), "--cpu-sample", str(args.cpu_sample),
+                                                                    "--descriptors", args.descriptors])
         if not args.no_others:
             others = {}
             for name in ("orb", "ransac", "pose"):
                 torch.cuda.empty_cache()
+                log("others: %s" % name)
                 try:
                     res = runners[name](args, rank, world, device, hp)
                 except Exception as exc:  # one workload failing must not cost the headline line
@@ -779,6 +857,7 @@ def main():
                     others[name] = res
             if rank == 0:
                 out["others"] = others
+    log("done")
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -15,7 +15,7 @@ for f in *.cu; do
   for h in *.cuh *.inc ../../include/hpusm.h; do [[ "$h" -nt "$o" ]] && stale=1; done
   if [[ ! -f "$o" || "$f" -nt "$o" || $stale -eq 1 ]]; then
     echo "nvcc $f"
-    "$NVCC" "${FLAGS[@]}" ${HPUSM_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
+    "$NVCC" "${FLAGS[@]}" ${HPUSM_PTXAS_V:+-Xptxas -v} ${HPUSM_EXTRA_FLAGS:-} -c "$f" -o "$o" &
     PIDS+=($!)
   fi
   OBJS+=("$o")

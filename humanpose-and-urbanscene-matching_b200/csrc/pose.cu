@@ -535,10 +535,13 @@ __global__ void pose_query_prep_kernel(const float* __restrict__ query, PoseQuer
 }
 
 constexpr int PF_THREADS = 128;
+#ifndef PF_MIN_BLOCKS
+#define PF_MIN_BLOCKS 5  // 96 registers: measured 0.49 ms per 10 M poses vs 0.55 ms at 4 blocks (120 registers) and 0.57 ms at 6 (80, spills)
+#endif
 
 // thread = database pose.  A pose the FP32 evaluation cannot certify goes to `list` (one atomic per warp) for the exact kernel.
 template <bool QIM>
-__global__ void __launch_bounds__(PF_THREADS)
+__global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS)
 pose_match_fast_kernel(const PoseQueryPrep* __restrict__ prep, const float* __restrict__ db, int64_t n, PoseFastParams prm,
                        uint8_t* __restrict__ match, float* __restrict__ score, int32_t* __restrict__ list,
                        int32_t* __restrict__ list_count) {

@@ -588,23 +588,48 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
     for (int h = tid; h < nhyp; h += RS_THREADS) counts_out[pair * nhyp + h] = counts[h];
   }
 
-  // phase C: replay the sequential loop (exact early-exit semantics), lowest hypothesis wins ties
-  if (best_hyp && tid == 0) {
-    int best = -1, best_c = 3, niters = nhyp;
-    for (int h = 0; h < nhyp && h < niters; ++h) {
+  // phase C: replay the sequential loop (exact early-exit semantics), lowest hypothesis wins ties.  The sequential loop
+  // only ever changes state at a RECORD (a count above every earlier count and above 3), so all threads first mark the
+  // records (slice maxima -> exclusive prefix maximum -> one pass over the slice) in a bit mask, and one thread then walks
+  // the dozen or so set bits instead of all nhyp counts.
+  if (best_hyp) {
+    __shared__ int slice_max[RS_THREADS];
+    unsigned* rec = reinterpret_cast<unsigned*>(hyp_of);  // the compaction list is no longer needed: nhyp ints >= nhyp / 32 words
+    const int per = (nhyp + RS_THREADS - 1) / RS_THREADS;
+    const int h0 = tid * per, h1 = min(nhyp, h0 + per);
+    int mx = 3;
+    for (int h = h0; h < h1; ++h) mx = max(mx, counts[h]);
+    __syncthreads();  // every thread is done reading hyp_of (phase B) before it is reused
+    slice_max[tid] = mx;
+    for (int wd = tid; wd < (nhyp + 31) / 32; wd += RS_THREADS) rec[wd] = 0u;
+    __syncthreads();
+    int run = 3;
+    for (int t = 0; t < tid; ++t) run = max(run, slice_max[t]);  // exclusive prefix maximum (256 broadcast reads)
+    for (int h = h0; h < h1; ++h) {
       const int c = counts[h];
-      if (c > best_c) {
-        best_c = c; best = h;
-        if (confidence > 0.0) niters = update_num_iters(confidence, (double)(K64 - c) / (double)K64, niters);
-      }
+      if (c > run) { run = c; atomicOr(&rec[h >> 5], 1u << (h & 31)); }
     }
-    best_hyp[pair] = best;
-    if (best >= 0) {
-      double sx[4], sy[4], dx[4], dy[4], H[9];
-      (void)hypothesis_points(best, sx, sy, dx, dy);
-      (void)hypothesis_solve(sx, sy, dx, dy, H);
+    __syncthreads();
+    if (tid == 0) {
+      int best = -1, niters = nhyp;
+      for (int wd = 0; wd < (nhyp + 31) / 32 && wd * 32 < niters; ++wd) {
+        unsigned bits = rec[wd];
+        while (bits) {
+          const int h = wd * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (h >= niters) { bits = 0; break; }
+          best = h;
+          if (confidence > 0.0) niters = update_num_iters(confidence, (double)(K64 - counts[h]) / (double)K64, niters);
+        }
+      }
+      best_hyp[pair] = best;
+      if (best >= 0) {
+        double sx[4], sy[4], dx[4], dy[4], H[9];
+        (void)hypothesis_points(best, sx, sy, dx, dy);
+        (void)hypothesis_solve(sx, sy, dx, dy, H);
 #pragma unroll
-      for (int i = 0; i < 9; ++i) best_H[pair * 9 + i] = H[i];
+        for (int i = 0; i < 9; ++i) best_H[pair * 9 + i] = H[i];
+      }
     }
   }
 }

@@ -204,12 +204,13 @@ def segment_matches(best_idx, count, kp_q, kp_t, min_count=16):
     with torch.cuda.device(dev):
         offs = torch.empty((nseg + 1,), dtype=torch.int64, device=dev)
         cap = int(count[count >= int(min_count)].sum().item())  # sizes the outputs (the only host read of the stage)
-        src = torch.empty((cap, 2), dtype=torch.float32, device=dev)
-        dst = torch.empty((cap, 2), dtype=torch.float32, device=dev)
-        sel = torch.empty((cap,), dtype=torch.int32, device=dev)
+        room = max(cap, 1)  # no image above min_count: the ABI still wants non-null outputs
+        src = torch.empty((room, 2), dtype=torch.float32, device=dev)
+        dst = torch.empty((room, 2), dtype=torch.float32, device=dev)
+        sel = torch.empty((room,), dtype=torch.int32, device=dev)
         check(lib.hpusm_segment_matches(_ptr(best_idx), _ptr(count), nseg, nq, _ptr(kp_q), _ptr(kp_t), int(min_count),
                                         _ptr(offs), _ptr(src), _ptr(dst), _ptr(sel), _stream(dev)))
-    return offs, src, dst, sel
+    return offs, src[:cap], dst[:cap], sel[:cap]
 
 
 def validate_homography_batch(H):

@@ -7,7 +7,7 @@ import torch, importlib, sys
 sys.path.insert(0, ".")
 import hpusm
 dev = torch.device("cuda:0")
-for op in ["lop3", "popc", "imax3", "fmax3", "imax", "fmax"]:
+for op in ["lop3", "popc", "imax3", "fmax3", "imax", "fmax", "ffma", "ffma2"]:
     for thr in (128, 512):
         iters = 1 << 16
         blocks = 148 * (1024 // thr)
