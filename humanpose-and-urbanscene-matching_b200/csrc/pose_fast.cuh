@@ -72,9 +72,44 @@ HPUSM_HD float pf_flag(float v) {
 #endif
 }
 HPUSM_HD double pf_flag(double v) { return v > 0.0 ? 1.0 : 0.0; }
-// v * w + (+0): keeps an exact zero non-negative when v < 0 and w == 0
-HPUSM_HD float pf_mul0(float v, float w) { return fmaf(v, w, 0.f); }
-HPUSM_HD double pf_mul0(double v, double w) { return v * w + 0.0; }
+
+// ---- pairs: the x and y of a joint go through the same arithmetic, so they travel as one operand.  On the device a
+// float pair is an aligned register pair and every operation is ONE packed sm_100 instruction (FADD2 / FMUL2 / FFMA2;
+// ptxas folds the broadcasts p2s(v) into the instruction's operand modifiers): half the issue slots of the scalar form.
+// Each half is rounded exactly like the scalar operation.
+struct P2d { double x, y; };
+HPUSM_HD P2d p2(double x, double y) { P2d r; r.x = x; r.y = y; return r; }
+HPUSM_HD P2d p2s(double v) { return p2(v, v); }
+HPUSM_HD double p2x(P2d a) { return a.x; }
+HPUSM_HD double p2y(P2d a) { return a.y; }
+HPUSM_HD P2d p2_add(P2d a, P2d b) { return p2(a.x + b.x, a.y + b.y); }
+HPUSM_HD P2d p2_sub(P2d a, P2d b) { return p2(a.x - b.x, a.y - b.y); }
+HPUSM_HD P2d p2_mul(P2d a, P2d b) { return p2(a.x * b.x, a.y * b.y); }
+HPUSM_HD P2d p2_fma(P2d a, P2d b, P2d c) { return p2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#ifdef __CUDA_ARCH__
+typedef unsigned long long P2f;
+HPUSM_HD P2f p2(float x, float y) { P2f r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+HPUSM_HD P2f p2s(float v) { P2f r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
+HPUSM_HD float p2x(P2f a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
+HPUSM_HD float p2y(P2f a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return hi; }
+HPUSM_HD P2f p2_add(P2f a, P2f b) { P2f r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+HPUSM_HD P2f p2_sub(P2f a, P2f b) { P2f r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+HPUSM_HD P2f p2_mul(P2f a, P2f b) { P2f r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+HPUSM_HD P2f p2_fma(P2f a, P2f b, P2f c) { P2f r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#else
+struct P2f { float x, y; };
+HPUSM_HD P2f p2(float x, float y) { P2f r; r.x = x; r.y = y; return r; }
+HPUSM_HD P2f p2s(float v) { return p2(v, v); }
+HPUSM_HD float p2x(P2f a) { return a.x; }
+HPUSM_HD float p2y(P2f a) { return a.y; }
+HPUSM_HD P2f p2_add(P2f a, P2f b) { return p2(a.x + b.x, a.y + b.y); }
+HPUSM_HD P2f p2_sub(P2f a, P2f b) { return p2(a.x - b.x, a.y - b.y); }
+HPUSM_HD P2f p2_mul(P2f a, P2f b) { return p2(a.x * b.x, a.y * b.y); }
+HPUSM_HD P2f p2_fma(P2f a, P2f b, P2f c) { return p2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+template <typename F> struct PairT;
+template <> struct PairT<float> { typedef P2f T; };
+template <> struct PairT<double> { typedef P2d T; };
 
 constexpr int PF_NJ = 18;
 constexpr int PF_NP = 14;   // joints 0..13 are the ones torso and legs use (face joints 14..17 only enter the scaling)
@@ -121,46 +156,53 @@ struct PfPart {
   bool ok;  // false: not certifiable in FP32 (ill conditioned, too few joints)
 };
 
-// One body part.  (xm, ym) scaled model coordinates, (xi, yi) scaled input coordinates of joints 0..13 (exact 0 for a
-// masked joint on both sides), w[j] = 1 for a joint that takes part, 0 for a masked one, n = number of joints that do.
+// One body part.  M / I: scaled (x, y) of the model / input side of joints 0..13 (exact 0 for a masked joint on both
+// sides), w[j] = 1 for a joint that takes part, 0 for a masked one, n = number of joints that do.
 template <typename F, typename Rows>
-HPUSM_HD PfPart<F> pf_part(const F (&xm)[PF_NP], const F (&ym)[PF_NP], const F (&xi)[PF_NP], const F (&yi)[PF_NP],
+HPUSM_HD PfPart<F> pf_part(const typename PairT<F>::T (&M)[PF_NP], const typename PairT<F>::T (&I)[PF_NP],
                            const F (&w)[PF_NP], F n_joints) {
+  typedef typename PairT<F>::T P2;
   constexpr int NP = Rows::N;
   PfPart<F> r;
-  F sx = F(0), sy = F(0), sX = F(0), sY = F(0);
+  P2 sI = p2s(F(0)), sM = p2s(F(0));
   HPUSM_UNROLL
   for (int k = 0; k < NP; ++k) {
     const int j = Rows::at(k);
-    sx += xi[j]; sy += yi[j]; sX += xm[j]; sY += ym[j];  // masked joints are exact zeros on both sides
+    sI = p2_add(sI, I[j]); sM = p2_add(sM, M[j]);  // masked joints are exact zeros on both sides
   }
   r.ok = n_joints >= F(3);
-  const F inv_n = pf_rcp(pf_max(n_joints, F(1)));
-  const F mx = sx * inv_n, my = sy * inv_n, mX = sX * inv_n, mY = sY * inv_n;
-  F dx[NP], dy[NP], dX[NP], dY[NP];
-  F cxx = F(0), cxy = F(0), cyy = F(0), cxX = F(0), cyX = F(0), cxY = F(0), cyY = F(0);
+  const P2 inv_n = p2s(pf_rcp(pf_max(n_joints, F(1))));
+  const P2 mI = p2_mul(sI, inv_n), mM = p2_mul(sM, inv_n);
+  P2 dI[NP], dM[NP];
+  P2 cd = p2s(F(0)), cX = p2s(F(0)), cY = p2s(F(0));  // (cxx, cyy), (cxX, cyX), (cxY, cyY)
+  F cxy = F(0);
   HPUSM_UNROLL
   for (int k = 0; k < NP; ++k) {
     const int j = Rows::at(k);
-    dx[k] = xi[j] - mx; dy[k] = yi[j] - my; dX[k] = xm[j] - mX; dY[k] = ym[j] - mY;
-    const F wx = w[j] * dx[k], wy = w[j] * dy[k];
-    cxx += wx * dx[k]; cxy += wx * dy[k]; cyy += wy * dy[k];
-    cxX += wx * dX[k]; cyX += wy * dX[k]; cxY += wx * dY[k]; cyY += wy * dY[k];
+    dI[k] = p2_sub(I[j], mI); dM[k] = p2_sub(M[j], mM);
+    const P2 wd = p2_mul(p2s(w[j]), dI[k]);
+    cd = p2_fma(wd, dI[k], cd);
+    cxy += p2x(wd) * p2y(dI[k]);
+    cX = p2_fma(wd, p2s(p2x(dM[k])), cX);
+    cY = p2_fma(wd, p2s(p2y(dM[k])), cY);
   }
+  const F cxx = p2x(cd), cyy = p2y(cd), cxX = p2x(cX), cyX = p2y(cX), cxY = p2x(cY), cyY = p2y(cY);
   const F det = cxx * cyy - cxy * cxy, tr = cxx + cyy;
   if (!(det > F(0.01) * tr * tr)) r.ok = false;
   const F id = pf_rcp(r.ok ? det : F(1));
   r.a00 = (cyy * cxX - cxy * cyX) * id; r.a10 = (cxx * cyX - cxy * cxX) * id;
   r.a01 = (cyy * cxY - cxy * cyY) * id; r.a11 = (cxx * cyY - cxy * cxY) * id;
+  const P2 A0 = p2(r.a00, r.a01), A1 = p2(r.a10, r.a11);
   r.max_d2 = F(0); r.shoulder_d2 = F(0);
   HPUSM_UNROLL
   for (int k = 0; k < NP; ++k) {
     const int j = Rows::at(k);
     // model - (input * A + t), both sides centred on the means of the fitted joints; a masked joint is (0,0) on both
     // sides and comes back as (0,0) (common.py:93-96): residual 0
-    const F fx = dX[k] - (dx[k] * r.a00 + dy[k] * r.a10);
-    const F fy = dY[k] - (dx[k] * r.a01 + dy[k] * r.a11);
-    const F d2 = w[j] * (fx * fx + fy * fy);
+    const P2 t = p2_fma(p2s(p2x(dI[k])), A0, p2_mul(p2s(p2y(dI[k])), A1));
+    const P2 f = p2_sub(dM[k], t);
+    const P2 sq = p2_mul(f, f);
+    const F d2 = w[j] * (p2x(sq) + p2y(sq));
     r.max_d2 = pf_max(r.max_d2, d2);
     if (k == 1 || k == 4) r.shoulder_d2 = pf_max(r.shoulder_d2, d2);  // torso rows 1 and 4 (pose_comparison.py:62)
   }
@@ -242,25 +284,30 @@ HPUSM_HD bool pose_fast_decide(const PoseQueryPrep& pq, float (&px)[PF_NJ], floa
 
   // scaled coordinates of joints 0..13: (raw - lo) * (w * inv): a masked joint comes out as an exact +0 on both sides,
   // a coordinate that equals the minimum as an exact 0 (the part gates count zeros).  Counts of non-zero scaled
-  // coordinates per part as sums of 0/1 flags.
-  F sxP[PF_NP], syP[PF_NP], sxQ[PF_NP], syQ[PF_NP], wp[PF_NP];
-  F nzP_t = F(0), nzP_l = F(0), nzQ_t = F(0), nzQ_l = F(0), n_t = F(0), n_l = F(0);
+  // coordinates per part as sums of 0/1 flags, (database pose, query) side by side.
+  typedef typename PairT<F>::T P2;
+  P2 SP[PF_NP], SQ[PF_NP];
+  F wp[PF_NP];
+  const P2 invP = p2(ixP, iyP), invQ = p2(ixQ, iyQ), loP2 = p2s(loPf), loQ2 = p2s(loQ), zero2 = p2s(F(0));
+  P2 nz_t = zero2, nz_l = zero2;  // (database pose, query)
+  F n_t = F(0), n_l = F(0);
   HPUSM_UNROLL
   for (int j = 0; j < PF_NP; ++j) {
     wp[j] = w[j];
-    const F wxP = w[j] * ixP, wyP = w[j] * iyP, wxQ = w[j] * ixQ, wyQ = w[j] * iyQ;
-    sxP[j] = pf_mul0(F(px[j]) - loPf, wxP); syP[j] = pf_mul0(F(py[j]) - loPf, wyP);
-    sxQ[j] = pf_mul0(F(pq.x[j]) - loQ, wxQ); syQ[j] = pf_mul0(F(pq.y[j]) - loQ, wyQ);
-    const F cP = F(pf_flag(sxP[j])) + F(pf_flag(syP[j])), cQ = F(pf_flag(sxQ[j])) + F(pf_flag(syQ[j]));
-    if ((FastTorso::ROWS >> j) & 1u) { nzP_t += cP; nzQ_t += cQ; n_t += w[j]; }
-    if ((FastLegs::ROWS >> j) & 1u) { nzP_l += cP; nzQ_l += cQ; n_l += w[j]; }
+    const P2 w2 = p2s(w[j]);
+    SP[j] = p2_fma(p2_sub(p2(F(px[j]), F(py[j])), loP2), p2_mul(w2, invP), zero2);
+    SQ[j] = p2_fma(p2_sub(p2(F(pq.x[j]), F(pq.y[j])), loQ2), p2_mul(w2, invQ), zero2);
+    const P2 c = p2(F(pf_flag(p2x(SP[j]))) + F(pf_flag(p2y(SP[j]))), F(pf_flag(p2x(SQ[j]))) + F(pf_flag(p2y(SQ[j]))));
+    if ((FastTorso::ROWS >> j) & 1u) { nz_t = p2_add(nz_t, c); n_t += w[j]; }
+    if ((FastLegs::ROWS >> j) & 1u) { nz_l = p2_add(nz_l, c); n_l += w[j]; }
   }
+  const F nzP_t = p2x(nz_t), nzQ_t = p2y(nz_t), nzP_l = p2x(nz_l), nzQ_l = p2y(nz_l);
   // A detected joint whose scaled coordinates are BOTH zero is left out of the reference's fit while its partner is
   // not: that takes two coordinates equal to the minimum inside one part -- such poses go to the exact kernel.
   if (F(2) * n_t - nzP_t >= F(2) || F(2) * n_t - nzQ_t >= F(2) || F(2) * n_l - nzP_l >= F(2) || F(2) * n_l - nzQ_l >= F(2))
     return false;
-  const PfPart<F> torso = QIM ? pf_part<F, FastTorso>(sxQ, syQ, sxP, syP, wp, n_t) : pf_part<F, FastTorso>(sxP, syP, sxQ, syQ, wp, n_t);
-  const PfPart<F> legs = QIM ? pf_part<F, FastLegs>(sxQ, syQ, sxP, syP, wp, n_l) : pf_part<F, FastLegs>(sxP, syP, sxQ, syQ, wp, n_l);
+  const PfPart<F> torso = QIM ? pf_part<F, FastTorso>(SQ, SP, wp, n_t) : pf_part<F, FastTorso>(SP, SQ, wp, n_t);
+  const PfPart<F> legs = QIM ? pf_part<F, FastLegs>(SQ, SP, wp, n_l) : pf_part<F, FastLegs>(SP, SQ, wp, n_l);
   if (!torso.ok || !legs.ok) return false;
   const F torso_dist = pf_sqrt(torso.max_d2), legs_dist = pf_sqrt(legs.max_d2), shoulder_dist = pf_sqrt(torso.shoulder_d2);
   const F nzm_t = QIM ? nzQ_t : nzP_t, nzi_t = QIM ? nzP_t : nzQ_t;  // small integers, held exactly

@@ -28,6 +28,9 @@
 namespace hpusm {
 
 constexpr int RS_THREADS = 256;
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 3  // 80 registers, 73 KB of shared memory per CTA: 126.4 ms on C4 vs 129.7 ms at 2 CTAs per SM
+#endif
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_CHUNK = 4096;  // matches staged in shared memory at a time (64 KB)
 constexpr int COUNTER_MAX_ATTEMPTS = 256;
@@ -457,7 +460,8 @@ ransac_sample_cv2_warp_kernel(const float* __restrict__ src, const float* __rest
   for (int i = h + lane; i < nhyp; i += 32) out[i] = make_int4(-1, -1, -1, -1);
 }
 
-// grid.x = pairs. dynamic smem: float4 pts[chunk]; float models[nhyp][9] (compacted); int counts[nhyp]; int hyp_of[nhyp].
+// grid.x = pairs. dynamic smem: float4 pts[chunk]; float models[nhyp][8] (compacted; h8 == 1 exactly after the
+// normalisation of the solver); int counts[nhyp]; int hyp_of[nhyp].
 //   A   one LANE per hypothesis: sample (redraw until the subset check passes | read the cv2 table) + FP64 closed-form
 //       solve; the models that exist are compacted (ballot + one smem atomic per warp), FP32 model parked in shared memory
 //   B   lane = hypothesis (model in 9 registers), the pair's matches stream through as broadcast LDS.128; work items
@@ -466,7 +470,7 @@ ransac_sample_cv2_warp_kernel(const float* __restrict__ src, const float* __rest
 constexpr int RS_SEG = 256;
 
 template <bool CV>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst,
                     const int64_t* __restrict__ pair_offsets, float thresh, int nhyp, double confidence,
                     uint64_t seed, int64_t pair0, int chunk, const int4* __restrict__ samples,
@@ -474,7 +478,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   extern __shared__ __align__(16) unsigned char rs_smem[];
   float4* pts = reinterpret_cast<float4*>(rs_smem);
   float* models = reinterpret_cast<float*>(rs_smem + (size_t)chunk * sizeof(float4));
-  int* counts = reinterpret_cast<int*>(models + (size_t)nhyp * 9);
+  int* counts = reinterpret_cast<int*>(models + (size_t)nhyp * 8);
   int* hyp_of = counts + nhyp;
   __shared__ int n_valid;
   const int64_t pair = blockIdx.x;
@@ -543,7 +547,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       const int j = base + __popc(b & ((1u << lane) - 1u));
       hyp_of[j] = h;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) models[j * 9 + i] = (float)H[i];
+      for (int i = 0; i < 8; ++i) models[j * 8 + i] = (float)H[i];
     }
     if (h < nhyp) counts[h] = ok ? 0 : -1;
   }
@@ -569,7 +573,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       f32x2 h2[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        const float c = h >= 0 ? models[j * 9 + i] : 0.f;
+        const float c = h >= 0 ? (i < 8 ? models[j * 8 + i] : 1.f) : 0.f;
         h2[i] = pack2(c, c);
       }
       const int p0 = sg * (RS_SEG / 2), p1 = min(npair, p0 + RS_SEG / 2);
@@ -1032,13 +1036,14 @@ ransac_finalize_kernel(const float* __restrict__ src, const float* __restrict__ 
 }
 
 static size_t ransac_smem_bytes(int nhyp, int chunk) {
-  return (size_t)chunk * sizeof(float4) + (size_t)nhyp * (9 * sizeof(float) + 2 * sizeof(int));
+  return (size_t)chunk * sizeof(float4) + (size_t)nhyp * (8 * sizeof(float) + 2 * sizeof(int));
 }
 
 static int ransac_pick_chunk(int nhyp) {
-  // keep at least two CTAs per SM resident when the hypothesis table allows it
-  const size_t table = (size_t)nhyp * 44;
-  size_t budget = 100 * 1024;
+  // keep RS_MIN_BLOCKS CTAs per SM resident when the hypothesis table allows it
+  const size_t table = (size_t)nhyp * 40;
+  size_t budget = (RS_MIN_BLOCKS >= 3 ? 73 : 100) * 1024;
+  if (table + 2048 * sizeof(float4) > budget) budget = 100 * 1024;
   if (table + 1024 * sizeof(float4) > budget) budget = 220 * 1024;
   if (table + 256 * sizeof(float4) > budget) return -1;
   size_t c = (budget - table) / sizeof(float4);
