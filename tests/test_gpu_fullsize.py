@@ -114,6 +114,21 @@ def test_c4_ransac_100k_pairs_properties(hpusm, cuda_device):
     err = ((pr[..., :2] / pr[..., 2:] - dst[:m * K].view(m, K, 2).double()) ** 2).sum(-1)
     mk = mask.view(m, K).bool()
     assert (err[mk] <= 25.0 + 1e-3).all() and (err[~mk] > 25.0 - 1e-3).all() and torch.equal(ninl.long(), mk.sum(dim=1))
+    # (6) a slice of the full-size batch against the oracle, bit for bit: the counts of every iteration of 16 pairs taken
+    # from the middle of the batch (scored with their own rows of the sample table), and the full result of the same pairs
+    from oracle import ransac_oracle
+    p0, np_ = 54321, 16
+    hs, hd = src[p0 * K:(p0 + np_) * K].cpu().numpy(), dst[p0 * K:(p0 + np_) * K].cpu().numpy()
+    ho = np.arange(np_ + 1, dtype=np.int64) * K
+    ref_counts = ransac_oracle.score_batch(hs, hd, ho, 5.0, nhyp, 4, 0, p0)
+    np.testing.assert_array_equal(counts[p0:p0 + np_].cpu().numpy(), ref_counts)
+    Hs, ms, ns, bs = hpusm.ransac_homography_batch(src[p0 * K:(p0 + np_) * K], dst[p0 * K:(p0 + np_) * K], offs[:np_ + 1], 5.0,
+                                                   nhyp, 0.995, seed=4, pair_index0=p0)
+    rH, rm, rn, rb = ransac_oracle.homography_batch(hs, hd, ho, 5.0, nhyp, 0.995, 4, True, 0, p0)
+    np.testing.assert_array_equal(bs.cpu().numpy(), rb)
+    np.testing.assert_array_equal(ms.cpu().numpy(), rm)
+    scale = np.abs(rH).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(Hs.cpu().numpy() - rH) / scale).max() < 1e-6
 
 
 def test_c5_pose_10m_properties(hpusm, cuda_device):
