@@ -82,6 +82,9 @@ SIGNATURES = {
     "hpusm_pose_topk_merge": (_i32, [_p, _p, _i64, _i32, _p, _p, _p]),
     "hpusm_orb_workspace_bytes": (_sz, [_i32, _i32, _i32, _f64]),
     "hpusm_orb_compute": (_i32, [_p, _i32, _i32, _i64, _i32, _f64, _p, _p, _i64, _p, _p, _sz, _p]),
+    "hpusm_orb_detect_workspace_bytes": (_sz, [_i32, _i32, _i32, _f64]),
+    "hpusm_orb_detect_and_compute": (_i32, [_p, _i32, _i32, _i64, _i32, _f64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p,
+                                            _p, _p, _p, _sz, _p]),
     "hpusm_microbench_popc": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_lop3": (_i32, [_i64, _i32, _i64, _p, _p]),
     "hpusm_microbench_ffma": (_i32, [_i32, _i64, _i32, _i64, _p, _p]),

@@ -64,36 +64,86 @@ class BFMatcher(object):
         return out
 
 
+class KeyPointArray(object):
+    """The keypoints of one image as arrays (what the device path produces), quacking like the list of cv2.KeyPoint the
+    reference passes around: len(), indexing and iteration give objects with .pt, .size, .angle, .response, .octave,
+    .class_id; `.xy` is the [n,2] float32 array the GPU matcher's gather takes directly."""
+
+    class _KP(object):
+        __slots__ = ("pt", "size", "angle", "response", "octave", "class_id")
+
+        def __init__(self, pt, size, angle, response, octave):
+            self.pt, self.size, self.angle, self.response, self.octave, self.class_id = pt, size, angle, response, octave, -1
+
+    def __init__(self, xy, size, angle, response, octave):
+        self.xy, self.size, self.angle, self.response, self.octave = xy, size, angle, response, octave
+
+    def __len__(self):
+        return len(self.xy)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return KeyPointArray(self.xy[i], self.size[i], self.angle[i], self.response[i], self.octave[i])
+        return KeyPointArray._KP((float(self.xy[i, 0]), float(self.xy[i, 1])), float(self.size[i]), float(self.angle[i]),
+                                 float(self.response[i]), int(self.octave[i]))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def to_cv2(self):
+        import cv2
+        return [cv2.KeyPoint(float(x), float(y), float(s), float(a), float(r), int(o), -1)
+                for (x, y), s, a, r, o in zip(self.xy, self.size, self.angle, self.response, self.octave)]
+
+
 class OrbGpu(object):
-    """The reference's ORB (features.py:19-20) with detection on OpenCV and DESCRIPTION on the GPU: `detectAndCompute`
-    returns the keypoints of cv2's detector and descriptors that are bit-identical to cv2's (hpusm_orb_compute:
-    INTER_LINEAR_EXACT pyramid, ORB's 7x7 Gaussian, rotated rBRIEF tests).  `last_descriptors` keeps the device tensor of
-    the last call so a caller that goes on to match (BFMatcher.knn2) can skip the upload."""
+    """The reference's ORB (features.py:19-20) on the GPU: `detectAndCompute(img, None)` returns cv2's keypoints (same
+    order, identical pt / octave / size / response / angle, as a KeyPointArray) and cv2's descriptors bit for bit --
+    pyramid, FAST + non-maximum suppression, orientation, smoothing and the rBRIEF tests all run on the device
+    (hpusm_orb_detect_and_compute).  Masks, and images dense enough for OpenCV's per-level keypoint cap to bite, go to
+    the OpenCV detector for detection (description still on the GPU).  `last_descriptors` keeps the device tensor of the
+    last call so a caller that goes on to match can skip the upload."""
 
     def __init__(self, cv_detector):
         self.cv = cv_detector
         self.last_descriptors = None
 
+    @staticmethod
+    def _gray(image):
+        img = np.ascontiguousarray(image)
+        if img.ndim != 2 or img.dtype != np.uint8:
+            raise ValueError("OrbGpu: grayscale uint8 images only (the reference reads them with cv2.imread(path, 0))")
+        return img
+
     def detect(self, image, mask=None):
-        return self.cv.detect(image, mask)
+        if mask is not None:
+            return self.cv.detect(image, mask)
+        return self.detectAndCompute(image, None, want_descriptors=False)[0]
 
     def compute(self, image, keypoints):
         if len(keypoints) == 0:
             self.last_descriptors = None
             return keypoints, None
-        pts = np.float32([kp.pt for kp in keypoints])
-        octs = np.int32([kp.octave for kp in keypoints])
-        angs = np.float32([kp.angle for kp in keypoints])
+        if isinstance(keypoints, KeyPointArray):
+            pts, octs, angs = keypoints.xy, keypoints.octave, keypoints.angle
+        else:
+            pts = np.float32([kp.pt for kp in keypoints])
+            octs = np.int32([kp.octave for kp in keypoints])
+            angs = np.float32([kp.angle for kp in keypoints])
         lxy, cs = engine.orb_keypoint_params(pts, octs, angs)
-        img = np.ascontiguousarray(image)
-        if img.ndim != 2 or img.dtype != np.uint8:
-            raise ValueError("OrbGpu: grayscale uint8 images only (the reference reads them with cv2.imread(path, 0))")
-        desc = engine.orb_compute(up(img, np.uint8), up(lxy, np.int32), up(cs, np.float32))
+        desc = engine.orb_compute(up(self._gray(image), np.uint8), up(lxy, np.int32), up(cs, np.float32))
         self.last_descriptors = desc
         return keypoints, down(desc)
 
-    def detectAndCompute(self, image, mask=None):
-        return self.compute(image, self.detect(image, mask))
+    def detectAndCompute(self, image, mask=None, want_descriptors=True):
+        if mask is not None:
+            return self.compute(image, self.cv.detect(image, mask))
+        out = engine.orb_detect_and_compute(up(self._gray(image), np.uint8), want_descriptors=want_descriptors)
+        if out["over_quota"]:  # OpenCV would cull this level by response: let it
+            return self.compute(image, self.cv.detect(image, None)) if want_descriptors else (self.cv.detect(image, None), None)
+        kps = KeyPointArray(down(out["pt"]), down(out["size"]), down(out["angle"]), down(out["response"]), down(out["octave"]))
+        self.last_descriptors = out["desc"]
+        return kps, (down(out["desc"]) if want_descriptors else None)
 
     def __getattr__(self, name):  # everything else (getters, setters) is the OpenCV detector's
         return getattr(self.cv, name)
@@ -189,6 +239,8 @@ def find_homography_both_ways(p_a, p_b, thresh=5.0, maxIters=2000, confidence=0.
 
 
 def _kp_array(kps):
+    if isinstance(kps, KeyPointArray):
+        return np.ascontiguousarray(kps.xy, dtype=np.float32).reshape(-1, 2)
     if isinstance(kps, np.ndarray):
         return np.ascontiguousarray(kps, dtype=np.float32).reshape(-1, 2)
     return np.float32([_pt(kp) for kp in kps]).reshape(-1, 2)

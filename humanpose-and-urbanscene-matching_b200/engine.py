@@ -284,7 +284,9 @@ def ransac_score_batch(src, dst, pair_offsets, thresh=5.0, nhyp=1024, seed=0, ou
 
 
 # ---- ORB description (the step in front of K2) --------------------------------------------------------------
-ORB_LEVELS, ORB_SCALE = 8, 1.2  # features.py:19-20
+ORB_LEVELS = 8                           # features.py:19-20
+ORB_SCALE = float(np.float32(1.2))       # ORB::create takes a float: OpenCV works with the double 1.2000000476837158
+ORB_FAST_THRESHOLD, ORB_EDGE, ORB_PATCH, ORB_NFEATURES = 20, 31, 31, 100000
 
 
 def orb_keypoint_params(pts, octaves, angles, scale_factor=ORB_SCALE):
@@ -323,6 +325,58 @@ def orb_compute(img, kp_lxy, kp_cs, nlevels=ORB_LEVELS, scale_factor=ORB_SCALE, 
         check(lib.hpusm_orb_compute(_ptr(img), w, h, w, int(nlevels), float(scale_factor), _ptr(kp_lxy), _ptr(kp_cs), n,
                                     _ptr(desc), _ptr(ws), ws.numel(), _stream(dev)))
     return desc
+
+
+def orb_level_quotas(nlevels=ORB_LEVELS, nfeatures=ORB_NFEATURES, scale_factor=ORB_SCALE):
+    """nfeaturesPerLevel of OpenCV's computeKeyPoints (float32 arithmetic): the per-level caps on the keypoint count."""
+    f32 = np.float32
+    factor = f32(1.0 / scale_factor)
+    nd = f32(nfeatures) * (f32(1) - factor) / (f32(1) - f32(np.power(np.float64(factor), np.float64(nlevels))))
+    out, total = [], 0
+    for _ in range(nlevels - 1):
+        out.append(int(np.rint(nd)))
+        total += out[-1]
+        nd = f32(nd * factor)
+    out.append(max(nfeatures - total, 0))
+    return out
+
+
+def orb_detect_and_compute(img, capacity=None, want_descriptors=True, nlevels=ORB_LEVELS, scale_factor=ORB_SCALE):
+    """cv2.ORB.detectAndCompute(img, None) of the reference's ORB on the device.  img [h,w] uint8 CUDA tensor.
+    Returns a dict of device tensors cut to the keypoint count: pt [n,2] f32, octave [n] i32, angle / response / size
+    [n] f32, desc [n,32] u8 (None when not wanted), plus level_counts (host list), and over_quota (a level exceeded
+    OpenCV's per-level cap: cv2 would have culled by response, the device path does not -- fall back)."""
+    img = _cuda(img, torch.uint8, "img")
+    if img.dim() != 2:
+        raise ValueError("img must be [height, width] uint8")
+    h, w = img.shape
+    dev = img.device
+    cap = int(capacity) if capacity else max(4096, (h * w) // 8)
+    with torch.cuda.device(dev):
+        f32, i32 = torch.float32, torch.int32
+        xy = torch.empty((cap, 2), dtype=f32, device=dev)
+        octave = torch.empty((cap,), dtype=i32, device=dev)
+        angle = torch.empty((cap,), dtype=f32, device=dev)
+        response = torch.empty((cap,), dtype=f32, device=dev)
+        size = torch.empty((cap,), dtype=f32, device=dev)
+        lxy = torch.empty((cap, 3), dtype=i32, device=dev)
+        cs = torch.empty((cap, 2), dtype=f32, device=dev)
+        desc = torch.empty((cap, 32), dtype=torch.uint8, device=dev) if want_descriptors else None
+        counts = torch.empty((nlevels + 1,), dtype=i32, device=dev)
+        ws = _workspace(lib.hpusm_orb_detect_workspace_bytes(w, h, int(nlevels), float(scale_factor)), dev)
+        check(lib.hpusm_orb_detect_and_compute(_ptr(img), w, h, w, int(nlevels), float(scale_factor), ORB_FAST_THRESHOLD,
+                                               ORB_EDGE, ORB_PATCH, cap, _ptr(xy), _ptr(octave), _ptr(angle), _ptr(response),
+                                               _ptr(size), _ptr(lxy), _ptr(cs), _ptr(desc), _ptr(counts), _ptr(ws),
+                                               ws.numel(), _stream(dev)))
+        level_counts = counts.cpu().tolist()  # the one host read: how many keypoints there are
+    n = level_counts[-1]
+    if n > cap:
+        return orb_detect_and_compute(img, capacity=n, want_descriptors=want_descriptors, nlevels=nlevels,
+                                      scale_factor=scale_factor)
+    quotas = orb_level_quotas(nlevels, ORB_NFEATURES, scale_factor)
+    return {"pt": xy[:n], "octave": octave[:n], "angle": angle[:n], "response": response[:n], "size": size[:n],
+            "kp_lxy": lxy[:n], "kp_cs": cs[:n], "desc": desc[:n] if desc is not None else None,
+            "level_counts": level_counts[:-1], "over_quota": any(c > q for c, q in zip(level_counts[:-1], quotas))}
 
 
 def perspective_transform(pts, H):

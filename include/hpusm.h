@@ -302,6 +302,24 @@ int hpusm_orb_compute(const uint8_t* img, int width, int height, int64_t pitch, 
                       const int32_t* kp_lxy, const float* kp_cs, int64_t n, uint8_t* desc, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* Detection + description: cv2.ORB.detectAndCompute(img, None) for the reference's configuration (FAST threshold 20,
+ * ORB_FAST_SCORE, edgeThreshold 31, patchSize 31; features.py:19-20), restated in oracle/orb_oracle.py and pinned on cv2's own
+ * keypoint lists: same keypoints in the same order (level by level, row-major inside a level) with identical pt, octave,
+ * size, response and angle, and their descriptors.  Everything stays on the device and is asynchronous: the number of
+ * keypoints is only known there.
+ *   capacity      rows available in every output; keypoints beyond it are dropped (compare level_counts[nlevels] with it).
+ *   kp_xy [cap][2] float32 KeyPoint.pt; kp_octave [cap] int32; kp_angle, kp_response, kp_size [cap] float32;
+ *   kp_lxy [cap][3] int32 and kp_cs [cap][2] float32: the keypoints in the form hpusm_orb_compute takes;
+ *   desc [cap][32] uint8 (may be NULL: detection only);
+ *   level_counts [nlevels + 1] int32: keypoints per level, then their total.  OpenCV caps every level at a quota
+ *   (21717 on level 0 for nfeatures = 100000) by response; that cull is NOT done here: a caller that sees a count above
+ *   the quota must fall back (the drop-in does) -- it does not happen on images below ~2 Mpixel of dense texture. */
+size_t hpusm_orb_detect_workspace_bytes(int width, int height, int nlevels, double scale_factor);
+int hpusm_orb_detect_and_compute(const uint8_t* img, int width, int height, int64_t pitch, int nlevels, double scale_factor,
+                                 int fast_threshold, int edge_threshold, int patch_size, int64_t capacity, float* kp_xy,
+                                 int32_t* kp_octave, float* kp_angle, float* kp_response, float* kp_size, int32_t* kp_lxy,
+                                 float* kp_cs, uint8_t* desc, int32_t* level_counts, void* ws, size_t ws_bytes, void* stream);
+
 /* Integer-pipe micro-benchmarks: every thread issues `iters` POPC.32 (resp. LOP3) in 8 independent chains; returns
  * nothing useful in `sink`.  bench.py uses them as the measured denominators of the Hamming roofline. */
 int hpusm_microbench_popc(int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);

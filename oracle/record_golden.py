@@ -298,8 +298,11 @@ def record_orb_descriptors():
         kp, desc = orb.detectAndCompute(img, None)
         kp2, desc2 = orb.compute(img, kp)
         assert np.array_equal(desc, desc2) and len(kp2) == len(kp)
+        kd = orb.detect(img, None)  # the same keypoints, through the detection-only entry point
+        assert [(q.pt, q.octave, q.angle) for q in kd] == [(q.pt, q.octave, q.angle) for q in kp]
         arrays.update({"img_%d" % k: img, "pt_%d" % k: np.float32([q.pt for q in kp]),
                        "octave_%d" % k: np.int32([q.octave for q in kp]), "angle_%d" % k: np.float32([q.angle for q in kp]),
+                       "response_%d" % k: np.float32([q.response for q in kp]), "size_%d" % k: np.float32([q.size for q in kp]),
                        "desc_%d" % k: desc})
     save("orb_descriptors.npz", names=np.array(ORB_FIXTURES), **arrays)
 

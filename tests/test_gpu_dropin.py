@@ -155,7 +155,12 @@ def test_orb_detector_dropin_equals_cv2(mods):
         img = g["img_%d" % k]
         kp, desc = detector.detectAndCompute(img, None)
         kp_ref, desc_ref = ref.detectAndCompute(img, None)
-        assert [q.pt for q in kp] == [q.pt for q in kp_ref]
+        assert isinstance(kp, ft.KeyPointArray) and len(kp) == len(kp_ref)
+        assert [(q.pt, q.octave, q.angle, q.response, q.size) for q in kp] == \
+               [(q.pt, q.octave, q.angle, q.response, q.size) for q in kp_ref]
+        assert [(q.pt, q.angle) for q in kp.to_cv2()[:5]] == [(q.pt, q.angle) for q in kp_ref[:5]]
+        kd = detector.detect(img, None)
+        assert [q.pt for q in kd] == [q.pt for q in kp_ref]
         np.testing.assert_array_equal(desc, desc_ref)
         np.testing.assert_array_equal(desc, g["desc_%d" % k])
     assert detector.getNLevels() == 8  # attribute access falls through to the OpenCV detector

@@ -379,6 +379,40 @@ def test_orb_compute_is_cv2_orb_compute(hpusm, cuda_device):
     np.testing.assert_array_equal(dist.cpu().numpy(), rd)
 
 
+def test_orb_detect_and_compute_is_cv2(hpusm, cuda_device):
+    """hpusm_orb_detect_and_compute against cv2.ORB.detectAndCompute of the reference's detector (urban_scene.py:31-32) on
+    three img/ fixtures: the same keypoints in the same order -- pt, octave, angle, response, size identical -- and their
+    descriptors bit for bit; per-level counts; a capacity that is too small is grown."""
+    g = load_golden("orb_descriptors.npz")
+    for k, name in enumerate(g["names"]):
+        img = g["img_%d" % k]
+        out = hpusm.engine.orb_detect_and_compute(dev(img, cuda_device), capacity=1000 if k == 0 else None)
+        assert not out["over_quota"]
+        for key in ("pt", "octave", "angle", "response", "size", "desc"):
+            np.testing.assert_array_equal(out[key].cpu().numpy(), g["%s_%d" % (key, k)], err_msg="%s %s" % (name, key))
+        assert out["level_counts"] == [int((g["octave_%d" % k] == l).sum()) for l in range(8)]
+        lxy, cs = hpusm.engine.orb_keypoint_params(g["pt_%d" % k], g["octave_%d" % k], g["angle_%d" % k])
+        np.testing.assert_array_equal(out["kp_lxy"].cpu().numpy(), lxy)
+        np.testing.assert_array_equal(out["kp_cs"].cpu().numpy(), cs)
+
+
+def test_orb_detect_odd_shapes_against_oracle(hpusm, cuda_device):
+    """Detection on synthetic images whose sizes are not multiples of any tile (incl. one too small for the upper pyramid
+    levels to hold a keypoint) against the oracle's detect."""
+    from oracle import orb_oracle
+    rng = np.random.default_rng(12)
+    for (h, w) in ((97, 131), (241, 333), (77, 400)):
+        base = rng.integers(0, 256, (h // 4 + 2, w // 4 + 2), dtype=np.uint8)
+        img = np.kron(base, np.ones((4, 4), np.uint8))[:h, :w].copy()       # blocky texture: plenty of corners
+        img = np.clip(img.astype(np.int32) + rng.integers(-6, 7, img.shape), 0, 255).astype(np.uint8)
+        want = orb_oracle.detect(img)
+        out = hpusm.engine.orb_detect_and_compute(dev(img, cuda_device))
+        assert len(want["pt"]) > 0
+        for key in ("pt", "octave", "angle", "response", "size"):
+            np.testing.assert_array_equal(out[key].cpu().numpy(), want[key], err_msg="%dx%d %s" % (h, w, key))
+        np.testing.assert_array_equal(out["desc"].cpu().numpy(), orb_oracle.compute(img, want["pt"], want["octave"], want["angle"]))
+
+
 def test_orb_compute_odd_shapes(hpusm, cuda_device):
     """Images whose sizes are not multiples of the kernels' tiles, keypoints on every level incl. close to the border
     margin OpenCV keeps (31 px): the device descriptors equal the oracle's."""

@@ -327,6 +327,19 @@ def test_orb_oracle_reproduces_cv2_descriptors():
     assert total > 5000
 
 
+def test_orb_oracle_detect_reproduces_cv2_keypoints():
+    """oracle/orb_oracle.detect (FAST-9/16 + non-maximum suppression per pyramid level, border filter, intensity-centroid
+    angle through cv::fastAtan2) against cv2.ORB.detect on three img/ fixtures: the same keypoints in the same order with
+    identical pt, octave, angle, response and size."""
+    from oracle import orb_oracle
+    g = load_golden("orb_descriptors.npz")
+    for k, name in enumerate(g["names"]):
+        got = orb_oracle.detect(g["img_%d" % k])
+        assert got["exact_order"]
+        for key in ("pt", "octave", "angle", "response", "size"):
+            np.testing.assert_array_equal(got[key], g["%s_%d" % (key, k)], err_msg="%s %s" % (name, key))
+
+
 def test_orb_oracle_building_blocks_match_cv2():
     """The restated resize and blur against the cv2 functions themselves (only when cv2 is importable: same image here
     and on the GPU box)."""
