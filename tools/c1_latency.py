@@ -57,4 +57,19 @@ for det in ("sift", "orb"):
     run_ours(); run_cv2()
     out[det] = {"shape": "%dx%d" % (len(dm), len(di)), "ours_match_and_draw_ms": best_of(run_ours), "ours_knn_only_ms": best_of(run_ours_knn),
                 "cv2_match_and_draw_ms": best_of(run_cv2), "cv2_knn_only_ms": best_of(run_cv2_knn), "cv2_threads": cv2.getNumThreads()}
+# feature extraction (urban_scene.py:31-32: detector.detectAndCompute), the step in front of the matcher
+g = np.load(os.path.join(ROOT, "tests", "golden", "orb_descriptors.npz"))
+ours_det, _ = ft.init_feature("orb")
+ref_det = cv2.ORB_create(nfeatures=100000, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                         scoreType=cv2.ORB_FAST_SCORE, patchSize=31)
+for k, name in enumerate(g["names"]):
+    img = g["img_%d" % k]
+    dimg = torch.from_numpy(img).cuda()
+    hp = importlib.import_module("humanpose-and-urbanscene-matching_b200")
+    ours_det.detectAndCompute(img, None); ref_det.detectAndCompute(img, None)
+    out["orb_extract_%s" % str(name)] = {
+        "shape": "%dx%d" % img.shape, "keypoints": int(len(g["pt_%d" % k])),
+        "ours_detectAndCompute_ms": best_of(lambda: ours_det.detectAndCompute(img, None)),
+        "ours_device_only_ms": best_of(lambda: hp.engine.orb_detect_and_compute(dimg)),
+        "cv2_detectAndCompute_ms": best_of(lambda: ref_det.detectAndCompute(img, None))}
 print(json.dumps(out))
