@@ -55,6 +55,8 @@ def parse_args():
                     help="sift: integer-valued SIFT-like rows (the named config) or the general-float variant (x 1.0137)")
     ap.add_argument("--l2-engine", default="auto", choices=["auto", "i8", "bf16", "split", "simt"],
                     help="sift: force one L2 engine (default: HPUSM_L2_AUTO picks from the data)")
+    ap.add_argument("--hamming-engine", default="auto", choices=["auto", "popc", "tc"],
+                    help="orb: engine of the segmented Hamming matcher (auto = tcgen05 kind::i8 where its shape limits hold)")
     ap.add_argument("--nq", type=int, default=1 << 20)
     ap.add_argument("--nt", type=int, default=1 << 20, help="database rows PER GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
@@ -334,9 +336,19 @@ def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
             "fallback_rows": eng.knn2_l2_last_fallback_rows()}
 
 
+_I8_PEAK = {}
+
+
 def i8_sustained_peak(hp, device, seconds=2.0):
-    """Sustained issue rate of tcgen05.mma kind::i8 on this GPU (T op/s): the K1 kernel's roofline denominator, measured in
-    this run -- back-to-back MMAs on every SM for `seconds`, clocks sampled beside it (MEASURED_PEAKS.json has no INT8 line)."""
+    """Sustained issue rate of tcgen05.mma kind::i8 on this GPU (T op/s): the roofline denominator of the integer tensor-core
+    kernels, measured in this run -- back-to-back MMAs on every SM for `seconds`, clocks sampled beside it
+    (MEASURED_PEAKS.json has no INT8 line).  Measured once per process."""
+    if "v" not in _I8_PEAK:
+        _I8_PEAK["v"] = _i8_sustained_peak(hp, device, seconds)
+    return _I8_PEAK["v"]
+
+
+def _i8_sustained_peak(hp, device, seconds):
     eng = hp.engine
     rounds = 4096  # ~10 ms per launch
     eng.microbench_mma("i8", 64, device)
@@ -518,8 +530,10 @@ def run_orb(args, rank, world, device, hp):
     offs = (torch.arange(0, b - a + 1, device=device, dtype=torch.int64) * per)
     tm = Timer(args, rank, world, device, hp)
 
+    heng = args.hamming_engine
+
     def step():
-        return rt.image_scores_sharded(query, db, offs, 0.8)
+        return rt.image_scores_sharded(query, db, offs, 0.8, hamming_engine=heng)
 
     tm.fit_region(step)
     r = tm.run(step)
@@ -527,7 +541,7 @@ def run_orb(args, rank, world, device, hp):
     hq, hdb = query.cpu().pin_memory(), db.cpu().pin_memory()
     hs = torch.empty((args.images,), dtype=torch.int32).pin_memory()
     # the public host-array entry point: runs of whole images uploaded on a copy stream while earlier runs are scored
-    streamed = rt.StreamedImageScorer(per, 32, offs, device)
+    streamed = rt.StreamedImageScorer(per, 32, offs, device, hamming_engine=heng)
 
     def e2e_step():
         hs.copy_(rt.image_scores_sharded(hq, hdb, offs, 0.8, score_fn=streamed), non_blocking=True)
@@ -537,26 +551,41 @@ def run_orb(args, rank, world, device, hp):
         return None
     pairs = float(per) * args.images * per
     top = torch.topk(scores, min(len(planted) * world, 16)).indices.tolist()
-    ppeak, lpeak = popc_peak(hp, device, "popc"), popc_peak(hp, device, "lop3")
     k_ms = r["kernel_ms"] / max(r["kernel_n"], 1)
     pairs_per_launch = float(per) * (b - a) * per * tm.steps / max(r["kernel_n"], 1)
-    # per 256-bit pair the kernel issues 16 LOP3 (8 XOR + 4 carry-save adders) on the ALU pipe and 4 POPC on the XU pipe;
-    # the two pipes run side by side, so the bound is the slower of the two
-    t_bound = max(16.0 * pairs_per_launch / lpeak, 4.0 * pairs_per_launch / ppeak)
-    ach = 16.0 * pairs_per_launch / (k_ms * 1e-3)
-    out = base_line(args, world, "descriptor-pairs/sec (kNN+ratio)", "pairs/s", pairs * tm.steps / (r["ms"] * 1e-3), r["ms"], "u32 popc",
+    tensor = heng != "popc"   # at this shape AUTO resolves to the tensor-core engine
+    out = base_line(args, world, "descriptor-pairs/sec (kNN+ratio)", "pairs/s", pairs * tm.steps / (r["ms"] * 1e-3), r["ms"],
+                    "s8 x s8 -> s32 (tcgen05 kind::i8)" if tensor else "u32 popc",
                     "strong", {"workload": "synthetic ORB 256-bit Hamming, 10k-image database retrieval sharded across 2/4/8 B200",
                                "images": args.images, "descriptors_per_image": per, "query_descriptors": per, "ratio": 0.8,
-                               "sharding": "database images", "l2_flush": "database shard (%.0f MB) exceeds the 126 MB L2" % (db.numel() / 1e6),
+                               "sharding": "database images", "hamming_engine": "tc" if tensor else "popc",
+                               "l2_flush": "database shard (%.0f MB) exceeds the 126 MB L2" % (db.numel() / 1e6),
                                "top_images": top[:8]}, steps=tm.steps)
     out["e2e"] = {"value": pairs * tm.steps / (e["ms"] * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(hq.numel() + hdb.numel()),
                   "d2h_bytes_per_step": int(hs.numel() * 4)}
     out["gpu_launches"] = int(r["launches"])
-    out["roofline"] = {"bound": "integer pipes (16 LOP3 + 4 POPC.32 per pair)", "achieved": ach / 1e12, "peak": lpeak / 1e12, "unit": "Tlop3/s",
-                       "frac": t_bound / (k_ms * 1e-3), "traffic": measured_traffic("orb:%dx%d" % (args.images, world)), "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
-                       "peak_source": "hpusm_microbench_lop3 / hpusm_microbench_popc measured in this run",
-                       "popc_peak_Tpopc": ppeak / 1e12, "naive_popc_bound_ms": 8.0 * pairs_per_launch / ppeak * 1e3,
-                       "hbm_GBps_algorithmic": (db.numel() + query.numel()) / (k_ms * 1e-3) / 1e9}
+    if tensor:
+        # per pair the engine contracts 288 s8 x s8 products (256 descriptor bits + 32 augmentation columns): 576 operations
+        i8_peak, i8_clocks = i8_sustained_peak(hp, device)
+        ach = 576.0 * pairs_per_launch / (k_ms * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": i8_peak, "unit": "T op/s (s8 x s8 -> s32)", "frac": ach / i8_peak,
+                           "traffic": measured_traffic("orb_tc:%dx%d" % (args.images, world)), "kernel_ms": k_ms,
+                           "kernel_launches": int(r["kernel_n"]), "step_ms": r["ms"] / tm.steps,
+                           "peak_source": "hpusm_microbench_mma(i8) sustained for 2 s in this run; the step also holds the operand "
+                                          "expansion (32 -> 288 bytes per database row) and the plan kernels, outside kernel_ms",
+                           "peak_clocks": i8_clocks, "ops_per_pair": 576,
+                           "hbm_GBps_algorithmic": (db.numel() * 9 + query.numel()) / (k_ms * 1e-3) / 1e9}
+    else:
+        ppeak, lpeak = popc_peak(hp, device, "popc"), popc_peak(hp, device, "lop3")
+        # per 256-bit pair the kernel issues 16 LOP3 (8 XOR + 4 carry-save adders) on the ALU pipe and 4 POPC on the XU pipe;
+        # the two pipes run side by side, so the bound is the slower of the two
+        t_bound = max(16.0 * pairs_per_launch / lpeak, 4.0 * pairs_per_launch / ppeak)
+        ach = 16.0 * pairs_per_launch / (k_ms * 1e-3)
+        out["roofline"] = {"bound": "integer pipes (16 LOP3 + 4 POPC.32 per pair)", "achieved": ach / 1e12, "peak": lpeak / 1e12, "unit": "Tlop3/s",
+                           "frac": t_bound / (k_ms * 1e-3), "traffic": measured_traffic("orb:%dx%d" % (args.images, world)), "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
+                           "peak_source": "hpusm_microbench_lop3 / hpusm_microbench_popc measured in this run",
+                           "popc_peak_Tpopc": ppeak / 1e12, "naive_popc_bound_ms": 8.0 * pairs_per_launch / ppeak * 1e3,
+                           "hbm_GBps_algorithmic": (db.numel() + query.numel()) / (k_ms * 1e-3) / 1e9}
     out["clocks"] = r["clocks"]
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline_subprocess("orb")

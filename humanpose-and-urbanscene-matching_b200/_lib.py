@@ -50,8 +50,8 @@ SIGNATURES = {
     "hpusm_profile_collect": (_i32, [_p, _p]),
     "hpusm_knn2_hamming_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "hpusm_knn2_hamming": (_i32, [_p, _i64, _p, _i64, _i32, _p, _p, _p, _sz, _p]),
-    "hpusm_knn2_hamming_segmented_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
-    "hpusm_knn2_hamming_segmented": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _f64, _p, _p, _p, _sz, _p]),
+    "hpusm_knn2_hamming_segmented_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
+    "hpusm_knn2_hamming_segmented": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _f64, _i32, _p, _p, _p, _sz, _p]),
     "hpusm_knn2_l2_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "hpusm_knn2_l2": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _sz, _p]),
     "hpusm_knn2_l2_last_mode": (_i32, []),

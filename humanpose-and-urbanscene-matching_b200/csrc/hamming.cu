@@ -12,6 +12,7 @@
 // lexicographically on (distance, index), which reproduces OpenCV's "lowest train index wins" ties.
 #include <limits.h>
 #include "common.cuh"
+#include "hamming_internal.cuh"
 
 namespace hpusm {
 
@@ -313,20 +314,30 @@ int hpusm_knn2_hamming(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t n
   return HPUSM_OK;
 }
 
-size_t hpusm_knn2_hamming_segmented_workspace_bytes(int64_t nq, int64_t nt, int64_t nseg, int nbytes) {
-  (void)nq; (void)nt; (void)nseg; (void)nbytes;
+// Which engine a segmented call runs on: 0 = unsupported request, else HPUSM_HAMMING_POPC / HPUSM_HAMMING_TC.
+static int hamming_resolve_engine(int engine, int64_t nq, int64_t nt, int64_t nseg, int nbytes) {
+  if (engine == HPUSM_HAMMING_POPC) return HPUSM_HAMMING_POPC;
+  const bool ok = hamming_tc_eligible(nq, nt, nseg, nbytes);
+  if (engine == HPUSM_HAMMING_TC) return ok ? HPUSM_HAMMING_TC : 0;
+  return ok ? HPUSM_HAMMING_TC : HPUSM_HAMMING_POPC;
+}
+
+size_t hpusm_knn2_hamming_segmented_workspace_bytes(int64_t nq, int64_t nt, int64_t nseg, int nbytes, int engine) {
+  if (nq <= 0 || nt <= 0 || nseg <= 0) return 256;
+  if (hamming_resolve_engine(engine, nq, nt, nseg, nbytes) == HPUSM_HAMMING_TC) return hamming_tc_workspace_bytes(nq, nt, nseg);
   return 256;
 }
 
 int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
-                                 const int64_t* seg_offsets, int64_t nseg, int nbytes, double ratio,
+                                 const int64_t* seg_offsets, int64_t nseg, int nbytes, double ratio, int engine,
                                  int32_t* score, int32_t* best_idx, void* ws, size_t ws_bytes,
                                  void* stream) {
-  (void)ws; (void)ws_bytes;
   HPUSM_REQUIRE(nq >= 0 && nt >= 0 && nseg >= 0, HPUSM_ERR_INVALID,
                 "hpusm_knn2_hamming_segmented: negative size");
   HPUSM_REQUIRE(nbytes == 32 || nbytes == 64, HPUSM_ERR_UNSUPPORTED,
                 "hpusm_knn2_hamming_segmented: descriptor width %d bytes (built for 32 and 64)", nbytes);
+  HPUSM_REQUIRE(engine == HPUSM_HAMMING_AUTO || engine == HPUSM_HAMMING_POPC || engine == HPUSM_HAMMING_TC, HPUSM_ERR_INVALID,
+                "hpusm_knn2_hamming_segmented: unknown engine %d", engine);
   if (nseg == 0) return HPUSM_OK;
   HPUSM_REQUIRE(seg_offsets && score && (q || nq == 0) && (t || nt == 0), HPUSM_ERR_INVALID,
                 "hpusm_knn2_hamming_segmented: null pointer");
@@ -337,6 +348,15 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
   cudaStream_t st = as_stream(stream);
   HPUSM_CUDA_OK(cudaMemsetAsync(score, 0, (size_t)nseg * sizeof(int32_t), st));
   if (nq == 0) return HPUSM_OK;
+  const int resolved = nt == 0 ? HPUSM_HAMMING_POPC : hamming_resolve_engine(engine, nq, nt, nseg, nbytes);
+  HPUSM_REQUIRE(resolved != 0, HPUSM_ERR_UNSUPPORTED,
+                "hpusm_knn2_hamming_segmented: the tensor-core engine takes 32-byte descriptors, >= 128 queries, >= 16384 database "
+                "rows and images of >= 256 rows on average (got nbytes %d, nq %lld, nt %lld, nseg %lld)", nbytes, (long long)nq,
+                (long long)nt, (long long)nseg);
+  if (resolved == HPUSM_HAMMING_TC) {
+    if (best_idx) HPUSM_CUDA_OK(cudaMemsetAsync(best_idx, 0xff, (size_t)nseg * nq * sizeof(int32_t), st));
+    return hamming_tc_segmented(q, nq, t, nt, seg_offsets, nseg, ratio, score, best_idx, ws, ws_bytes, st);
+  }
   const int64_t tiles = (nq + HAM_QTILE - 1) / HAM_QTILE;
   // gridDim.y is limited to 65535: walk the segments in slabs.
   for (int64_t s0 = 0; s0 < nseg; s0 += 65535) {

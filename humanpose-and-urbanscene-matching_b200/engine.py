@@ -87,8 +87,14 @@ def knn2_hamming(q, t):
     return idx, dist
 
 
-def knn2_hamming_segmented(q, t, seg_offsets, ratio=0.8, want_best_idx=False):
-    """Per database image: kNN-2 inside the image + Lowe ratio + survivor count (score [nseg] i32)."""
+HAMMING_AUTO, HAMMING_POPC, HAMMING_TC = 0, 1, 2
+_HAMMING_ENGINES = {"auto": HAMMING_AUTO, "popc": HAMMING_POPC, "tc": HAMMING_TC}
+
+
+def knn2_hamming_segmented(q, t, seg_offsets, ratio=0.8, want_best_idx=False, engine=HAMMING_AUTO):
+    """Per database image: kNN-2 inside the image + Lowe ratio + survivor count (score [nseg] i32).
+    engine: HAMMING_AUTO / HAMMING_POPC / HAMMING_TC (or 'auto' / 'popc' / 'tc'); same answer from both engines."""
+    engine = _HAMMING_ENGINES.get(engine, engine)
     q = _cuda(q, torch.uint8, "q")
     t = _cuda(t, torch.uint8, "t")
     seg_offsets = _cuda(seg_offsets, torch.int64, "seg_offsets")
@@ -98,8 +104,8 @@ def knn2_hamming_segmented(q, t, seg_offsets, ratio=0.8, want_best_idx=False):
     with torch.cuda.device(q.device):
         score = torch.empty((nseg,), dtype=torch.int32, device=q.device)
         best = torch.empty((nseg, nq), dtype=torch.int32, device=q.device) if want_best_idx else None
-        ws = _workspace(lib.hpusm_knn2_hamming_segmented_workspace_bytes(nq, nt, nseg, nb), q.device)
-        check(lib.hpusm_knn2_hamming_segmented(_ptr(q), nq, _ptr(t), nt, _ptr(seg_offsets), nseg, nb, float(ratio),
+        ws = _workspace(lib.hpusm_knn2_hamming_segmented_workspace_bytes(nq, nt, nseg, nb, engine), q.device)
+        check(lib.hpusm_knn2_hamming_segmented(_ptr(q), nq, _ptr(t), nt, _ptr(seg_offsets), nseg, nb, float(ratio), engine,
                                                _ptr(score), _ptr(best), _ptr(ws), ws.numel(), _stream(q.device)))
     return (score, best) if want_best_idx else score
 

@@ -189,8 +189,9 @@ class StreamedImageScorer:
     tensor is an internal buffer, valid until the next call.
     """
 
-    def __init__(self, nq, nbytes, seg_offsets, device, images_per_chunk=512):
+    def __init__(self, nq, nbytes, seg_offsets, device, images_per_chunk=512, hamming_engine="auto"):
         self.device = torch.device(device)
+        self.hamming_engine = hamming_engine
         offs = torch.as_tensor(seg_offsets, dtype=torch.int64).cpu()
         self.nimg = int(offs.numel() - 1)
         self.nt = int(offs[-1]) if offs.numel() else 0
@@ -228,7 +229,8 @@ class StreamedImageScorer:
             if r1 == r0:  # a run of empty images
                 self.scores[i0:i1] = 0
                 continue
-            self.scores[i0:i1] = engine.knn2_hamming_segmented(self.dq, self.ddb[r0:r1], local, ratio)
+            self.scores[i0:i1] = engine.knn2_hamming_segmented(self.dq, self.ddb[r0:r1], local, ratio,
+                                                               engine=self.hamming_engine)
         return self.scores
 
 
@@ -286,11 +288,13 @@ class StreamedHomographyBatch:
         return self.H, self.mask, self.ninl
 
 
-def image_scores_sharded(q, db_shard, seg_offsets_shard, ratio=0.8, score_fn=None):
+def image_scores_sharded(q, db_shard, seg_offsets_shard, ratio=0.8, score_fn=None, hamming_engine="auto"):
     """Per-image ratio-survivor counts for a database sharded by images: [total images] int32 on every rank.
     Ranks may own different numbers of images; counts are padded to the largest shard for the gather."""
-    score_fn = score_fn or engine.knn2_hamming_segmented
-    local = score_fn(q, db_shard, seg_offsets_shard, ratio)
+    if score_fn is None:
+        local = engine.knn2_hamming_segmented(q, db_shard, seg_offsets_shard, ratio, engine=hamming_engine)
+    else:
+        local = score_fn(q, db_shard, seg_offsets_shard, ratio)
     rank, n = world()
     if n == 1:
         return local

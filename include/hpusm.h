@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HPUSM_ABI_VERSION 200
+#define HPUSM_ABI_VERSION 201
 
 #define HPUSM_OK 0
 #define HPUSM_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported width) */
@@ -47,6 +47,11 @@ extern "C" {
 #define HPUSM_L2_TC_I8 4  /* tcgen05 kind::i8, u8 operands, s32 accumulation: integer values in [0,255] and squared
                              norms below 4,000,000.  Fully asynchronous: the range check runs on the device and gates
                              the sweep there; a violation leaves every idx at -1 and is reported by hpusm_async_status() */
+
+/* Engines of the segmented Hamming matcher (hpusm_knn2_hamming_segmented). */
+#define HPUSM_HAMMING_AUTO 0 /* tensor-core engine where its shape limits hold, else the __popc engine */
+#define HPUSM_HAMMING_POPC 1 /* XOR + POPC on the integer pipes */
+#define HPUSM_HAMMING_TC 2   /* tcgen05 kind::i8 on signed expansions of the descriptor bits */
 
 int hpusm_version(void);
 const char* hpusm_last_error(void);
@@ -86,10 +91,16 @@ int hpusm_knn2_hamming(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t n
  *   survivors:  score[s] = #{ i : seg has >= 2 rows and (double)d0 < (double)d1 * ratio }.
  *   score [nseg] int32 is overwritten.
  *   best_idx (optional, may be NULL) [nseg][nq] int32: global row index of the nearest neighbour where
- *   the ratio test passed, else -1 (feeds the RANSAC stage without a second pass). */
-size_t hpusm_knn2_hamming_segmented_workspace_bytes(int64_t nq, int64_t nt, int64_t nseg, int nbytes);
+ *   the ratio test passed, else -1 (feeds the RANSAC stage without a second pass).
+ *   `engine` is one of HPUSM_HAMMING_*: the __popc engine (XOR + POPC on the integer pipes, any shape), or the tensor-core
+ *   engine (tcgen05 kind::i8 on +-1 / -+64 expansions of the bits, s32 accumulators that hold 128 * Hamming + column; built
+ *   for 32-byte descriptors, >= 128 queries, >= 16384 database rows and images of >= 256 rows on average -- other shapes
+ *   return HPUSM_ERR_UNSUPPORTED); HPUSM_HAMMING_AUTO takes the tensor-core engine where it applies.  Both give the same
+ *   score and best_idx, bit for bit.  The workspace (256-byte aligned) holds the expanded operands of the tensor engine:
+ *   288 bytes per database row, every image padded to a multiple of 128 rows. */
+size_t hpusm_knn2_hamming_segmented_workspace_bytes(int64_t nq, int64_t nt, int64_t nseg, int nbytes, int engine);
 int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
-                                 const int64_t* seg_offsets, int64_t nseg, int nbytes, double ratio,
+                                 const int64_t* seg_offsets, int64_t nseg, int nbytes, double ratio, int engine,
                                  int32_t* score, int32_t* best_idx, void* ws, size_t ws_bytes,
                                  void* stream);
 

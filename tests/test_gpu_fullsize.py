@@ -61,6 +61,10 @@ def test_c3_orb_10k_images_properties(hpusm, cuda_device):
                                                           dtype=torch.uint8)  # flip only the lowest bit of each byte
     offs = torch.arange(0, nimg + 1, device=cuda_device, dtype=torch.int64) * per
     score, best = hpusm.knn2_hamming_segmented(query, db, offs, 0.8, want_best_idx=True)
+    # (0) AUTO ran the tensor-core engine at this shape; the __popc engine gives the same 10 000 x 2048 answers
+    s_popc, b_popc = hpusm.knn2_hamming_segmented(query, db, offs, 0.8, want_best_idx=True, engine="popc")
+    assert torch.equal(score, s_popc) and torch.equal(best, b_popc)
+    del s_popc, b_popc
     # (1) the planted images win the retrieval by a wide margin
     top = torch.topk(score, 3).indices.sort().values.tolist()
     assert top == planted and int(score[17]) >= per // 2 - 8

@@ -101,6 +101,67 @@ def test_hamming_segmented_retrieval(hpusm, cuda_device):
     assert set(top.tolist()) & set(planted.tolist())
 
 
+def _ragged_orb_case(seed, nimg, lo, hi, nq):
+    """Images of lo..hi rows with the edge lengths of the tensor engine's 128-row tiles, empty and 1-row images, exact
+    duplicates of query rows (distance 0 twice: the index decides) and near duplicates."""
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(lo, hi + 1, nimg).astype(np.int64)
+    sizes[:12] = [0, 1, 2, 127, 128, 129, 255, 256, 257, 0, 64, 65]
+    rng.shuffle(sizes)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    db = rng.integers(0, 256, (int(offs[-1]), 32), dtype=np.uint8)
+    query = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    for im in rng.choice(nimg, nimg // 3, replace=False):
+        n = int(sizes[im])
+        if n < 2:
+            continue
+        rows = rng.choice(n, min(n, nq) // 2, replace=False)
+        src = rng.choice(nq, len(rows), replace=False)
+        d = query[src].copy()
+        d[:, rng.integers(0, 32)] ^= np.uint8(1 << rng.integers(0, 8))      # one bit away
+        db[offs[im] + rows] = d
+        db[offs[im] + rows[: len(rows) // 4]] = query[src[: len(rows) // 4]]  # exact copies
+        if n > 4:
+            db[offs[im] + rows[0]] = db[offs[im] + rows[1]] = query[src[0]]   # two rows at distance 0
+    return query, db, offs
+
+
+@pytest.mark.parametrize("nq", [128, 700, 1024])
+def test_hamming_tensor_engine_equals_oracle(hpusm, cuda_device, nq):
+    """The tcgen05 engine of the segmented matcher (keys 128 * Hamming + column in the s32 accumulators) against the CPU
+    restatement of BFMatcher(NORM_HAMMING).knnMatch + filter_matches per image (features.py:59, :45-55): ragged images,
+    images shorter than / equal to / one past a tile, empty images, ties."""
+    query, db, offs = _ragged_orb_case(3 + nq, 70, 200, 900, nq)
+    score, best = hpusm.knn2_hamming_segmented(dev(query, cuda_device), dev(db, cuda_device), dev(offs, cuda_device), 0.8,
+                                               want_best_idx=True, engine="tc")
+    rs, rb = knn_oracle.segmented_scores(query, db, offs, 0.8)
+    np.testing.assert_array_equal(score.cpu().numpy(), rs)
+    np.testing.assert_array_equal(best.cpu().numpy(), rb)
+    assert rs.sum() > 1000
+
+
+def test_hamming_engines_agree(hpusm, cuda_device):
+    """Both engines, many units per SM, a query count that is not a multiple of the 256-row unit, several ratios."""
+    query, db, offs = _ragged_orb_case(91, 900, 256, 2300, 2048 + 77)
+    q, t, o = dev(query, cuda_device), dev(db, cuda_device), dev(offs, cuda_device)
+    for ratio in (0.8, 0.75, 1.0):
+        s1, b1 = hpusm.knn2_hamming_segmented(q, t, o, ratio, want_best_idx=True, engine="popc")
+        s2, b2 = hpusm.knn2_hamming_segmented(q, t, o, ratio, want_best_idx=True, engine="tc")
+        s3 = hpusm.knn2_hamming_segmented(q, t, o, ratio)   # AUTO resolves to the tensor engine at this shape
+        assert torch.equal(s1, s2) and torch.equal(b1, b2) and torch.equal(s1, s3)
+        assert int(s1.sum()) > 0
+
+
+def test_hamming_tensor_engine_shape_limits(hpusm, cuda_device):
+    """Outside its shape limits the explicit tensor engine refuses; AUTO takes the __popc engine and answers."""
+    query, db, offs, _ = hpusm.synth.orb_database(40, per_image=64, seed=2)
+    q, t, o = dev(query, cuda_device), dev(db, cuda_device), dev(offs, cuda_device)
+    with pytest.raises(RuntimeError, match="tensor-core engine"):
+        hpusm.knn2_hamming_segmented(q, t, o, 0.8, engine="tc")
+    rs, _ = knn_oracle.segmented_scores(query, db, offs, 0.8)
+    np.testing.assert_array_equal(hpusm.knn2_hamming_segmented(q, t, o, 0.8).cpu().numpy(), rs)
+
+
 def test_knn_merge_equals_unsplit(hpusm, cuda_device):
     q, t = hpusm.synth.orb_like(700, 9000, seed=3)
     full_i, full_d = hpusm.knn2_hamming(dev(q, cuda_device), dev(t, cuda_device))
