@@ -575,6 +575,19 @@ def run_orb(args, rank, world, device, hp):
                                           "expansion (32 -> 288 bytes per database row) and the plan kernels, outside kernel_ms",
                            "peak_clocks": i8_clocks, "ops_per_pair": 576,
                            "hbm_GBps_algorithmic": (db.numel() * 9 + query.numel()) / (k_ms * 1e-3) / 1e9}
+        if world == 1:
+            # the __popc engine (north_star's integer-pipe form, and the cross-check of the tensor engine) on the same inputs
+            tm2 = Timer(args, rank, world, device, hp)
+            tm2.steps = max(3, min(args.steps, 10))
+            r2 = tm2.run(lambda: rt.image_scores_sharded(query, db, offs, 0.8, hamming_engine="popc"))
+            assert torch.equal(r2["out"], scores), "the two Hamming engines disagree"
+            ppeak, lpeak = popc_peak(hp, device, "popc"), popc_peak(hp, device, "lop3")
+            k2 = r2["kernel_ms"] / max(r2["kernel_n"], 1) * 1e-3
+            out["popc_engine"] = {"value": pairs * tm2.steps / (r2["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": r2["ms"] / tm2.steps,
+                                  "identical_scores": True,
+                                  "roofline": {"bound": "integer pipes (16 LOP3 + 4 POPC.32 per pair)",
+                                               "frac": max(16.0 * pairs / lpeak, 4.0 * pairs / ppeak) / k2, "kernel_ms": k2 * 1e3,
+                                               "traffic": measured_traffic("orb:%dx%d" % (args.images, world))}}
     else:
         ppeak, lpeak = popc_peak(hp, device, "popc"), popc_peak(hp, device, "lop3")
         # per 256-bit pair the kernel issues 16 LOP3 (8 XOR + 4 carry-save adders) on the ALU pipe and 4 POPC on the XU pipe;

@@ -29,6 +29,7 @@
 // and add the survivors to score[image].
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "hamming_internal.cuh"
 #include "tc_ptx.cuh"
@@ -129,40 +130,41 @@ ham_tc_plan_kernel(const int64_t* __restrict__ seg_offsets, int64_t nseg, const 
 // 4 descriptor bits -> bit 7 of 4 bytes (bit i of x lands on bits i, i+7, i+14, i+21, i+28: all different, no carries)
 __device__ __forceinline__ uint32_t ht_spread4(uint32_t x) { return ((x & 0xFu) * 0x10204081u) & 0x80808080u; }
 
-// One block per tile of 128 operand rows: 16 lanes per row, lane = 16 descriptor bits -> 16 operand bytes (-64 where the bit
+// A block per tile of 128 operand rows (blocks stride over the tiles of splits [split_lo, split_hi)): 16 lanes per row, lane = 16 descriptor bits -> 16 operand bytes (-64 where the bit
 // is set, +64 where it is clear), so a warp reads 64 contiguous descriptor bytes and writes two full 256-byte row bodies per
 // store; augmentation bytes [column, 0,0,0, 0...] for a real row, [column, 127,127,127, 0...] and a zero main part for the
 // rows that pad an image to whole tiles.
 __global__ void __launch_bounds__(256)
-ham_tc_expand_db_kernel(const uint8_t* __restrict__ t, const int64_t* __restrict__ seg_offsets, const int32_t* __restrict__ tile_off,
-                        int64_t nseg, const int2* __restrict__ tile_info, uint8_t* __restrict__ tb) {
-  const int tile = blockIdx.x;
-  if (tile >= __ldg(tile_off + nseg)) return;
-  const int2 info = __ldg(tile_info + tile);
-  const int64_t seg_end = __ldg(seg_offsets + (info.y & 0x7fffffff) + 1);
-  const int64_t left = seg_end - (int64_t)info.x;
-  const int real_rows = left < HT_TN ? (int)left : HT_TN;
-  const uint8_t* src = t + (int64_t)info.x * 32;
-  uint8_t* dst = tb + (int64_t)tile * HT_TN * HT_KA;
+ham_tc_expand_db_kernel(const uint8_t* __restrict__ t, const int64_t* __restrict__ seg_offsets, const int32_t* __restrict__ split_tile,
+                        int split_lo, int split_hi, const int2* __restrict__ tile_info, uint8_t* __restrict__ tb) {
+  const int tile_lo = __ldg(split_tile + split_lo), tile_hi = __ldg(split_tile + split_hi);
   const int sub = threadIdx.x & 15, r0 = threadIdx.x >> 4;   // 16 rows per pass
+  for (int tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+    const int2 info = __ldg(tile_info + tile);
+    const int64_t seg_end = __ldg(seg_offsets + (info.y & 0x7fffffff) + 1);
+    const int64_t left = seg_end - (int64_t)info.x;
+    const int real_rows = left < HT_TN ? (int)left : HT_TN;
+    const uint8_t* src = t + (int64_t)info.x * 32;
+    uint8_t* dst = tb + (int64_t)tile * HT_TN * HT_KA;
 #pragma unroll
-  for (int p = 0; p < HT_TN / 16; ++p) {
-    const int r = p * 16 + r0;
-    uint4 w = make_uint4(0u, 0u, 0u, 0u);
-    if (r < real_rows) {
-      const uint32_t b = __ldg(reinterpret_cast<const uint16_t*>(src + r * 32) + sub);
-      w.x = ht_spread4(b) ^ 0x40404040u;          // set bit: 0xC0 = -64, clear bit: 0x40 = +64
-      w.y = ht_spread4(b >> 4) ^ 0x40404040u;
-      w.z = ht_spread4(b >> 8) ^ 0x40404040u;
-      w.w = ht_spread4(b >> 12) ^ 0x40404040u;
+    for (int p = 0; p < HT_TN / 16; ++p) {
+      const int r = p * 16 + r0;
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if (r < real_rows) {
+        const uint32_t b = __ldg(reinterpret_cast<const uint16_t*>(src + r * 32) + sub);
+        w.x = ht_spread4(b) ^ 0x40404040u;          // set bit: 0xC0 = -64, clear bit: 0x40 = +64
+        w.y = ht_spread4(b >> 4) ^ 0x40404040u;
+        w.z = ht_spread4(b >> 8) ^ 0x40404040u;
+        w.w = ht_spread4(b >> 12) ^ 0x40404040u;
+      }
+      *reinterpret_cast<uint4*>(dst + r * HT_KA + sub * 16) = w;
     }
-    *reinterpret_cast<uint4*>(dst + r * HT_KA + sub * 16) = w;
-  }
-  {
-    const int r = threadIdx.x >> 1;
-    uint4 w = make_uint4(0u, 0u, 0u, 0u);
-    if ((threadIdx.x & 1) == 0) w.x = (uint32_t)r | (r < real_rows ? 0u : 0x7F7F7F00u);
-    *reinterpret_cast<uint4*>(dst + r * HT_KA + HT_KB + (threadIdx.x & 1) * 16) = w;
+    {
+      const int r = threadIdx.x >> 1;
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if ((threadIdx.x & 1) == 0) w.x = (uint32_t)r | (r < real_rows ? 0u : 0x7F7F7F00u);
+      *reinterpret_cast<uint4*>(dst + r * HT_KA + HT_KB + (threadIdx.x & 1) * 16) = w;
+    }
   }
 }
 
@@ -209,7 +211,7 @@ __device__ __forceinline__ uint32_t ht_min32_shifted(const uint32_t (&acc)[32], 
 
 __global__ void __launch_bounds__(HT_THREADS, 1)
 ham_tc_segmented_kernel(const uint8_t* __restrict__ qa, const __grid_constant__ CUtensorMap map_t,
-                        const __grid_constant__ CUtensorMap map_ta, int64_t nq, int q_blocks, int splits,
+                        const __grid_constant__ CUtensorMap map_ta, int64_t nq, int q_blocks, int split0, int splits,
                         const int32_t* __restrict__ split_tile, const int2* __restrict__ tile_info, double ratio,
                         int32_t* __restrict__ score, int32_t* __restrict__ best_idx) {
   extern __shared__ uint8_t ht_smem_raw[];
@@ -257,7 +259,7 @@ ham_tc_segmented_kernel(const uint8_t* __restrict__ qa, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ta) : "memory");
       uint32_t it = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int split = u / q_blocks;
+        const int split = split0 + u / q_blocks;
         const int t0 = __ldg(split_tile + split), t1 = __ldg(split_tile + split + 1);
         for (int j = t0; j < t1; ++j, ++it) {
           const int s = it % HT_STAGES;
@@ -277,7 +279,7 @@ ham_tc_segmented_kernel(const uint8_t* __restrict__ qa, const __grid_constant__ 
     const uint32_t b_addr = smem_u32(smem_b);
     const uint64_t adesc_aug = umma_desc_sw32(smem_u32(smem_aaug));
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
-      const int split = u / q_blocks;
+      const int split = split0 + u / q_blocks;
       const int t0 = __ldg(split_tile + split), t1 = __ldg(split_tile + split + 1);
       mbar_wait(a_ready, un & 1);
       tc_fence_after();
@@ -321,7 +323,7 @@ ham_tc_segmented_kernel(const uint8_t* __restrict__ qa, const __grid_constant__ 
     const int rq = m * 128 + quarter * 32 + lane;
     uint32_t un = 0, buf = (uint32_t)m, slot = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
-      const int split = u / q_blocks, qb = u - split * q_blocks;
+      const int qb = u % q_blocks, split = split0 + u / q_blocks;
       const int t0 = __ldg(split_tile + split), t1 = __ldg(split_tile + split + 1);
       const int64_t row = (int64_t)qb * HT_QB + rq;
       // -- the unit's query rows go into tensor memory: thread = row; this warp stores words [32 cg, 32 cg + 32) --
@@ -412,25 +414,41 @@ ham_tc_segmented_kernel(const uint8_t* __restrict__ qa, const __grid_constant__ 
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
+// Default: expand the whole database, then match it (one launch each).  HPUSM_HAMMING_CHUNKS=n (2..8) cuts the database into
+// n chunks of whole images (each a run of `spc` splits) and expands chunk c + 1 on an internal side stream while chunk c is
+// being matched -- the expansion is HBM-write bound and needs few issue slots, the matching kernel is tensor-pipe bound and
+// leaves HBM idle, two expansion blocks fit on an SM beside the matching CTA.  Measured on C3: the step is
+// no shorter (8.56 ms with 8 chunks against 8.49 ms), because the board sits at its power cap either way and the
+// matching kernel slows down by what the overlapped expansion draws.  Kept as an experiment switch, off by default.
 struct HtLayout {
   size_t tile_off, split_tile, tile_info, qa, tb, total;
   int64_t max_tiles;
-  int splits, q_blocks;
+  int chunks, spc /* splits per chunk */, q_blocks;
 };
+
+static int ht_env_chunks() {
+  static const int v = []() { const char* e = getenv("HPUSM_HAMMING_CHUNKS"); return e ? atoi(e) : 0; }();
+  return v;
+}
 
 static HtLayout ht_layout(int64_t nq, int64_t nt, int64_t nseg) {
   HtLayout L;
   L.max_tiles = nt / HT_TN + nseg;    // sum over images of ceil(rows / 128) <= this
   L.q_blocks = (int)((nq + HT_QB - 1) / HT_QB);
-  int64_t s = (2 * (int64_t)sm_count() + L.q_blocks - 1) / L.q_blocks;
-  const int64_t by_tiles = L.max_tiles / 32;   // at least ~32 tiles per unit
-  if (s > by_tiles) s = by_tiles;
-  if (s > nseg) s = nseg;
-  if (s < 1) s = 1;
-  L.splits = (int)s;
+  int64_t chunks = ht_env_chunks() > 0 ? ht_env_chunks() : 1;
+  if (chunks > 8) chunks = 8;
+  if (chunks > nseg) chunks = nseg;
+  if (chunks < 1) chunks = 1;
+  int64_t spc = (2 * (int64_t)sm_count() + L.q_blocks - 1) / L.q_blocks;   // two units per SM and launch
+  const int64_t by_tiles = L.max_tiles / chunks / 32;                        // at least ~32 tiles per unit
+  if (spc > by_tiles) spc = by_tiles;
+  if (spc > nseg / chunks) spc = nseg / chunks;
+  if (spc < 1) spc = 1;
+  L.chunks = (int)chunks;
+  L.spc = (int)spc;
   size_t off = 0;
   L.tile_off = off; off += align_up((size_t)(nseg + 1) * sizeof(int32_t), 1024);
-  L.split_tile = off; off += align_up((size_t)(L.splits + 1) * sizeof(int32_t), 1024);
+  L.split_tile = off; off += align_up((size_t)(L.chunks * L.spc + 1) * sizeof(int32_t), 1024);
   L.tile_info = off; off += align_up((size_t)L.max_tiles * sizeof(int2), 1024);
   L.qa = off; off += align_up((size_t)nq * HT_KB, 1024);
   L.tb = off; off += align_up((size_t)L.max_tiles * HT_TN * HT_KA, 1024);
@@ -447,6 +465,22 @@ bool hamming_tc_eligible(int64_t nq, int64_t nt, int64_t nseg, int nbytes) {
 
 size_t hamming_tc_workspace_bytes(int64_t nq, int64_t nt, int64_t nseg) { return ht_layout(nq, nt, nseg).total; }
 
+// One side stream per device, created on first use (shared by all host threads: work on it is ordered by events only).
+static cudaStream_t ht_side_stream(int dev) {
+  static std::atomic<cudaStream_t> streams[64];
+  if (dev < 0 || dev >= 64) return nullptr;
+  cudaStream_t s = streams[dev].load(std::memory_order_acquire);
+  if (s) return s;
+  cudaStream_t made = nullptr;
+  if (cudaStreamCreateWithFlags(&made, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  cudaStream_t expected = nullptr;
+  if (!streams[dev].compare_exchange_strong(expected, made, std::memory_order_acq_rel)) {
+    cudaStreamDestroy(made);
+    return expected;
+  }
+  return made;
+}
+
 // score and best_idx are already cleared (score 0, best_idx -1) by the caller.
 int hamming_tc_segmented(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, const int64_t* seg_offsets, int64_t nseg,
                          double ratio, int32_t* score, int32_t* best_idx, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -459,17 +493,7 @@ int hamming_tc_segmented(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t
   int2* tile_info = reinterpret_cast<int2*>(base + L.tile_info);
   uint8_t* qa = reinterpret_cast<uint8_t*>(base + L.qa);
   uint8_t* tb = reinterpret_cast<uint8_t*>(base + L.tb);
-
-  HPUSM_LAUNCH(ham_tc_scan_kernel, 1, 1024, 0, st, seg_offsets, nseg, tile_off);
-  HPUSM_CHECK_LAUNCH();
-  HPUSM_LAUNCH(ham_tc_plan_kernel, (unsigned)((nseg + 255) / 256), 256, 0, st, seg_offsets, nseg, tile_off, L.splits, tile_info,
-               split_tile);
-  HPUSM_CHECK_LAUNCH();
-  HPUSM_LAUNCH(ham_tc_expand_q_kernel, (unsigned)((nq + 15) / 16), 256, 0, st, q, nq, qa);
-  HPUSM_CHECK_LAUNCH();
-  HPUSM_LAUNCH(ham_tc_expand_db_kernel, (unsigned)L.max_tiles, 256, 0, st, t, seg_offsets, tile_off, nseg,
-               tile_info, tb);
-  HPUSM_CHECK_LAUNCH();
+  const int splits = L.chunks * L.spc;
 
   CUtensorMap map_t, map_ta;
   int rc = tc_make_map(&map_t, tb, L.max_tiles * HT_TN, HT_KA, 128, CU_TENSOR_MAP_SWIZZLE_128B, HT_TN, 1);
@@ -482,12 +506,61 @@ int hamming_tc_segmented(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t
     HPUSM_CUDA_OK(cudaFuncSetAttribute(ham_tc_segmented_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
     attr_done[dev].store(true, std::memory_order_release);
   }
-  const int units = L.q_blocks * L.splits;
-  const int grid = units < sm_count() ? units : sm_count();
-  HPUSM_LAUNCH_TIMED(ham_tc_segmented_kernel, grid, HT_THREADS, HT_SMEM_BYTES, st, qa, map_t, map_ta, nq, L.q_blocks, L.splits,
-                     split_tile, tile_info, ratio, score, best_idx);
+  cudaStream_t side = L.chunks > 1 ? ht_side_stream(dev) : nullptr;
+  HPUSM_REQUIRE(L.chunks == 1 || side, HPUSM_ERR_CUDA, "hamming tensor engine: cannot create the expansion stream");
+
+  HPUSM_LAUNCH(ham_tc_scan_kernel, 1, 1024, 0, st, seg_offsets, nseg, tile_off);
   HPUSM_CHECK_LAUNCH();
-  return HPUSM_OK;
+  HPUSM_LAUNCH(ham_tc_plan_kernel, (unsigned)((nseg + 255) / 256), 256, 0, st, seg_offsets, nseg, tile_off, splits, tile_info,
+               split_tile);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(ham_tc_expand_q_kernel, (unsigned)((nq + 15) / 16), 256, 0, st, q, nq, qa);
+  HPUSM_CHECK_LAUNCH();
+
+  const int units = L.q_blocks * L.spc;
+  const int grid = units < sm_count() ? units : sm_count();
+  const unsigned expand_grid = (unsigned)(2 * sm_count());
+  if (L.chunks == 1) {
+    HPUSM_LAUNCH(ham_tc_expand_db_kernel, expand_grid * 4, 256, 0, st, t, seg_offsets, split_tile, 0, splits, tile_info, tb);
+    HPUSM_CHECK_LAUNCH();
+    HPUSM_LAUNCH_TIMED(ham_tc_segmented_kernel, grid, HT_THREADS, HT_SMEM_BYTES, st, qa, map_t, map_ta, nq, L.q_blocks, 0, L.spc,
+                       split_tile, tile_info, ratio, score, best_idx);
+    HPUSM_CHECK_LAUNCH();
+    return HPUSM_OK;
+  }
+  // fork: the side stream starts after the plan; chunk c is matched on `st` once its expansion has finished
+  cudaEvent_t ev[9];
+  int nev = 0;
+  auto new_event = [&]() -> cudaEvent_t {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ev[nev++] = e;
+    return e;
+  };
+  int result = HPUSM_OK;
+  do {
+    cudaEvent_t planned = new_event();
+    if (!planned || cudaEventRecord(planned, st) != cudaSuccess || cudaStreamWaitEvent(side, planned, 0) != cudaSuccess) {
+      result = HPUSM_ERR_CUDA; break;
+    }
+    for (int c = 0; c < L.chunks && result == HPUSM_OK; ++c) {
+      // the first chunk is expanded with the whole GPU, the later ones with two blocks per SM beside the matching CTAs
+      ham_tc_expand_db_kernel<<<c == 0 ? expand_grid * 4 : expand_grid, 256, 0, side>>>(t, seg_offsets, split_tile, c * L.spc,
+                                                                                        (c + 1) * L.spc, tile_info, tb);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      cudaEvent_t done = new_event();
+      if (cudaGetLastError() != cudaSuccess || !done || cudaEventRecord(done, side) != cudaSuccess ||
+          cudaStreamWaitEvent(st, done, 0) != cudaSuccess) {
+        result = HPUSM_ERR_CUDA; break;
+      }
+      HPUSM_LAUNCH_TIMED(ham_tc_segmented_kernel, grid, HT_THREADS, HT_SMEM_BYTES, st, qa, map_t, map_ta, nq, L.q_blocks, c * L.spc,
+                         L.spc, split_tile, tile_info, ratio, score, best_idx);
+      if (cudaGetLastError() != cudaSuccess) result = HPUSM_ERR_CUDA;
+    }
+  } while (false);
+  for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);   // released by the runtime once the recorded work has completed
+  if (result != HPUSM_OK) set_error("hamming tensor engine: launch / event failure: %s", cudaGetErrorString(cudaPeekAtLastError()));
+  return result;
 }
 
 }  // namespace hpusm
