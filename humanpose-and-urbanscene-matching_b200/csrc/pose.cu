@@ -756,81 +756,20 @@ __device__ void block_topk(Get get, int64_t count, int k, float* out_s, int64_t*
   }
 }
 
-// One CTA = TK_TILE database entries held in registers (TK_PER per thread, entry = lo + r*TK_THREADS + tid, so a
-// thread's entries are in increasing index order); k rounds of block-wide lexicographic arg-min over the registers,
-// the winner's owner retires its entry.  One pass over match/score (5 B per pose), no re-reads.
-constexpr int TK_PER = 16;
-constexpr int TK_TILE = TK_THREADS * TK_PER;
-
-__global__ void __launch_bounds__(TK_THREADS)
-pose_topk_partial_kernel(const uint8_t* __restrict__ match, const float* __restrict__ score, int64_t n,
-                         int64_t index_offset, int k, float* __restrict__ part_s, int64_t* __restrict__ part_i,
-                         int32_t* __restrict__ match_count) {
-  __shared__ float red_s[TK_THREADS / 32];
-  __shared__ int red_r[TK_THREADS / 32];   // winner's slot: r * TK_THREADS + tid, or -1
-  const int64_t lo = (int64_t)blockIdx.x * TK_TILE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float v[TK_PER];
-  int cnt = 0;
-#pragma unroll
-  for (int r = 0; r < TK_PER; ++r) {
-    const int64_t g = lo + (int64_t)r * TK_THREADS + tid;
-    float s = INFINITY;
-    if (g < n && match[g]) {
-      ++cnt;
-      const float x = score[g];
-      if (x == x) s = x;  // NaN scores never rank
-    }
-    v[r] = s;
-  }
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0 && cnt) atomicAdd(match_count, cnt);
-  float* out_s = part_s + (int64_t)blockIdx.x * k;
-  int64_t* out_i = part_i + (int64_t)blockIdx.x * k;
-  for (int round = 0; round < k; ++round) {
-    float bs = INFINITY;
-    int br = -1;
-#pragma unroll
-    for (int r = 0; r < TK_PER; ++r)
-      if (v[r] < bs) { bs = v[r]; br = r * TK_THREADS + tid; }   // strict: lowest index wins inside the thread
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int orr = __shfl_xor_sync(0xffffffffu, br, o);
-      if (orr >= 0 && (br < 0 || os < bs || (os == bs && orr < br))) { bs = os; br = orr; }
-    }
-    if (lane == 0) { red_s[warp] = bs; red_r[warp] = br; }
-    __syncthreads();
-    bs = red_s[0]; br = red_r[0];
-#pragma unroll
-    for (int w = 1; w < TK_THREADS / 32; ++w) {
-      const float os = red_s[w];
-      const int orr = red_r[w];
-      if (orr >= 0 && (br < 0 || os < bs || (os == bs && orr < br))) { bs = os; br = orr; }
-    }
-    __syncthreads();
-    if (br < 0) {  // ran out of candidates: pad the rest
-      for (int rr = round + tid; rr < k; rr += TK_THREADS) { out_s[rr] = INFINITY; out_i[rr] = -1; }
-      break;
-    }
-    if (tid == 0) { out_s[round] = bs; out_i[round] = lo + br + index_offset; }
-    if ((br % TK_THREADS) == tid) {
-      const int r = br / TK_THREADS;
-#pragma unroll
-      for (int q = 0; q < TK_PER; ++q) if (q == r) v[q] = INFINITY;
-    }
-  }
-}
+constexpr int TK_TILE = 4096;   // candidates one reduction CTA folds into k; smallest tile of the selection passes
 
 // One reduction level over candidate lists: CTA b takes candidates [b * TK_TILE, (b + 1) * TK_TILE) and writes its k
 // best to slot b of the output.  Levels repeat until one CTA is left (a single CTA over the 39 k candidates of a
 // 10 M pose database took 0.5 ms -- a fifth of the whole retrieval step; two levels take a few microseconds).
 __global__ void __launch_bounds__(TK_THREADS)
-pose_topk_reduce_kernel(const float* __restrict__ part_s, const int64_t* __restrict__ part_i, int64_t count, int k,
-                        float* __restrict__ top_s, int64_t* __restrict__ top_i) {
+pose_topk_reduce_kernel(const float* __restrict__ part_s, const int64_t* __restrict__ part_i, int64_t count,
+                        const int32_t* __restrict__ count_ptr /* optional: the count lives on the device, `count` is its cap */,
+                        int k, float* __restrict__ top_s, int64_t* __restrict__ top_i) {
   __shared__ float red_s[TK_THREADS / 32];
   __shared__ int64_t red_i[TK_THREADS / 32];
+  if (count_ptr) count = min(count, (int64_t)*count_ptr);
   const int64_t lo = (int64_t)blockIdx.x * TK_TILE;
-  const int64_t cnt = count - lo < TK_TILE ? count - lo : TK_TILE;
+  const int64_t cnt = count - lo < TK_TILE ? (count - lo > 0 ? count - lo : 0) : TK_TILE;
   auto get = [&](int64_t i, float& s, int64_t& id) {
     id = part_i[lo + i];
     if (id < 0) return false;
@@ -840,10 +779,191 @@ pose_topk_reduce_kernel(const float* __restrict__ part_s, const int64_t* __restr
   block_topk(get, cnt, k, top_s + (int64_t)blockIdx.x * k, top_i + (int64_t)blockIdx.x * k, red_s, red_i);
 }
 
-static int topk_blocks(int64_t n) {
-  int64_t b = (n + TK_TILE - 1) / TK_TILE;
-  if (b < 1) b = 1;
-  return (int)b;
+// The k best of a candidate list whose length lives on the device (all entries valid).  Short lists (the usual case: a few
+// dozen candidates) are ranked by counting in shared memory and go straight to the final output from CTA 0; long lists are
+// folded TK_TILE candidates per CTA into k-lists for pose_topk_final_kernel.
+constexpr int TK_RANK_MAX = 1024;
+__global__ void __launch_bounds__(TK_THREADS)
+pose_topk_select_kernel(const float* __restrict__ cand_s, const int64_t* __restrict__ cand_i, int64_t cap,
+                        const int32_t* __restrict__ count_ptr, int k, float* __restrict__ lvl_s, int64_t* __restrict__ lvl_i,
+                        float* __restrict__ top_s, int64_t* __restrict__ top_i) {
+  __shared__ float red_s[TK_THREADS / 32];
+  __shared__ int64_t red_i[TK_THREADS / 32];
+  __shared__ float rs[TK_RANK_MAX];
+  __shared__ int64_t ri[TK_RANK_MAX];
+  const int64_t count = min(cap, (int64_t)*count_ptr);
+  const bool direct = count <= TK_TILE;
+  if (direct && blockIdx.x != 0) return;
+  float* out_s = direct ? top_s : lvl_s + (int64_t)blockIdx.x * k;
+  int64_t* out_i = direct ? top_i : lvl_i + (int64_t)blockIdx.x * k;
+  const int64_t lo = (int64_t)blockIdx.x * TK_TILE;
+  const int64_t cnt = count - lo < TK_TILE ? (count - lo > 0 ? count - lo : 0) : TK_TILE;
+  if (cnt <= TK_RANK_MAX) {
+    for (int c = threadIdx.x; c < cnt; c += TK_THREADS) { rs[c] = cand_s[lo + c]; ri[c] = cand_i[lo + c]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cnt; c += TK_THREADS) {
+      const float s = rs[c];
+      const int64_t id = ri[c];
+      int rank = 0;
+      for (int o = 0; o < cnt; ++o) rank += (rs[o] < s || (rs[o] == s && ri[o] < id)) ? 1 : 0;
+      if (rank < k) { out_s[rank] = s; out_i[rank] = id; }
+    }
+    for (int r = (int)cnt + threadIdx.x; r < k; r += TK_THREADS) { out_s[r] = INFINITY; out_i[r] = -1; }
+    return;
+  }
+  auto get = [&](int64_t i, float& s, int64_t& id) {
+    id = cand_i[lo + i];
+    s = cand_s[lo + i];
+    return true;
+  };
+  block_topk(get, cnt, k, out_s, out_i, red_s, red_i);
+}
+
+// Last level after pose_topk_select_kernel: nothing to do when the list was short enough for the direct path.
+__global__ void __launch_bounds__(TK_THREADS)
+pose_topk_final_kernel(const float* __restrict__ lvl_s, const int64_t* __restrict__ lvl_i, int64_t lvl_count, int64_t cap,
+                       const int32_t* __restrict__ count_ptr, int k, float* __restrict__ top_s, int64_t* __restrict__ top_i) {
+  __shared__ float red_s[TK_THREADS / 32];
+  __shared__ int64_t red_i[TK_THREADS / 32];
+  if (min(cap, (int64_t)*count_ptr) <= TK_TILE) return;
+  auto get = [&](int64_t i, float& s, int64_t& id) {
+    id = lvl_i[i];
+    if (id < 0) return false;
+    s = lvl_s[i];
+    return true;
+  };
+  block_topk(get, lvl_count, k, top_s, top_i, red_s, red_i);
+}
+
+// ---- threshold selection: the k best of n scored poses in two streaming passes ------------------------------------------
+// Pass 1 (pose_topk_min_kernel): the lexicographic minimum (score, index) of every block's tile of entries.  The k-th
+// smallest of those minima, T (pose_topk_kth_kernel, rank counting), is an upper bound of the k-th smallest entry (k entries
+// are <= T: the minima themselves), and the entries <= T all lie in the k tiles whose minima are <= T: at most k * tile of
+// them, usually a few dozen.  With fewer than k tiles every matching entry is a candidate.
+// Pass 2 (pose_topk_filter_kernel) appends them to a candidate list; pose_topk_reduce_kernel picks the k best.  Both
+// passes stream match + score (5 B per pose; the second one mostly from L2) instead of k block-wide arg-min rounds per tile.
+constexpr int TK_MAX_TILES = 512;     // tiles of the selection passes: the k-th smallest of their minima is found by rank counting
+
+struct TkThreshold {
+  float s;
+  int pad;
+  int64_t i;
+};
+
+__device__ __forceinline__ bool tk_less(float sa, int64_t ia, float sb, int64_t ib) { return sa < sb || (sa == sb && ia < ib); }
+
+template <typename F>
+__device__ __forceinline__ void tk_scan_tile(const uint8_t* __restrict__ match, const float* __restrict__ score, int64_t lo,
+                                             int64_t hi, F f) {
+  // 16 consecutive entries per thread and pass: one 16-byte match load + four 16-byte score loads, all independent
+  // (lo is a multiple of 16)
+  const bool vec = ((reinterpret_cast<uintptr_t>(match) | reinterpret_cast<uintptr_t>(score)) & 15) == 0;
+  for (int64_t g = lo + 16 * (int64_t)threadIdx.x; g < hi; g += 16 * TK_THREADS) {
+    if (vec && g + 16 <= hi) {
+      const uint4 m = *reinterpret_cast<const uint4*>(match + g);
+      if ((m.x | m.y | m.z | m.w) == 0u) continue;
+      const float4* sp = reinterpret_cast<const float4*>(score + g);
+      const float4 v0 = sp[0], v1 = sp[1], v2 = sp[2], v3 = sp[3];
+      const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+      const float4 vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (mw[q] & 0x000000ffu) f(vv[q].x, g + 4 * q);
+        if (mw[q] & 0x0000ff00u) f(vv[q].y, g + 4 * q + 1);
+        if (mw[q] & 0x00ff0000u) f(vv[q].z, g + 4 * q + 2);
+        if (mw[q] & 0xff000000u) f(vv[q].w, g + 4 * q + 3);
+      }
+    } else {
+      for (int64_t e = g; e < min(hi, g + 16); ++e)
+        if (match[e]) f(score[e], e);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+pose_topk_min_kernel(const uint8_t* __restrict__ match, const float* __restrict__ score, int64_t n, int64_t tile,
+                     float* __restrict__ min_s, int64_t* __restrict__ min_i, int32_t* __restrict__ match_count) {
+  __shared__ float red_s[TK_THREADS / 32];
+  __shared__ int64_t red_i[TK_THREADS / 32];
+  const int64_t lo = (int64_t)blockIdx.x * tile, hi = min(n, lo + tile);
+  float bs = INFINITY;
+  int64_t bi = ((int64_t)1 << 62) + blockIdx.x;   // an empty tile ranks after every entry, tiles among themselves by number
+  int cnt = 0;
+  tk_scan_tile(match, score, lo, hi, [&](float x, int64_t g) {
+    ++cnt;
+    if (x == x && tk_less(x, g, bs, bi)) { bs = x; bi = g; }   // NaN scores never rank
+  });
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (tk_less(os, oi, bs, bi)) { bs = os; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    red_s[warp] = bs; red_i[warp] = bi;
+    if (cnt) atomicAdd(match_count, cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < TK_THREADS / 32; ++w)
+      if (tk_less(red_s[w], red_i[w], bs, bi)) { bs = red_s[w]; bi = red_i[w]; }
+    min_s[blockIdx.x] = bs; min_i[blockIdx.x] = bi;
+  }
+}
+
+// T = the k-th smallest tile minimum (nb >= k): every block stages all minima in shared memory, a thread per tile counts the
+// minima before its own.  The minimum of tile a precedes that of tile b on equal scores iff a < b (tiles partition the index
+// range in order); an empty tile (score +inf, index >= 2^62) follows every entry.
+constexpr int TK_KTH_THREADS = 256;   // 8 tiles per block, a warp per tile: the lanes share the counting
+__global__ void __launch_bounds__(TK_KTH_THREADS)
+pose_topk_kth_kernel(const float* __restrict__ min_s, const int64_t* __restrict__ min_i, int nb, int k, TkThreshold* __restrict__ thr) {
+  __shared__ float ss[TK_MAX_TILES];
+  __shared__ int key[TK_MAX_TILES];
+#pragma unroll
+  for (int o = threadIdx.x; o < TK_MAX_TILES; o += TK_KTH_THREADS) {
+    const bool in = o < nb;
+    const float s = in ? __ldg(min_s + o) : INFINITY;
+    const int64_t i = in ? __ldg(min_i + o) : 0;
+    ss[o] = s;
+    key[o] = o + (i >= ((int64_t)1 << 62) ? nb : 0);
+  }
+  __syncthreads();
+  // fewer tiles than k: the minima bound nothing, every matching entry is a candidate (at most nb * tile <= cap of them)
+  if (nb < k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { thr->s = INFINITY; thr->i = INT64_MAX; }
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (TK_KTH_THREADS / 32) + (threadIdx.x >> 5);
+  if (j >= nb) return;
+  const float s = ss[j];
+  const int kj = key[j];
+  int rank = 0;
+  for (int o = lane; o < nb; o += 32) rank += (ss[o] < s || (ss[o] == s && key[o] < kj)) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  if (lane == 0 && rank == k - 1) { thr->s = s; thr->i = min_i[j]; }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+pose_topk_filter_kernel(const uint8_t* __restrict__ match, const float* __restrict__ score, int64_t n, int64_t tile,
+                        int64_t index_offset, const TkThreshold* __restrict__ thr, int64_t cap, float* __restrict__ cand_s,
+                        int64_t* __restrict__ cand_i, int32_t* __restrict__ cand_count) {
+  const float ts = thr->s;
+  const int64_t ti = thr->i;
+  const int64_t lo = (int64_t)blockIdx.x * tile, hi = min(n, lo + tile);
+  tk_scan_tile(match, score, lo, hi, [&](float x, int64_t g) {
+    if (x == x && !tk_less(ts, ti, x, g)) {
+      const int slot = atomicAdd(cand_count, 1);
+      if (slot < cap) { cand_s[slot] = x; cand_i[slot] = g + index_offset; }
+    }
+  });
+}
+
+static int64_t topk_tile(int64_t n) {
+  int64_t tile = (n + TK_MAX_TILES - 1) / TK_MAX_TILES;
+  if (tile < TK_TILE) tile = TK_TILE;
+  return (tile + TK_TILE - 1) / TK_TILE * TK_TILE;
 }
 
 }  // namespace hpusm
@@ -1006,40 +1126,73 @@ int hpusm_feature_scaling_batch(const double* pts, int64_t n, int npts, double* 
   return HPUSM_OK;
 }
 
-// workspace: two (score, index) candidate buffers, ping-ponged by the reduction levels
+// workspace: tile minima, the threshold, the candidate list (at most k tiles of entries) and one level of k-lists
+struct TkLayout {
+  size_t min_s, min_i, thr, count, cand_s, cand_i, lvl_s, lvl_i, total;
+  int64_t tile, cap;
+  int nb, lvl_blocks;
+};
+
+static TkLayout tk_layout(int64_t n, int k) {
+  TkLayout L;
+  L.tile = topk_tile(n > 0 ? n : 1);
+  L.nb = (int)(((n > 0 ? n : 1) + L.tile - 1) / L.tile);
+  L.cap = (int64_t)k * L.tile;
+  L.lvl_blocks = (int)((L.cap + TK_TILE - 1) / TK_TILE);
+  size_t off = 0;
+  L.min_s = off; off += align_up((size_t)L.nb * sizeof(float), 256);
+  L.min_i = off; off += align_up((size_t)L.nb * sizeof(int64_t), 256);
+  L.thr = off; off += 256;
+  L.count = off; off += 256;
+  L.cand_s = off; off += align_up((size_t)L.cap * sizeof(float), 256);
+  L.cand_i = off; off += align_up((size_t)L.cap * sizeof(int64_t), 256);
+  L.lvl_s = off; off += align_up((size_t)L.lvl_blocks * k * sizeof(float), 256);
+  L.lvl_i = off; off += align_up((size_t)L.lvl_blocks * k * sizeof(int64_t), 256);
+  L.total = off;
+  return L;
+}
+
 size_t hpusm_pose_topk_workspace_bytes(int64_t n, int k) {
-  const int b = topk_blocks(n > 0 ? n : 1);
-  return 2 * (align_up((size_t)b * k * sizeof(float), 256) + align_up((size_t)b * k * sizeof(int64_t), 256));
+  if (k <= 0 || k > TK_MAXK) return 256;
+  return tk_layout(n, k).total;
 }
 
 int hpusm_pose_topk(const uint8_t* match, const float* score, int64_t n, int64_t index_offset, int k, float* top_score,
                     int64_t* top_index, int32_t* match_count, void* ws, size_t ws_bytes, void* stream) {
   HPUSM_REQUIRE(n >= 0 && k > 0 && k <= TK_MAXK, HPUSM_ERR_INVALID, "hpusm_pose_topk: k must be in 1..%d", TK_MAXK);
-  HPUSM_REQUIRE(n < ((int64_t)1 << 31) * TK_TILE, HPUSM_ERR_UNSUPPORTED, "hpusm_pose_topk: too many poses for one call");
+  HPUSM_REQUIRE(n < ((int64_t)1 << 33), HPUSM_ERR_UNSUPPORTED, "hpusm_pose_topk: too many poses for one call");
   HPUSM_REQUIRE(top_score && top_index && match_count && (n == 0 || (match && score)), HPUSM_ERR_INVALID,
                 "hpusm_pose_topk: null pointer");
   cudaStream_t st = as_stream(stream);
-  const int b = topk_blocks(n > 0 ? n : 1);
-  const size_t need = hpusm_pose_topk_workspace_bytes(n, k);
-  HPUSM_REQUIRE(ws && is_aligned(ws, 256) && ws_bytes >= need, HPUSM_ERR_WORKSPACE,
-                "hpusm_pose_topk: workspace needs %zu bytes, got %zu", need, ws_bytes);
-  const size_t s_bytes = align_up((size_t)b * k * sizeof(float), 256), i_bytes = align_up((size_t)b * k * sizeof(int64_t), 256);
+  const TkLayout L = tk_layout(n, k);
+  HPUSM_REQUIRE(ws && is_aligned(ws, 256) && ws_bytes >= L.total, HPUSM_ERR_WORKSPACE,
+                "hpusm_pose_topk: workspace needs %zu bytes, got %zu", L.total, ws_bytes);
   char* w = reinterpret_cast<char*>(ws);
-  float* ps[2] = {reinterpret_cast<float*>(w), reinterpret_cast<float*>(w + s_bytes + i_bytes)};
-  int64_t* pi[2] = {reinterpret_cast<int64_t*>(w + s_bytes), reinterpret_cast<int64_t*>(w + 2 * s_bytes + i_bytes)};
+  float* min_s = reinterpret_cast<float*>(w + L.min_s);
+  int64_t* min_i = reinterpret_cast<int64_t*>(w + L.min_i);
+  TkThreshold* thr = reinterpret_cast<TkThreshold*>(w + L.thr);
+  int32_t* cand_count = reinterpret_cast<int32_t*>(w + L.count);
+  float* cand_s = reinterpret_cast<float*>(w + L.cand_s);
+  int64_t* cand_i = reinterpret_cast<int64_t*>(w + L.cand_i);
+  float* lvl_s = reinterpret_cast<float*>(w + L.lvl_s);
+  int64_t* lvl_i = reinterpret_cast<int64_t*>(w + L.lvl_i);
   HPUSM_CUDA_OK(cudaMemsetAsync(match_count, 0, sizeof(int32_t), st));
-  HPUSM_LAUNCH(pose_topk_partial_kernel, b, TK_THREADS, 0, st, match, score, n, index_offset, k, ps[0], pi[0], match_count);
+  HPUSM_CUDA_OK(cudaMemsetAsync(cand_count, 0, sizeof(int32_t), st));
+  HPUSM_LAUNCH(pose_topk_min_kernel, L.nb, TK_THREADS, 0, st, match, score, n, L.tile, min_s, min_i, match_count);
   HPUSM_CHECK_LAUNCH();
-  int64_t count = (int64_t)b * k;
-  int cur = 0;
-  while (count > TK_TILE) {  // reduction levels: every CTA folds TK_TILE candidates into k
-    const int blocks = (int)((count + TK_TILE - 1) / TK_TILE);
-    HPUSM_LAUNCH(pose_topk_reduce_kernel, blocks, TK_THREADS, 0, st, ps[cur], pi[cur], count, k, ps[cur ^ 1], pi[cur ^ 1]);
-    HPUSM_CHECK_LAUNCH();
-    count = (int64_t)blocks * k;
-    cur ^= 1;
-  }
-  HPUSM_LAUNCH(pose_topk_reduce_kernel, 1, TK_THREADS, 0, st, ps[cur], pi[cur], count, k, top_score, top_index);
+  HPUSM_LAUNCH(pose_topk_kth_kernel, (L.nb + TK_KTH_THREADS / 32 - 1) / (TK_KTH_THREADS / 32), TK_KTH_THREADS, 0, st, min_s, min_i, L.nb, k,
+               thr);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(pose_topk_filter_kernel, L.nb, TK_THREADS, 0, st, match, score, n, L.tile, index_offset, thr, L.cap, cand_s, cand_i,
+               cand_count);
+  HPUSM_CHECK_LAUNCH();
+  // a short candidate list (the usual case) is finished by CTA 0 of the select kernel; a long one is folded TK_TILE
+  // candidates per CTA into k-lists, which the final kernel reduces
+  HPUSM_LAUNCH(pose_topk_select_kernel, L.lvl_blocks, TK_THREADS, 0, st, cand_s, cand_i, L.cap, cand_count, k, lvl_s, lvl_i, top_score,
+               top_index);
+  HPUSM_CHECK_LAUNCH();
+  HPUSM_LAUNCH(pose_topk_final_kernel, 1, TK_THREADS, 0, st, lvl_s, lvl_i, (int64_t)L.lvl_blocks * k, L.cap, cand_count, k, top_score,
+               top_index);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;
 }
@@ -1050,7 +1203,7 @@ int hpusm_pose_topk_merge(const float* cand_score, const int64_t* cand_index, in
                 "hpusm_pose_topk_merge: count must be in 0..%d and k in 1..%d", TK_TILE, TK_MAXK);
   HPUSM_REQUIRE(top_score && top_index && (count == 0 || (cand_score && cand_index)), HPUSM_ERR_INVALID,
                 "hpusm_pose_topk_merge: null pointer");
-  HPUSM_LAUNCH(pose_topk_reduce_kernel, 1, TK_THREADS, 0, as_stream(stream), cand_score, cand_index, count, k, top_score,
+  HPUSM_LAUNCH(pose_topk_reduce_kernel, 1, TK_THREADS, 0, as_stream(stream), cand_score, cand_index, count, nullptr, k, top_score,
                top_index);
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;

@@ -760,8 +760,48 @@ def test_pose_topk(hpusm, cuda_device):
     assert int(cnt.item()) == int(match.sum())
 
 
+@pytest.mark.parametrize("case", ["all_equal", "few", "none", "unaligned", "one_tile_hot", "tiny"])
+def test_pose_topk_threshold_selection_edges(hpusm, cuda_device, case):
+    """The two-pass selection (tile minima -> k-th smallest as threshold -> candidate list): every score equal (the list
+    holds whole tiles), fewer matches than k, no match at all, views that are not 16-byte aligned, all of the best entries
+    inside ONE tile, and a database smaller than one tile."""
+    rng = np.random.default_rng(17)
+    n, k, off = 300_000, 16, 0
+    match = (rng.random(n) < 0.4).astype(np.uint8)
+    score = rng.random(n).astype(np.float32)
+    if case == "all_equal":
+        score[:] = 0.25
+    elif case == "few":
+        match[:] = 0
+        match[[5, 99_999, 250_000]] = 1
+    elif case == "none":
+        match[:] = 0
+    elif case == "one_tile_hot":
+        match[8192:8192 + 4096] = 1
+        score[8192:8192 + 4096] = -1.0 - rng.random(4096).astype(np.float32)
+    elif case == "tiny":
+        n = 37
+        match, score = match[:n].copy(), score[:n].copy()
+        match[:] = 1
+    m, s = dev(match, cuda_device), dev(score, cuda_device)
+    if case == "unaligned":
+        m, s, match, score, off = m[3:], s[3:], match[3:], score[3:], 3
+    ts, ti, cnt = hpusm.pose_topk(m, s, k=k, index_offset=off)
+    nn = len(match)
+    ok = match == 1
+    order = np.lexsort((np.arange(nn), np.where(ok, score, np.inf)))[:k]
+    order = order[ok[order]]
+    want_i = np.full(k, -1, np.int64)
+    want_s = np.full(k, np.inf, np.float32)
+    want_i[:len(order)] = order + off
+    want_s[:len(order)] = score[order]
+    np.testing.assert_array_equal(ti.cpu().numpy(), want_i)
+    np.testing.assert_array_equal(ts.cpu().numpy(), want_s)
+    assert int(cnt.item()) == int(match.sum())
+
+
 def test_pose_topk_large_and_merge(hpusm, cuda_device):
-    """More than one reduction level (3 M entries -> 733 partial lists -> 3 -> 1) and the candidate-list merge used
+    """3 M entries with heavy ties (many candidates at the threshold) and the candidate-list merge used
     after the all-gather: both equal the lexicographic (score, index) reference, padding and ties included."""
     rng = np.random.default_rng(9)
     n = 3_000_000
