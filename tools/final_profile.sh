@@ -13,6 +13,10 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:pose_match_fast -s 1 -c 1 -o $O/r2_pose_fast_final $SHORT --workload pose > $O/ncu_pose.log 2>&1; echo "ncu pose rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:ransac_score -s 1 -c 1 -o $O/r2_ransac_score_final $SHORT --workload ransac --pairs 20000 > $O/ncu_rs.log 2>&1; echo "ncu ransac rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:l2_i8_knn2 -s 1 -c 1 -o $O/r2_l2_i8_final $SHORT --no-others > $O/ncu_i8.log 2>&1; echo "ncu i8 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:ham_tc_segmented -s 1 -c 1 -o $O/r2_ham_tc $SHORT --workload orb > $O/ncu_ham.log 2>&1; echo "ncu hamming tc rc=$?"
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:ham_tc -c 10 --csv --log-file $O/r2_orb_tc_launches.csv $SHORT --workload orb > $O/ncu_ham_l.log 2>&1; echo "orb launch list rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pose_ -c 24 --csv --log-file $O/r2_pose_launches.csv $SHORT --workload pose > $O/ncu_pose_l.log 2>&1; echo "pose launch list rc=$?"
+python bench.py --workload orb --steps 10 --warmup 3 > $O/r2_bench_orb_tc.json 2> $O/r2_bench_orb_tc.err; echo "bench orb rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:orb_ -c 6 -o $O/r2_orb_compute python -m pytest tests/test_gpu_parity.py -q -k test_orb_compute_is_cv2 > $O/ncu_orb.log 2>&1; echo "ncu orb rc=$?"
 python tests/dropin_latency.py > $O/r2_dropin_latency.json 2>/dev/null; echo "dropin latency rc=$?"
 python tools/c1_latency.py > $O/r2_c1_latency.json 2>/dev/null; echo "c1 latency rc=$?"
