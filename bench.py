@@ -333,7 +333,55 @@ def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
     return {"ms": r["ms"], "e2e_ms": e["ms"], "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "launches": r["launches"],
             "clocks": r["clocks"], "survivors": survivors, "mode": mode, "parity": parity, "nt_rank": nt_rank,
             "h2d": int(hq.numel() * 4 + ht.numel() * 4), "d2h": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel()),
-            "fallback_rows": eng.knn2_l2_last_fallback_rows()}
+            "fallback_rows": eng.knn2_l2_last_fallback_rows(), "answer": (mi.clone(), md.clone())}
+
+
+def sift_query_sharded_pass(args, rank, world, device, hp, nt_rank, row0, db_sharded_answer):
+    """The strong-scaling problem (the fixed nq x nt pairs) with the QUERIES sharded and the database replicated
+    (retrieval.knn2_query_sharded): every rank matches its 1/N of the queries against the whole database, the answers are
+    all-gathered.  Same data as the row-sharded strong pass (whose shards are gathered into the replica), and the answer
+    must be identical to it -- checked here on the hardware."""
+    eng, rt = hp.engine, hp.retrieval
+    nq = args.nq
+    q, t = make_workload(nq, nt_rank, rank, device)
+    t_full = rt.allgather(t).reshape(-1, 128).contiguous()
+    del t
+    qa, qb = rt.shard_range(nq, rank, world)
+    q_slice = q[qa:qb].contiguous()
+    l2_mode = {"auto": eng.L2_AUTO, "i8": eng.L2_TC_I8, "bf16": eng.L2_TC_INT, "split": eng.L2_TC_SPLIT,
+               "simt": eng.L2_SIMT}[args.l2_engine]
+    ws = eng.knn2_l2_workspace(qb - qa, t_full.shape[0], 128, l2_mode, device)
+    idx = torch.empty((qb - qa, 2), dtype=torch.int32, device=device)
+    dst = torch.empty((qb - qa, 2), dtype=torch.float32, device=device)
+
+    def local_knn(qq, tt):
+        return eng.knn2_l2(qq, tt, mode=l2_mode, out=(idx, dst), workspace=ws)
+
+    def step():
+        return rt.knn2_query_sharded(q_slice, t_full, nq, kind="l2", ratio=0.8, knn_fn=local_knn)
+
+    tm = Timer(args, rank, world, device, hp)
+    r = tm.run(step)
+    mi, md, keep, count = r["out"]
+    same = bool(torch.equal(mi, db_sharded_answer[0]) and torch.equal(md, db_sharded_answer[1]))
+    assert same, "query-sharded and row-sharded answers differ"
+    hq, ht = q_slice.cpu().pin_memory(), t_full.cpu().pin_memory()
+    h_idx = torch.empty((nq, 2), dtype=torch.int32).pin_memory()
+    h_dst = torch.empty((nq, 2), dtype=torch.float32).pin_memory()
+    h_keep = torch.empty((nq,), dtype=torch.uint8).pin_memory()
+    streamed = rt.StreamedL2Matcher(qb - qa, t_full.shape[0], 128, device, mode=l2_mode)
+
+    def e2e_step():
+        gi, gd, kp, _ = rt.knn2_query_sharded(hq, ht, nq, kind="l2", ratio=0.8, knn_fn=streamed)
+        h_idx.copy_(gi, non_blocking=True)
+        h_dst.copy_(gd, non_blocking=True)
+        h_keep.copy_(kp, non_blocking=True)
+
+    e = tm.run(e2e_step, profile=False)
+    assert int(h_keep.sum()) == int(count.item()), "e2e pass disagrees with the resident pass"
+    del streamed
+    return {"ms": r["ms"], "e2e_ms": e["ms"], "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "identical": same,
+            "nt_rank": int(t_full.shape[0]), "h2d": int(hq.numel() * 4 + ht.numel() * 4)}
 
 
 _I8_PEAK = {}
@@ -377,6 +425,10 @@ def run_sift(args, rank, world, device, hp):
         a, b = hp.retrieval.shard_range(args.nt, rank, world, align=128)
         log("sift: strong-scaling pass")
         strong = sift_pass(args, rank, world, device, hp, b - a, a, "strong")
+        log("sift: strong-scaling pass, queries sharded / database replicated")
+        strong_q = sift_query_sharded_pass(args, rank, world, device, hp, b - a, a, strong["answer"])
+    weak.pop("answer", None)
+    strong.pop("answer", None)
     if rank != 0:
         return None
     nq, nt = args.nq, args.nt
@@ -422,6 +474,14 @@ def run_sift(args, rank, world, device, hp):
                      "nt_per_gpu": res["nt_rank"], "kernel_ms": res["kernel_ms"] / max(res["kernel_n"], 1),
                      "note": "efficiency at N GPUs = value(N) / (N x value(1)) for weak, value(N) / (N x value(1)) for strong "
                              "(strong: the same nq x nt pairs in 1/N of the time)"}
+    if world > 1:
+        out["strong_scaling_query_sharded"] = {
+            "value": pairs_strong * args.steps / (strong_q["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": strong_q["ms"] / args.steps,
+            "e2e": pairs_strong * args.steps / (strong_q["e2e_ms"] * 1e-3), "nq_per_gpu": -(-nq // world), "nt_per_gpu": strong_q["nt_rank"],
+            "kernel_ms": strong_q["kernel_ms"] / max(strong_q["kernel_n"], 1), "h2d_bytes_per_step": strong_q["h2d"],
+            "identical_to_row_sharded": strong_q["identical"],
+            "note": "same nq x nt pairs, retrieval.knn2_query_sharded: 1/N of the queries per rank against the replicated database, "
+                    "one all-gather of the answers; the form for databases that fit every GPU"}
     if weak["parity"] is not None:
         out["nccl_parity"] = weak["parity"]
     return out

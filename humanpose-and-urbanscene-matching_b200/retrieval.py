@@ -1,6 +1,7 @@
 """Query-versus-database drivers, sharded over the ranks of one node (torch.distributed; NCCL on GPUs).
 
-The database shards by rows (descriptors, C2), by images (C3) or by poses (C5); queries are replicated; every rank
+The database shards by rows (descriptors, C2; knn2_query_sharded is the form with the queries sharded and the database
+replicated), by images (C3) or by poses (C5); queries are replicated; every rank
 runs the single-GPU kernels on its shard and the only exchange is one small all-gather of per-rank partial answers
 (SURVEY.md 8e):
     kNN-2        [nq,2] (idx, dist) per rank  -> lexicographic (dist, global idx) merge kernel + ratio kernel
@@ -66,6 +67,29 @@ def knn2_sharded(q, t_shard, row_offset, kind="l2", ratio=0.8, knn_fn=None, merg
             raise TypeError("knn2_sharded: distances must be 32-bit, got %s" % d.dtype)
         g = allgather(torch.cat([idx.to(torch.int32), d.contiguous().view(torch.int32)], dim=1))  # [n, nq, 4]
         idx, d = merge_fn(g[:, :, :2].contiguous(), g[:, :, 2:].contiguous().view(d.dtype))
+    keep, count = ratio_fn(idx, d, ratio)
+    return idx, d, keep, count
+
+
+def knn2_query_sharded(q_slice, t_full, nq_total, kind="l2", ratio=0.8, knn_fn=None, ratio_fn=None):
+    """Global kNN-2 + Lowe ratio with the QUERIES sharded and the database replicated (the zero-exchange
+    alternative): rank r matches its rows shard_range(nq_total, r, world) against the whole database; the only
+    collective is the all-gather of the answers (16 B per query).  The form to use when the database fits every GPU and
+    the queries are many: a rank's work is exactly 1/N of the single-GPU work, whereas row-sharding the database keeps the
+    per-query costs (operand preparation, re-rank, the start-up of every running top-2 list) on every rank.
+    Every rank returns the same (idx [nq_total,2], dist [nq_total,2], keep, count)."""
+    if knn_fn is None:
+        knn_fn = engine.knn2_l2 if kind == "l2" else engine.knn2_hamming
+    ratio_fn = ratio_fn or engine.ratio_filter
+    idx, d = knn_fn(q_slice, t_full)
+    rank, n = world()
+    if n > 1:
+        per = -(-int(nq_total) // n)
+        packed = torch.full((per, 4), -1, dtype=torch.int32, device=idx.device)
+        packed[:idx.shape[0], :2] = idx
+        packed[:idx.shape[0], 2:] = d.contiguous().view(torch.int32)
+        g = allgather(packed).reshape(n * per, 4)[:int(nq_total)]
+        idx, d = g[:, :2].contiguous(), g[:, 2:].contiguous().view(d.dtype)
     keep, count = ratio_fn(idx, d, ratio)
     return idx, d, keep, count
 

@@ -64,6 +64,11 @@ def _worker(rank, nranks, port, out_dir):
     lo, hi = rt.shard_range(len(t), rank, nranks, align=128)
     idx, d, keep, count = rt.knn2_sharded(torch.from_numpy(q), torch.from_numpy(t[lo:hi]), lo, kind="hamming", knn_fn=knn_fn,
                                           merge_fn=merge_fn, ratio_fn=ratio_fn)
+    # -- the same problem with the QUERIES sharded (uneven slices) and the database replicated
+    nq2 = len(q) - 1   # odd: the last rank's slice is one row short and is padded for the gather
+    qlo, qhi = rt.shard_range(nq2, rank, nranks)
+    qi, qd, qkeep, qcount = rt.knn2_query_sharded(torch.from_numpy(q[qlo:qhi]), torch.from_numpy(t), nq2, kind="hamming",
+                                                  knn_fn=knn_fn, ratio_fn=ratio_fn)
     # -- image-sharded retrieval (C3 plumbing) with ragged shards
     query, db, offs, planted = hp.synth.orb_database(7, per_image=64, seed=6, ragged=True)
     a, b = rt.shard_segments(offs, rank, nranks)
@@ -71,7 +76,8 @@ def _worker(rank, nranks, port, out_dir):
     scores = rt.image_scores_sharded(torch.from_numpy(query), torch.from_numpy(db[offs[a]:offs[b]]), local_offs, 0.8,
                                      score_fn=score_fn)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), idx=idx.numpy(), d=d.numpy(), keep=keep.numpy(),
-             count=count.numpy(), scores=scores.numpy())
+             count=count.numpy(), scores=scores.numpy(), qidx=qi.numpy(), qd=qd.numpy(), qkeep=qkeep.numpy(),
+             qcount=qcount.numpy())
     dist.destroy_process_group()
 
 
@@ -116,3 +122,7 @@ def test_world2_gloo_sharded_equals_unsharded(tmp_path):
         np.testing.assert_array_equal(g["d"], rd)
         np.testing.assert_array_equal(g["keep"].astype(bool), knn_oracle.ratio_keep(ri, rd, 0.8))
         np.testing.assert_array_equal(g["scores"], rs)
+        np.testing.assert_array_equal(g["qidx"], ri[:-1])
+        np.testing.assert_array_equal(g["qd"], rd[:-1])
+        np.testing.assert_array_equal(g["qkeep"], g["keep"][:-1])
+        assert int(g["qcount"][0]) == int(g["keep"][:-1].sum())
