@@ -45,24 +45,34 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-// Four distinct indices in [0, K), K >= 4, as a function of (seed, pair, hyp, attempt) only.
-__host__ __device__ __forceinline__ void sample4(uint64_t seed, uint64_t pair, uint64_t hyp, uint32_t attempt, uint32_t K,
-                                                 uint32_t out[4]) {
-  uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (pair + 1)) ^ (0x8CB92BA72F3D8DD7ull * (hyp + 1)) ^
-               (0xA0761D6478BD642Full * (uint64_t)attempt);
-  (void)splitmix64(s);
+// Four distinct indices in [0, K), K >= 4, as a function of (seed, pair, hyp, attempt) only: two splitmix64 outputs of the
+// key give four 32-bit uniforms; each becomes a rank among the indices not yet used.  sample_key() is the part of the key
+// that does not depend on the attempt (hoisted out of the redraw loop).
+__host__ __device__ __forceinline__ uint64_t sample_key(uint64_t seed, uint64_t pair, uint64_t hyp) {
+  return seed ^ (0xD1B54A32D192ED03ull * (pair + 1)) ^ (0x8CB92BA72F3D8DD7ull * (hyp + 1));
+}
+__host__ __device__ __forceinline__ void sample4_keyed(uint64_t key, uint32_t attempt, uint32_t K, uint32_t out[4]) {
+  uint64_t s = key ^ (0xA0761D6478BD642Full * (uint64_t)attempt);
+  const uint64_t r0 = splitmix64(s), r1 = splitmix64(s);
+  const uint32_t u[4] = {(uint32_t)(r0 >> 32), (uint32_t)r0, (uint32_t)(r1 >> 32), (uint32_t)r1};
   uint32_t sorted[4];
+#pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint64_t r = splitmix64(s);
-    uint32_t v = (uint32_t)(((r >> 32) * (uint64_t)(K - j)) >> 32);  // rank among the unused indices
+    uint32_t v = (uint32_t)(((uint64_t)u[j] * (uint64_t)(K - j)) >> 32);  // rank among the unused indices
     int pos = 0;
+#pragma unroll
     for (int c = 0; c < j; ++c) {
       if (v >= sorted[c]) { ++v; pos = c + 1; }
     }
+#pragma unroll
     for (int c = j; c > pos; --c) sorted[c] = sorted[c - 1];
     sorted[pos] = v;
     out[j] = v;
   }
+}
+__host__ __device__ __forceinline__ void sample4(uint64_t seed, uint64_t pair, uint64_t hyp, uint32_t attempt, uint32_t K,
+                                                 uint32_t out[4]) {
+  sample4_keyed(sample_key(seed, pair, hyp), attempt, K, out);
 }
 
 // OpenCV's RNG::next(): multiply-with-carry.
@@ -214,21 +224,6 @@ __device__ __forceinline__ void sample_points_smem(const float4* pts, const uint
     sx[j] = (double)f[base]; sy[j] = (double)f[base + 2];
     dx[j] = (double)(-f[base + 4]); dy[j] = (double)(-f[base + 6]);
   }
-}
-
-// Counter sampler: redraw (attempt = 0, 1, ...) until the subset check passes.  false after COUNTER_MAX_ATTEMPTS.
-template <bool SMEM>
-__device__ __forceinline__ bool counter_sample(const float4* pts, const float* __restrict__ src, const float* __restrict__ dst,
-                                               uint32_t K, uint64_t seed, uint64_t pair, uint64_t hyp, double* sx, double* sy,
-                                               double* dx, double* dy) {
-  for (uint32_t a = 0; a < COUNTER_MAX_ATTEMPTS; ++a) {
-    uint32_t id[4];
-    sample4(seed, pair, hyp, a, K, id);
-    if (SMEM) sample_points_smem(pts, id, sx, sy, dx, dy);
-    else sample_points(src, dst, id, sx, sy, dx, dy);
-    if (cv_check_subset(sx, sy, dx, dy)) return true;
-  }
-  return false;
 }
 
 // ---- inlier tests -----------------------------------------------------------------------------------------------------
@@ -515,7 +510,8 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
   __syncthreads();
 
   // The points of hypothesis h (after redraws / from the cv2 table); false when the iteration has no sample.
-  auto hypothesis_points = [&](int h, double* sx, double* sy, double* dx, double* dy) -> bool {
+  // `a`: counter sampler only -- the attempt whose draw is wanted (phase A1 leaves the first passing one in counts[h])
+  auto hypothesis_points = [&](int h, int a, double* sx, double* sy, double* dx, double* dy) -> bool {
     if (K < 4) return false;
     if (CV) {
       const int4 q = __ldg(smp + h);
@@ -525,11 +521,68 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       else sample_points(s, d, id, sx, sy, dx, dy);
       return true;
     }
-    return resident ? counter_sample<true>(pts, s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy)
-                    : counter_sample<false>(pts, s, d, K, seed, (uint64_t)(pair + pair0), (uint64_t)h, sx, sy, dx, dy);
+    if (a < 0) return false;
+    uint32_t id[4];
+    sample4(seed, (uint64_t)(pair + pair0), (uint64_t)h, (uint32_t)a, K, id);
+    if (resident) sample_points_smem(pts, id, sx, sy, dx, dy);
+    else sample_points(s, d, id, sx, sy, dx, dy);
+    return true;
   };
 
-  // phase A
+  // phase A1 (counter sampler): find, for every hypothesis, the FIRST attempt whose sample passes OpenCV's subset check.
+  // A lane per hypothesis looping until its own draw passes leaves the warp running for the unluckiest of its 32 lanes
+  // (one draw in five passes on C4's data: 17 iterations per warp where the average lane needs 5; the sampling was 39 %
+  // of the kernel).  Here a warp works on 8 hypotheses at a time, 4 consecutive attempts of each in parallel (lane =
+  // (slot, attempt)); the lowest passing attempt wins, which is what the sequential loop returns; a resolved slot pulls
+  // the warp's next hypothesis, so all lanes stay busy until the hypotheses run out.
+  if (!CV) {
+    const int slot = lane >> 2, sub = lane & 3;
+    // every warp owns a contiguous run of hypotheses and hands them to its slots from a register counter (a block-wide
+    // shared-memory counter put an atomic's latency into every round of the dependent chain)
+    const int per_warp = (nhyp + RS_WARPS - 1) / RS_WARPS;
+    int next = warp * per_warp;
+    const int h_end = min(nhyp, next + per_warp);
+    int h = -1, r = 0;
+    uint64_t key = 0;
+    for (;;) {
+      const unsigned needm = __ballot_sync(0xffffffffu, h < 0 && sub == 0);
+      if (needm) {
+        if (h < 0) {
+          h = next + __popc(needm & ((1u << (slot * 4)) - 1u));
+          r = 0;
+          key = sample_key(seed, (uint64_t)(pair + pair0), (uint64_t)h);
+        }
+        next += __popc(needm);
+      }
+      const bool active = h < h_end;
+      if (!__any_sync(0xffffffffu, active)) break;
+      bool pass = false;
+      const int a = r * 4 + sub;
+      if (active && K >= 4 && a < COUNTER_MAX_ATTEMPTS) {
+        uint32_t id[4];
+        double sx[4], sy[4], dx[4], dy[4];
+        sample4_keyed(key, (uint32_t)a, K, id);
+        if (resident) sample_points_smem(pts, id, sx, sy, dx, dy);
+        else sample_points(s, d, id, sx, sy, dx, dy);
+        pass = cv_check_subset(sx, sy, dx, dy);
+      }
+      const unsigned mine = (__ballot_sync(0xffffffffu, pass) >> (slot * 4)) & 0xFu;
+      if (active) {
+        if (mine) {
+          if (sub == 0) counts[h] = r * 4 + __ffs(mine) - 1;
+          h = -1;
+        } else if (K < 4 || (r + 1) * 4 >= COUNTER_MAX_ATTEMPTS) {
+          if (sub == 0) counts[h] = -1;
+          h = -1;
+        } else {
+          ++r;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // phase A2: one LANE per hypothesis: the sample's points + the FP64 closed-form solve, compaction of the models that exist
   const int rounds = (nhyp + RS_THREADS - 1) / RS_THREADS;
   for (int r = 0; r < rounds; ++r) {
     const int h = r * RS_THREADS + tid;
@@ -537,7 +590,7 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
     double H[9];
     if (h < nhyp) {
       double sx[4], sy[4], dx[4], dy[4];
-      ok = hypothesis_points(h, sx, sy, dx, dy) && hypothesis_solve(sx, sy, dx, dy, H);
+      ok = hypothesis_points(h, CV ? 0 : counts[h], sx, sy, dx, dy) && hypothesis_solve(sx, sy, dx, dy, H);
     }
     const unsigned b = __ballot_sync(0xffffffffu, ok);
     int base = 0;
@@ -629,7 +682,9 @@ ransac_score_kernel(const float* __restrict__ src, const float* __restrict__ dst
       best_hyp[pair] = best;
       if (best >= 0) {
         double sx[4], sy[4], dx[4], dy[4], H[9];
-        (void)hypothesis_points(best, sx, sy, dx, dy);
+        // counts[] now holds inlier counts: the winner's draw is found again by walking its attempts (it has one: it scored)
+        for (int a = 0; a < (CV ? 1 : COUNTER_MAX_ATTEMPTS); ++a)
+          if (hypothesis_points(best, a, sx, sy, dx, dy) && (CV || cv_check_subset(sx, sy, dx, dy))) break;
         (void)hypothesis_solve(sx, sy, dx, dy, H);
 #pragma unroll
         for (int i = 0; i < 9; ++i) best_H[pair * 9 + i] = H[i];

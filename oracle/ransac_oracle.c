@@ -55,12 +55,13 @@ static uint64_t mix64(uint64_t* s) {
 void ransac_oracle_sample4(uint64_t seed, uint64_t pair, uint64_t hyp, uint32_t attempt, uint32_t K, uint32_t out[4]) {
   uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (pair + 1)) ^ (0x8CB92BA72F3D8DD7ull * (hyp + 1)) ^
                (0xA0761D6478BD642Full * (uint64_t)attempt);
-  (void)mix64(&s);
+  /* two 64-bit outputs = four 32-bit uniforms */
+  const uint64_t r0 = mix64(&s), r1 = mix64(&s);
+  const uint32_t u[4] = {(uint32_t)(r0 >> 32), (uint32_t)r0, (uint32_t)(r1 >> 32), (uint32_t)r1};
   uint32_t taken[4]; /* ascending list of the indices already drawn */
   for (int j = 0; j < 4; ++j) {
-    const uint64_t r = mix64(&s);
     /* rank of the new index among the K-j still unused ones, then skip over the used ones */
-    uint32_t v = (uint32_t)(((r >> 32) * (uint64_t)(K - (uint32_t)j)) >> 32);
+    uint32_t v = (uint32_t)(((uint64_t)u[j] * (uint64_t)(K - (uint32_t)j)) >> 32);
     int pos = 0;
     for (int c = 0; c < j; ++c)
       if (v >= taken[c]) { ++v; pos = c + 1; }
