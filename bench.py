@@ -53,7 +53,7 @@ def parse_args():
                     help="sift = BASELINE.json's headline config (default); the others are the remaining configs")
     ap.add_argument("--descriptors", default="int", choices=["int", "float"],
                     help="sift: integer-valued SIFT-like rows (the named config) or the general-float variant (x 1.0137)")
-    ap.add_argument("--l2-engine", default="auto", choices=["auto", "i8", "bf16", "split", "simt"],
+    ap.add_argument("--l2-engine", default="auto", choices=["auto", "i8", "bf16", "split", "q16", "simt"],
                     help="sift: force one L2 engine (default: HPUSM_L2_AUTO picks from the data)")
     ap.add_argument("--hamming-engine", default="auto", choices=["auto", "popc", "tc"],
                     help="orb: engine of the segmented Hamming matcher (auto = tcgen05 kind::i8 where its shape limits hold)")
@@ -265,6 +265,7 @@ DTYPE_OF = {
     "tcgen05-i8-exact-int": "u8 operands (exact for SIFT's integers 0..255) / s32 accumulate + f32 re-rank",
     "tcgen05-bf16-exact-int": "bf16 operands (exact for integer-valued SIFT) / f32 accumulate + f32 re-rank",
     "tcgen05-bf16-split": "bf16 hi/lo split operands / f32 accumulate + verified f32 re-rank",
+    "tcgen05-i8-q16-split": "15-bit fixed point in two s8 operands / s32 accumulate + verified f32 re-rank",
     "simt-fp32": "f32",
 }
 
@@ -280,7 +281,7 @@ def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
     if args.descriptors == "float":  # same rows, no longer integer valued: exercises the split-operand engine
         q, t = (q * 1.0137).contiguous(), (t * 1.0137).contiguous()
     l2_mode = {"auto": eng.L2_AUTO, "i8": eng.L2_TC_I8, "bf16": eng.L2_TC_INT, "split": eng.L2_TC_SPLIT,
-               "simt": eng.L2_SIMT}[args.l2_engine]
+               "q16": eng.L2_TC_Q16, "simt": eng.L2_SIMT}[args.l2_engine]
     ws = eng.knn2_l2_workspace(nq, nt_rank, 128, l2_mode, device)
     idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
     dst = torch.empty((nq, 2), dtype=torch.float32, device=device)
@@ -296,7 +297,7 @@ def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
     mi, md, keep, count = r["out"]
     survivors = int(count.item())
     mode = {0: "auto", 1: "simt-fp32", 2: "tcgen05-bf16-exact-int", 3: "tcgen05-bf16-split",
-            4: "tcgen05-i8-exact-int"}.get(eng.knn2_l2_last_mode(), "?")
+            4: "tcgen05-i8-exact-int", 5: "tcgen05-i8-q16-split"}.get(eng.knn2_l2_last_mode(), "?")
 
     # on-hardware parity of the NCCL path: the merged answer of a query slice == ONE single-GPU pass over the gathered database
     parity = None
@@ -349,7 +350,7 @@ def sift_query_sharded_pass(args, rank, world, device, hp, nt_rank, row0, db_sha
     qa, qb = rt.shard_range(nq, rank, world)
     q_slice = q[qa:qb].contiguous()
     l2_mode = {"auto": eng.L2_AUTO, "i8": eng.L2_TC_I8, "bf16": eng.L2_TC_INT, "split": eng.L2_TC_SPLIT,
-               "simt": eng.L2_SIMT}[args.l2_engine]
+               "q16": eng.L2_TC_Q16, "simt": eng.L2_SIMT}[args.l2_engine]
     ws = eng.knn2_l2_workspace(qb - qa, t_full.shape[0], 128, l2_mode, device)
     idx = torch.empty((qb - qa, 2), dtype=torch.int32, device=device)
     dst = torch.empty((qb - qa, 2), dtype=torch.float32, device=device)

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libhpusm.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = -1, -2, -3, -4
-L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT, L2_TC_I8 = 0, 1, 2, 3, 4
+L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT, L2_TC_I8, L2_TC_Q16 = 0, 1, 2, 3, 4, 5
 POSE_DETAIL = 8 + 27 + 44
 
 

@@ -37,7 +37,7 @@ int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d,
   HPUSM_REQUIRE(nq >= 0 && nt >= 0, HPUSM_ERR_INVALID, "hpusm_knn2_l2: negative size");
   HPUSM_REQUIRE(d > 0 && d % 4 == 0 && d <= 512, HPUSM_ERR_UNSUPPORTED,
                 "hpusm_knn2_l2: descriptor length %d (need a multiple of 4, at most 512)", d);
-  HPUSM_REQUIRE(mode >= HPUSM_L2_AUTO && mode <= HPUSM_L2_TC_I8, HPUSM_ERR_INVALID, "hpusm_knn2_l2: bad mode %d", mode);
+  HPUSM_REQUIRE(mode >= HPUSM_L2_AUTO && mode <= HPUSM_L2_TC_Q16, HPUSM_ERR_INVALID, "hpusm_knn2_l2: bad mode %d", mode);
   if (nq == 0) return HPUSM_OK;
   HPUSM_REQUIRE(q && idx && dist && (t || nt == 0), HPUSM_ERR_INVALID, "hpusm_knn2_l2: null pointer");
   HPUSM_REQUIRE(is_aligned(q, 16) && is_aligned(t, 16), HPUSM_ERR_INVALID,
@@ -52,7 +52,7 @@ int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d,
 
   int engine = mode;
   if (mode == HPUSM_L2_AUTO) engine = (l2_tc_available() && tc_shape_ok(d) && nt >= 2) ? HPUSM_L2_AUTO : HPUSM_L2_SIMT;
-  if (mode == HPUSM_L2_TC_INT || mode == HPUSM_L2_TC_SPLIT || mode == HPUSM_L2_TC_I8)
+  if (mode == HPUSM_L2_TC_INT || mode == HPUSM_L2_TC_SPLIT || mode == HPUSM_L2_TC_I8 || mode == HPUSM_L2_TC_Q16)
     HPUSM_REQUIRE(tc_shape_ok(d), HPUSM_ERR_UNSUPPORTED,
                   "hpusm_knn2_l2: the tensor-core engine is built for d == 128, got %d", d);
 

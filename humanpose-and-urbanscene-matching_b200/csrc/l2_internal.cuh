@@ -29,4 +29,10 @@ size_t l2_tc_i8_workspace_bytes(int64_t nq, int64_t nt);
 int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_t* idx, float* dist, void* ws,
                   size_t ws_bytes, cudaStream_t st, bool require, int* eligible);
 
+// l2_tc_q16.cu (tcgen05 kind::i8 engine for general float descriptors: 15-bit fixed point in two signed bytes, two
+// accumulators per tile, top-M candidates, verified re-rank)
+size_t l2_tc_q16_workspace_bytes(int64_t nq, int64_t nt);
+int l2_tc_q16_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_t* idx, float* dist, void* ws,
+                   size_t ws_bytes, cudaStream_t st, int64_t* fallback_rows);
+
 }  // namespace hpusm

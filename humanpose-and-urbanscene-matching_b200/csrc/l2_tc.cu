@@ -410,8 +410,9 @@ size_t l2_tc_workspace_bytes(int64_t nq, int64_t nt, int d, int mode) {
   const size_t a = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_INT) ? tc_layout(nq, nt, mode).total : 0;
   const size_t b = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_SPLIT) ? l2_tc_split_workspace_bytes(nq, nt) : 0;
   const size_t c = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_I8) ? l2_tc_i8_workspace_bytes(nq, nt) : 0;
-  const size_t ab = a > b ? a : b;
-  return ab > c ? ab : c;
+  const size_t e = (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_Q16) ? l2_tc_q16_workspace_bytes(nq, nt) : 0;
+  const size_t ab = a > b ? a : b, ce = c > e ? c : e;
+  return ab > ce ? ab : ce;
 }
 
 int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, int mode, int32_t* idx, float* dist, void* ws,
@@ -420,6 +421,10 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
   if (mode == HPUSM_L2_TC_SPLIT) {
     *resolved_mode = HPUSM_L2_TC_SPLIT;
     return l2_tc_split_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
+  }
+  if (mode == HPUSM_L2_TC_Q16) {
+    *resolved_mode = HPUSM_L2_TC_Q16;
+    return l2_tc_q16_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
   }
   if (mode == HPUSM_L2_AUTO || mode == HPUSM_L2_TC_I8) {
     // u8 operands on the integer tensor pipe when every value is an integer in [0,255] (what cv2 SIFT produces)

@@ -13,8 +13,8 @@ import torch
 from . import _lib
 from ._lib import lib, check
 
-L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT, L2_TC_I8 = (_lib.L2_AUTO, _lib.L2_SIMT, _lib.L2_TC_INT, _lib.L2_TC_SPLIT,
-                                                       _lib.L2_TC_I8)
+L2_AUTO, L2_SIMT, L2_TC_INT, L2_TC_SPLIT, L2_TC_I8, L2_TC_Q16 = (_lib.L2_AUTO, _lib.L2_SIMT, _lib.L2_TC_INT,
+                                                                  _lib.L2_TC_SPLIT, _lib.L2_TC_I8, _lib.L2_TC_Q16)
 POSE_DETAIL = _lib.POSE_DETAIL
 
 # thresholds.py:7-13 of the reference, in the order hpusm_pose_match_batch expects

@@ -47,6 +47,10 @@ extern "C" {
 #define HPUSM_L2_TC_I8 4  /* tcgen05 kind::i8, u8 operands, s32 accumulation: integer values in [0,255] and squared
                              norms below 4,000,000.  Fully asynchronous: the range check runs on the device and gates
                              the sweep there; a violation leaves every idx at -1 and is reported by hpusm_async_status() */
+#define HPUSM_L2_TC_Q16 5 /* tcgen05 kind::i8 for GENERAL floats: 15-bit fixed point split into two signed bytes, two s32
+                             accumulators per tile (13 integer MMAs where the bf16 split needs 25 at half the rate),
+                             top-6 per list + verified FP32 re-rank with error bounds measured on the data; synchronises
+                             the stream once (count of rows sent to the exact fallback)                             */
 
 /* Engines of the segmented Hamming matcher (hpusm_knn2_hamming_segmented). */
 #define HPUSM_HAMMING_AUTO 0 /* tensor-core engine where its shape limits hold, else the __popc engine */
@@ -109,7 +113,7 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
  * Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) (features.py:42,:59).
  *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512.
  *   The tensor-core engines are built for d == 128 (SIFT); HPUSM_L2_AUTO takes the exact FP32 engine for other
- *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 return HPUSM_ERR_UNSUPPORTED there.
+ *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 / HPUSM_L2_TC_Q16 return HPUSM_ERR_UNSUPPORTED there.
  *   HPUSM_L2_TC_INT / HPUSM_L2_TC_I8 never synchronise: their value-range check runs on the device (see hpusm_async_status);
  *   HPUSM_L2_AUTO checks the value range on the device: integers in [0,255] (what OpenCV SIFT emits) run on the u8
  *   integer tensor pipe, integers in [0,256] on the bf16 engine, anything else (mixed signs included) on the split engine, whose

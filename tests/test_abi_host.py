@@ -176,7 +176,7 @@ def test_public_python_surface_is_complete():
     for name in ["knn2_l2", "knn2_hamming", "knn2_hamming_segmented", "knn2_merge", "ratio_filter", "gather_matches",
                  "segment_matches", "ransac_homography_batch", "ransac_score_batch", "perspective_transform", "affine_lsq_batch",
                  "procrustes_batch", "pose_match_batch", "pose_match_pairs", "scene_score_batch", "pose_topk", "pose_topk_merge",
-                 "L2_AUTO", "L2_SIMT", "L2_TC_INT", "L2_TC_SPLIT", "L2_TC_I8"]:
+                 "L2_AUTO", "L2_SIMT", "L2_TC_INT", "L2_TC_SPLIT", "L2_TC_I8", "L2_TC_Q16"]:
         assert hasattr(pkg.engine, name), "engine.%s is missing" % name
     for name in pkg.__all__:
         assert hasattr(pkg, name), "__all__ names %s, which does not exist" % name

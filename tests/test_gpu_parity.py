@@ -962,6 +962,74 @@ def test_l2_split_engine_near_ties_take_the_exact_fallback(hpusm, cuda_device):
     assert torch.equal(idx, sidx) and torch.equal(dist, sdist)  # both end in the same exact FP32 re-rank
 
 
+# ---- K1q fixed-point integer tensor engine (general float descriptors) ---------------------------------------------
+def _q16_equals_exact(hpusm, cuda_device, q, t):
+    """Both engines end in the same exact FP32 re-rank, and the proof is strict: the answers must be IDENTICAL."""
+    dq, dt = dev(q, cuda_device), dev(t, cuda_device)
+    idx, dist = hpusm.knn2_l2(dq, dt, mode=hpusm.engine.L2_TC_Q16)
+    assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_Q16
+    fb = hpusm.engine.knn2_l2_last_fallback_rows()
+    sidx, sdist = hpusm.knn2_l2(dq, dt, mode=hpusm.engine.L2_SIMT)
+    assert torch.equal(idx, sidx) and torch.equal(dist, sdist)
+    return idx, dist, fb
+
+
+def test_l2_q16_engine_general_floats(hpusm, cuda_device):
+    """HPUSM_L2_TC_Q16 on non-integer descriptors: identical to the exact FP32 engine and equal to the float64 brute
+    force (ties within the stated 1e-5 relative tolerance aside); units, database splits, ragged tails on both sides,
+    fewer rows than one tile."""
+    rng = np.random.default_rng(177)
+    for nq, nt in [(300, 900), (1, 5), (129, 3), (257, 64), (256, 65), (4000, 70001), (20000, 1085)]:
+        q = rng.standard_normal((nq, 128)).astype(np.float32)
+        t = rng.standard_normal((nt, 128)).astype(np.float32)
+        k = min(nq, nt) // 3
+        if k:
+            t[:k] = q[:k] + 0.05 * rng.standard_normal((k, 128)).astype(np.float32)  # planted near neighbours
+        idx, dist, fb = _q16_equals_exact(hpusm, cuda_device, q, t)
+        assert fb <= max(2, nq // 50), (nq, nt, fb)   # the proof covers (nearly) every row: the tensor path did the work
+        ri, rd = knn_oracle.knn2_l2(q, t)
+        assert_l2_parity(idx, dist, ri, rd, q, t)
+
+
+def test_l2_q16_engine_sift_like_and_value_ranges(hpusm, cuda_device):
+    """Real-valued SIFT-like rows (norm ~ 512: the quantisation bound is at its loosest relative to the neighbour gaps),
+    tiny and huge magnitudes (the scale is measured on the data), one dominant component, flat rows, all-zero input."""
+    rng = np.random.default_rng(178)
+    q, t = hpusm.synth.sift_like(3000, 20000, seed=5, planted=0.3)
+    q = (q * np.float32(1.0137)).astype(np.float32)
+    t = (t * np.float32(1.0137)).astype(np.float32)
+    idx, dist, fb = _q16_equals_exact(hpusm, cuda_device, q, t)
+    assert fb < 300
+    ri, rd = knn_oracle.knn2_l2(q, t)
+    assert_l2_parity(idx, dist, ri, rd, q, t)
+    for scale in (1e-12, 1e12):
+        _q16_equals_exact(hpusm, cuda_device, (rng.standard_normal((500, 128)) * scale).astype(np.float32),
+                          (rng.standard_normal((3000, 128)) * scale).astype(np.float32))
+    t = rng.standard_normal((5000, 128)).astype(np.float32)
+    t[:, 0] += 1000.0
+    _q16_equals_exact(hpusm, cuda_device, rng.standard_normal((300, 128)).astype(np.float32), t)
+    _q16_equals_exact(hpusm, cuda_device, np.zeros((130, 128), np.float32), np.zeros((700, 128), np.float32))
+    flat = np.full((700, 128), 3.25, np.float32) + rng.integers(0, 2, (700, 128)).astype(np.float32)
+    _q16_equals_exact(hpusm, cuda_device, np.full((130, 128), 3.25, np.float32), flat)
+
+
+def test_l2_q16_near_ties_and_bad_values_take_the_exact_fallback(hpusm, cuda_device):
+    """Rows whose lists cannot be proven complete (20 database rows within 1e-4 of a query) are redone by the exact engine;
+    a non-finite value sends EVERY row there -- the answer is the exact engine's either way."""
+    rng = np.random.default_rng(179)
+    nq, nt = 257, 6000
+    q = rng.standard_normal((nq, 128)).astype(np.float32)
+    t = rng.standard_normal((nt, 128)).astype(np.float32)
+    for r in range(40):
+        t[100 * r:100 * r + 20] = q[r] + 1e-4 * rng.standard_normal((20, 128)).astype(np.float32)
+    _, _, fb = _q16_equals_exact(hpusm, cuda_device, q, t)
+    assert fb >= 30
+    t[17, 5] = np.inf
+    dq, dt = dev(q, cuda_device), dev(t, cuda_device)
+    hpusm.knn2_l2(dq, dt, mode=hpusm.engine.L2_TC_Q16)
+    assert hpusm.engine.knn2_l2_last_fallback_rows() == nq
+
+
 def test_scene_score_batch_reference(hpusm, cuda_device):
     """Batched scene score vs the reference's perspective_correction + affine_multi (recorded, picks pinned), and the
     seeded picks vs the oracle."""
