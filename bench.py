@@ -445,7 +445,7 @@ def run_sift(args, rank, world, device, hp):
     mode = head["mode"]
     peak_tf, peak_clocks = bf16_tf, None
     peak_source = "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"
-    if mode == "tcgen05-i8-exact-int":
+    if mode in ("tcgen05-i8-exact-int", "tcgen05-i8-q16-split"):
         # MEASURED_PEAKS.json has no INT8 line: the denominator is this GPU's own sustained kind::i8 issue rate, measured now
         log("sift: sustained kind::i8 issue rate (roofline denominator)")
         peak_tf, peak_clocks = i8_sustained_peak(hp, device)
@@ -469,6 +469,10 @@ def run_sift(args, rank, world, device, hp):
                      "peak_clocks": peak_clocks, "ncu": measured_traffic("sift:%s:%dx%d" % (mode, nq, nt), "ncu")},
         "clocks": head["clocks"],
     }
+    if mode == "tcgen05-i8-q16-split" and out["roofline"]["frac"]:
+        # general floats cost 13 kind::i8 MMAs of K = 32 per tile where the integer engine needs 5: 832 issued op per pair
+        # for 256 algorithmic ones.  `frac` stays algorithmic; this is the share of the measured issue rate the kernel uses.
+        out["roofline"]["frac_issued"] = out["roofline"]["frac"] * 832.0 / FLOP_PER_PAIR
     for name, res, pairs in (("weak_scaling", weak, pairs_weak), ("strong_scaling", strong, pairs_strong)):
         out[name] = {"value": pairs * args.steps / (res["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": res["ms"] / args.steps,
                      "e2e": pairs * args.steps / (res["e2e_ms"] * 1e-3), "nq": nq, "nt_global": int(pairs / nq),

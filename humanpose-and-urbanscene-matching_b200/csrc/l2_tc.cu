@@ -459,8 +459,14 @@ int l2_tc_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int d, in
     HPUSM_CUDA_OK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     HPUSM_CUDA_OK(cudaStreamSynchronize(st));
     if (h_flag != 0) {
-      *resolved_mode = HPUSM_L2_TC_SPLIT;
-      return l2_tc_split_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
+      // general floats: the fixed-point integer engine (l2_tc_q16.cu); HPUSM_L2_FLOAT=split keeps the bf16 split engine
+      static const bool use_split = []() { const char* e = getenv("HPUSM_L2_FLOAT"); return e && e[0] == 's'; }();
+      if (use_split) {
+        *resolved_mode = HPUSM_L2_TC_SPLIT;
+        return l2_tc_split_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
+      }
+      *resolved_mode = HPUSM_L2_TC_Q16;
+      return l2_tc_q16_knn2(q, nq, t, nt, idx, dist, ws, ws_bytes, st, fallback_rows);
     }
   }
   CUtensorMap map_q, map_qa, map_t, map_ta;

@@ -269,6 +269,9 @@ __device__ __forceinline__ void q16_slow16(const int (&key)[32], int hi, int col
 
 // cand [splits * Q_CGS][nq][Q_M] (-1 = empty); kth [splits * Q_CGS][nq]: the list's M-th key = bound on every row of
 // the list's columns that is NOT listed (INT_MIN: all of them are listed, INT_MAX: unknown).
+// DBG 0 = product.  Experiment switches (HPUSM_Q16_DBG, wrong answers, used by tools/q16_time.py to decompose the step):
+// 1 = hand-over + tensor-memory loads but no scan, 2 = hand-over only, 10 = the MMA warp runs free (pace of MMA + TMA alone).
+template <int DBG>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 l2_q16_knn_kernel(const int8_t* __restrict__ qu, const __grid_constant__ CUtensorMap map_t,
                   const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt, int q_blocks, int splits,
@@ -352,7 +355,7 @@ l2_q16_knn_kernel(const int8_t* __restrict__ qu, const __grid_constant__ CUtenso
         const uint64_t bdesc_aug = umma_desc_sw32(b_addr + s * Q_B_BYTES + 2 * Q_SLAB);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-          mbar_wait_sleepy(tmem_empty + buf, buf_phase ^ 1, Q_SLEEP_NS);   // the epilogue has read this set out
+          if (!(DBG & 8)) mbar_wait_sleepy(tmem_empty + buf, buf_phase ^ 1, Q_SLEEP_NS);   // the epilogue has read this set out
           tc_fence_after();
           const uint32_t d1 = tmem_base + (uint32_t)(Q_ACC_COL0 + buf * 2 * Q_TN);
           const uint32_t d2 = d1 + Q_TN;
@@ -425,19 +428,25 @@ l2_q16_knn_kernel(const int8_t* __restrict__ qu, const __grid_constant__ CUtenso
 #pragma unroll
       for (int j = 0; j < Q_M; ++j) { top.k[j] = Q_KEY_NONE; top.i[j] = -1; }
       bool dirty = false;
-      for (int j = 0; j < tiles; ++j) {
+      for (int j = 0; j < ((DBG & 8) ? 0 : tiles); ++j) {   // DBG 8: the MMA warp runs free (pace of MMA + TMA alone)
         const int col0 = (int)(t_begin + (int64_t)j * Q_TN) + cg * 32;
         uint32_t a1[32], a2[32];
         const uint32_t phase = m == 0 ? (buf == 1u ? 1u : 0u) : (buf == 1u ? 0u : 1u);
+        const uint32_t taddr = lane_base + (uint32_t)(Q_ACC_COL0 + buf * 2 * Q_TN + cg * 32);
         mbar_wait_sleepy(tmem_full + buf, phase, Q_SLEEP_NS);
         tc_fence_after();
-        const uint32_t taddr = lane_base + (uint32_t)(Q_ACC_COL0 + buf * 2 * Q_TN + cg * 32);
-        tc_ld32(taddr, a1);
-        tc_ld32(taddr + Q_TN, a2);
-        tc_wait_ld();
+        if ((DBG & 3) != 2) {
+          tc_ld32(taddr, a1);
+          tc_ld32(taddr + Q_TN, a2);
+          tc_wait_ld();
+        }
         tc_fence_before();
         mbar_arrive(tmem_empty + buf);   // every lane arrives (l2_tc_i8.cu)
         buf = buf == 0 ? 2u : buf - 1u;  // two pieces on: (buf + 2) % 3
+        if ((DBG & 3) != 0) {
+          if ((DBG & 3) == 1 && (a1[0] ^ a2[5]) == 0x12345678u) dirty = true;
+          continue;
+        }
         int key[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) key[i] = (int)a1[i] * 128 + (int)a2[i];
@@ -631,7 +640,10 @@ int l2_tc_q16_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_q16_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_q16_knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_q16_knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_q16_knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_q16_knn_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
     attr_done[dev].store(true, std::memory_order_release);
   }
   const int q_blocks = (int)((nq + Q_QB - 1) / Q_QB);
@@ -639,8 +651,20 @@ int l2_tc_q16_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32
   rows_per_split = (rows_per_split + Q_TN - 1) / Q_TN * Q_TN;
   const int units = q_blocks * L.splits;
   const int grid = units < sm_count() ? units : sm_count();
-  HPUSM_LAUNCH_TIMED(l2_q16_knn_kernel, grid, Q_THREADS, Q_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
-                     rows_per_split, cand, kth);
+  const char* dbg_env = getenv("HPUSM_Q16_DBG");   // experiment switches (wrong answers), see the kernel
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  if (dbg == 1)
+    HPUSM_LAUNCH_TIMED(l2_q16_knn_kernel<1>, grid, Q_THREADS, Q_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, cand, kth);
+  else if (dbg == 2)
+    HPUSM_LAUNCH_TIMED(l2_q16_knn_kernel<2>, grid, Q_THREADS, Q_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, cand, kth);
+  else if (dbg == 10)
+    HPUSM_LAUNCH_TIMED(l2_q16_knn_kernel<10>, grid, Q_THREADS, Q_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, cand, kth);
+  else
+    HPUSM_LAUNCH_TIMED(l2_q16_knn_kernel<0>, grid, Q_THREADS, Q_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, cand, kth);
   HPUSM_CHECK_LAUNCH();
   HPUSM_LAUNCH(l2_q16_finalize_kernel, (unsigned)((nq + 7) / 8), 256, 0, st, q, nq, t, cand, kth, L.splits * Q_CGS, P, idx, dist,
                list);

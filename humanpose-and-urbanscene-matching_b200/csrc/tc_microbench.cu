@@ -13,7 +13,9 @@ constexpr int MB_MMAS_PER_ROUND = 64;                       // 64 x 128 tensor c
 constexpr int MB_A_BYTES = 128 * 128, MB_B_BYTES = MB_N * 128;
 constexpr int MB_SMEM = MB_A_BYTES + MB_B_BYTES + 1024;
 
-template <int KIND>  // 0: kind::f16 with bf16 operands (K = 16 per step), 1: kind::i8 with u8 operands (K = 32 per step)
+// 0: kind::f16 with bf16 operands (K = 16 per step), 1: kind::i8 with u8 operands (K = 32 per step); N = the MMA's N;
+// A_TMEM: the A operand is read from tensor memory (the form the kNN engines use) instead of shared memory
+template <int KIND, int N = MB_N, bool A_TMEM = false>
 __global__ void __launch_bounds__(128, 1) mma_microbench_kernel(int rounds) {
   extern __shared__ uint8_t mb_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mb_raw) + 1023) & ~(uintptr_t)1023);
@@ -36,14 +38,16 @@ __global__ void __launch_bounds__(128, 1) mma_microbench_kernel(int rounds) {
   const uint32_t tmem_base = slot;
   if (warp == 0) {
     const uint64_t adesc = umma_desc_sw128(smem_u32(smem)), bdesc = umma_desc_sw128(smem_u32(smem + MB_A_BYTES));
-    const uint32_t idesc = KIND == 0 ? tc_idesc_bf16(MB_N) : ((2u << 4) | ((uint32_t)(MB_N >> 3) << 17) | ((128u >> 4) << 24));
+    const uint32_t idesc = KIND == 0 ? tc_idesc_bf16(N) : ((2u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24));
     for (int r = 0; r < rounds; ++r) {
       if (elect_one()) {
 #pragma unroll 8
         for (int i = 0; i < MB_MMAS_PER_ROUND; ++i) {
-          const uint32_t d = tmem_base + (uint32_t)((i & 1) * MB_N);
+          const uint32_t d = tmem_base + (uint32_t)((i & 1) * N);
           const uint64_t koff = (uint64_t)(2 * (i & 3));
-          if (KIND == 0) {
+          if (A_TMEM) {
+            tc_mma_i8_ts(d, tmem_base + (uint32_t)(2 * N + 8 * (i & 3)), bdesc + koff, idesc, 1u);
+          } else if (KIND == 0) {
             tc_mma_bf16(d, adesc + koff, bdesc + koff, idesc, 1u);
           } else {
             asm volatile(
@@ -75,16 +79,29 @@ using namespace hpusm;
 extern "C" {
 
 // kind 0 = bf16 (kind::f16), 1 = u8 (kind::i8).  Every SM issues rounds x 64 MMAs of 128 x 256 x (16 | 32).
+// kinds 2..5 = u8 at N = 64 / 64 with A in tensor memory / 128 / 128 with A in tensor memory (the shapes of the kNN engines).
 int hpusm_microbench_mma(int kind, int rounds, void* stream) {
-  HPUSM_REQUIRE((kind == 0 || kind == 1) && rounds > 0 && rounds <= (1 << 20), HPUSM_ERR_INVALID,
+  HPUSM_REQUIRE(kind >= 0 && kind <= 5 && rounds > 0 && rounds <= (1 << 20), HPUSM_ERR_INVALID,
                 "hpusm_microbench_mma: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (kind == 0) {
     HPUSM_CUDA_OK(cudaFuncSetAttribute(mma_microbench_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
     HPUSM_LAUNCH(mma_microbench_kernel<0>, sm_count(), 128, MB_SMEM, st, rounds);
-  } else {
+  } else if (kind == 1) {
     HPUSM_CUDA_OK(cudaFuncSetAttribute(mma_microbench_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
     HPUSM_LAUNCH(mma_microbench_kernel<1>, sm_count(), 128, MB_SMEM, st, rounds);
+  } else if (kind == 2) {   // u8, N = 64, both operands in shared memory
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(mma_microbench_kernel<1, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    HPUSM_LAUNCH((mma_microbench_kernel<1, 64, false>), sm_count(), 128, MB_SMEM, st, rounds);
+  } else if (kind == 3) {   // u8, N = 64, A in tensor memory
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(mma_microbench_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    HPUSM_LAUNCH((mma_microbench_kernel<1, 64, true>), sm_count(), 128, MB_SMEM, st, rounds);
+  } else if (kind == 4) {   // u8, N = 128, both operands in shared memory
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(mma_microbench_kernel<1, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    HPUSM_LAUNCH((mma_microbench_kernel<1, 128, false>), sm_count(), 128, MB_SMEM, st, rounds);
+  } else {                  // u8, N = 128, A in tensor memory
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(mma_microbench_kernel<1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    HPUSM_LAUNCH((mma_microbench_kernel<1, 128, true>), sm_count(), 128, MB_SMEM, st, rounds);
   }
   HPUSM_CHECK_LAUNCH();
   return HPUSM_OK;

@@ -551,12 +551,14 @@ def pose_topk_merge(cand_score, cand_index, k=16):
 
 
 def microbench_mma(kind, rounds, device):
-    """Back-to-back tcgen05.mma on every SM (kind "bf16" | "i8"); returns the operations issued (2 x MACs) for timing."""
-    k = {"bf16": 0, "i8": 1}[kind]
+    """Back-to-back tcgen05.mma on every SM (kind "bf16" | "i8" at N = 256, both operands in shared memory; "i8n64",
+    "i8n64t", "i8n128", "i8n128t": u8 at the kNN engines' shapes, t = A operand in tensor memory); returns the
+    operations issued (2 x MACs) for timing."""
+    k, n = {"bf16": (0, 256), "i8": (1, 256), "i8n64": (2, 64), "i8n64t": (3, 64), "i8n128": (4, 128), "i8n128t": (5, 128)}[kind]
     with torch.cuda.device(device):
         check(lib.hpusm_microbench_mma(k, int(rounds), _stream(device)))
     sms = torch.cuda.get_device_properties(device).multi_processor_count
-    return 2.0 * 128 * 256 * (16 if k == 0 else 32) * 64 * int(rounds) * sms
+    return 2.0 * 128 * n * (16 if k == 0 else 32) * 64 * int(rounds) * sms
 
 
 def microbench_popc(blocks, threads, iters, device, op="popc"):

@@ -38,7 +38,7 @@ extern "C" {
 
 /* L2 kNN engine selection (hpusm_knn2_l2 `mode`). */
 #define HPUSM_L2_AUTO 0   /* tensor-core path; engine chosen from the data (u8 integer MMA, else bf16 exact-int, else
-                             hi/lo split); reads a 4-byte flag back per decision, i.e. synchronises the stream      */
+                             the fixed-point integer engine HPUSM_L2_TC_Q16); reads a 4-byte flag back per decision, i.e. synchronises the stream      */
 #define HPUSM_L2_SIMT 1   /* exact FP32 CUDA-core brute force (cross-check / tiny inputs)             */
 #define HPUSM_L2_TC_INT 2 /* tcgen05, bf16 operands, integer values in [0,256] (checked on the device: a violation leaves
                              every idx at -1 and is reported by hpusm_async_status())                                   */
@@ -116,7 +116,7 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
  *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 / HPUSM_L2_TC_Q16 return HPUSM_ERR_UNSUPPORTED there.
  *   HPUSM_L2_TC_INT / HPUSM_L2_TC_I8 never synchronise: their value-range check runs on the device (see hpusm_async_status);
  *   HPUSM_L2_AUTO checks the value range on the device: integers in [0,255] (what OpenCV SIFT emits) run on the u8
- *   integer tensor pipe, integers in [0,256] on the bf16 engine, anything else (mixed signs included) on the split engine, whose
+ *   integer tensor pipe, integers in [0,256] on the bf16 engine, anything else (mixed signs included) on the fixed-point engine HPUSM_L2_TC_Q16, whose
  *   answer is the exact FP32 one as well (candidate lists are proven complete or the row is redone by the FP32 engine).
  *   idx  [nq][2] int32 as above.
  *   dist [nq][2] float32 = sqrtf( sum_k (q_k - t_k)^2 ), the sum taken in FP32 in increasing k with
@@ -347,7 +347,9 @@ int hpusm_microbench_ffma(int packed, int64_t blocks, int threads, int64_t iters
  * op 0: 3-input s32 max, 1: 3-input f32 max, 2: 2-input s32 max, 3: 2-input f32 max. */
 int hpusm_microbench_minmax(int op, int64_t blocks, int threads, int64_t iters, uint32_t* sink, void* stream);
 /* Tensor-pipe issue rate: every SM issues rounds x 64 back-to-back tcgen05.mma of 128 x 256 x (16 bf16 | 32 u8) and nothing
- * else.  kind 0 = bf16 operands (kind::f16), 1 = u8 operands (kind::i8).  The measured denominator of the K1 roofline. */
+ * else.  kind 0 = bf16 operands (kind::f16), 1 = u8 operands (kind::i8).  The measured denominator of the K1 roofline.
+ * kinds 2..5: u8 at the kNN engines' own MMA shapes -- N = 64, N = 64 with A in tensor memory, N = 128, N = 128 with A in
+ * tensor memory (rounds x 64 MMAs of 128 x N x 32). */
 int hpusm_microbench_mma(int kind, int rounds, void* stream);
 
 #ifdef __cplusplus

@@ -291,24 +291,24 @@ def test_l2_i8_fuzz_against_fp32_engine(hpusm, cuda_device):
 
 def test_l2_auto_engine_selection(hpusm, cuda_device):
     """HPUSM_L2_AUTO: u8 engine for integers in [0,255] with bounded norms, bf16 exact-int engine for other integers
-    in [0,256], split engine for the rest (mixed signs included).  The explicit integer engines never synchronise: on
+    in [0,256], the fixed-point integer engine (Q16) for the rest (mixed signs included).  The explicit integer engines never synchronise: on
     data they cannot hold the device-side check leaves every idx at -1 and hpusm_async_status() reports it after the
     next synchronisation -- an error, not a wrong answer."""
     rng = np.random.default_rng(11)
     E = hpusm.engine
     cases = [
         (rng.integers(0, 256, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_I8),
-        (rng.integers(-9, 10, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_SPLIT),    # negative query values
+        (rng.integers(-9, 10, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_Q16),      # negative query values
         (rng.integers(0, 257, (300, 128)), rng.integers(0, 100, (900, 128)), E.L2_TC_INT),      # a value of 256
         (rng.integers(0, 100, (300, 128)), rng.integers(200, 256, (900, 128)), E.L2_TC_INT),    # ||t||^2 > 4e6
-        (rng.integers(0, 100, (300, 128)) + 0.5, rng.integers(0, 100, (900, 128)), E.L2_TC_SPLIT),
+        (rng.integers(0, 100, (300, 128)) + 0.5, rng.integers(0, 100, (900, 128)), E.L2_TC_Q16),
     ]
     for q, t, want in cases:
         q, t = q.astype(np.float32), t.astype(np.float32)
         idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=E.L2_AUTO)
         assert E.knn2_l2_last_mode() == want
         ri, rd = knn_oracle.knn2_l2(q, t)
-        if want == E.L2_TC_SPLIT:
+        if want == E.L2_TC_Q16:
             assert_l2_parity(idx, dist, ri, rd, q, t)
         else:
             np.testing.assert_array_equal(idx.cpu().numpy(), ri)
@@ -920,7 +920,7 @@ def test_posedb_streaming_search(hpusm, cuda_device, tmp_path):
 
 # ---- K1 split-operand tensor engine (general float descriptors) ---------------------------------------------------
 def test_l2_split_engine_general_floats(hpusm, cuda_device):
-    """HPUSM_L2_TC_SPLIT / AUTO on non-integer descriptors: indices equal the float64 brute force (ties within the
+    """HPUSM_L2_TC_SPLIT (and AUTO, which takes the fixed-point engine) on non-integer descriptors: indices equal the float64 brute force (ties within the
     stated 1e-5 relative tolerance aside), distances to 2e-6; units, database splits and ragged tails included."""
     rng = np.random.default_rng(77)
     for nq, nt in [(300, 900), (1, 5), (129, 3), (4000, 70001), (20000, 1085)]:
@@ -929,9 +929,9 @@ def test_l2_split_engine_general_floats(hpusm, cuda_device):
         k = min(nq, nt) // 3
         if k:
             t[:k] = q[:k] + 0.05 * rng.standard_normal((k, 128)).astype(np.float32)  # planted near neighbours
-        for mode in (hpusm.engine.L2_TC_SPLIT, hpusm.engine.L2_AUTO):
+        for mode, resolved in ((hpusm.engine.L2_TC_SPLIT, hpusm.engine.L2_TC_SPLIT), (hpusm.engine.L2_AUTO, hpusm.engine.L2_TC_Q16)):
             idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=mode)
-            assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_SPLIT
+            assert hpusm.engine.knn2_l2_last_mode() == resolved
             ri, rd = knn_oracle.knn2_l2(q, t)
             assert_l2_parity(idx, dist, ri, rd, q, t)
 
@@ -941,7 +941,7 @@ def test_l2_split_engine_sift_like_unnormalised(hpusm, cuda_device):
     q, t = hpusm.synth.sift_like(3000, 20000, seed=5, planted=0.3)
     q = (q * np.float32(1.0137)).astype(np.float32)
     t = (t * np.float32(1.0137)).astype(np.float32)
-    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_AUTO)
+    idx, dist = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device), mode=hpusm.engine.L2_TC_SPLIT)
     assert hpusm.engine.knn2_l2_last_mode() == hpusm.engine.L2_TC_SPLIT
     ri, rd = knn_oracle.knn2_l2(q, t)
     assert_l2_parity(idx, dist, ri, rd, q, t)

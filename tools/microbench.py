@@ -18,7 +18,7 @@ for op in ["lop3", "popc", "imax3", "fmax3", "imax", "fmax", "ffma", "ffma2"]:
         ms = e0.elapsed_time(e1)
         ops = blocks * thr * iters
         print(op, thr, "%.1f Gop/s" % (ops / ms / 1e6), "-> %.1f lanes/clk/SM at 1.9 GHz" % (ops / ms / 1e6 / 148 / 1.9))
-for kind in ("bf16", "i8"):
+for kind in ("bf16", "i8", "i8n128", "i8n128t", "i8n64", "i8n64t"):
     for rounds in (2000, 20000):
         hpusm.engine.microbench_mma(kind, 200, dev)
         torch.cuda.synchronize()
