@@ -185,6 +185,9 @@ __device__ __forceinline__ void i8_process64(const uint32_t (&acc0)[32], const u
 }
 
 // part_idx [splits * I8_CGS][nq][2];  qu [nq][160] u8 operand rows of the queries
+// DBG 0 = product.  Experiment switches (HPUSM_I8_DBG, wrong answers, tools/q16_time.py --engine i8 decomposes the step):
+// 1 = hand-over + tensor-memory loads but no scan, 2 = hand-over only, 10 = the MMA warp runs free (MMA + TMA alone).
+template <int DBG>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtensorMap map_t,
                   const __grid_constant__ CUtensorMap map_ta, int64_t nq, int64_t nt, int q_blocks, int splits,
@@ -273,7 +276,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
           const bool tr = trace && blockIdx.x == 0 && it >= 6000 && it < 6064 && lane == 0;
           if (tr) trace[((it - 6000) * 2 + m) * 8 + 0] = clock64();
 #endif
-          mbar_wait_sleepy(tmem_empty + buf, buf_phase ^ 1, I8_SLEEP_NS);   // the epilogue has read this accumulator out
+          if (!(DBG & 8)) mbar_wait_sleepy(tmem_empty + buf, buf_phase ^ 1, I8_SLEEP_NS);   // the epilogue has read this accumulator out
           tc_fence_after();
 #ifdef I8_TRACE
           if (tr) trace[((it - 6000) * 2 + m) * 8 + 1] = clock64();
@@ -364,7 +367,7 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
       // parity bits of this warp's 64 columns, fetched one tile ahead so that an insertion never waits on memory
       uint2 pb_next = make_uint2(0u, 0u);
       if (tiles > 0) pb_next = __ldg(reinterpret_cast<const uint2*>(par + (((int)t_begin + cg * 64) >> 5)));
-      for (int j = 0; j < tiles; ++j) {
+      for (int j = 0; j < ((DBG & 8) ? 0 : tiles); ++j) {
         const int col0 = (int)(t_begin + (int64_t)j * I8_TN) + cg * 64;
         const uint2 pb = pb_next;
         if (j + 1 < tiles) pb_next = __ldg(reinterpret_cast<const uint2*>(par + ((col0 + I8_TN) >> 5)));
@@ -382,9 +385,11 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
         if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 24 + (ew & 7)] = clock64();
 #endif
         const uint32_t taddr = lane_base + (uint32_t)(I8_ACC_COL0 + buf * I8_TN + cg * 64);
-        tc_ld32(taddr, acc0);
-        tc_ld32(taddr + 32, acc1);
-        tc_wait_ld();
+        if ((DBG & 3) != 2) {
+          tc_ld32(taddr, acc0);
+          tc_ld32(taddr + 32, acc1);
+          tc_wait_ld();
+        }
         tc_fence_before();
         mbar_arrive(tmem_empty + buf);   // every lane arrives: one hop fewer on the hand-over than syncwarp + elected arrive
 #ifdef I8_TRACE
@@ -392,6 +397,10 @@ l2_i8_knn2_kernel(const uint8_t* __restrict__ qu, const __grid_constant__ CUtens
 #endif
         buf = buf == 0 ? 2u : buf - 1u;   // two pieces on: (buf + 2) % 3
         top.thr = max(top.thr, shared_thr - 1);
+        if ((DBG & 3) != 0) {
+          if ((DBG & 3) == 1 && (acc0[0] ^ acc1[5]) == 0x12345678u) top.i0 = 7;
+          continue;
+        }
         i8_process64(acc0, acc1, col0, top, pb, sh);
 #ifdef I8_TRACE
         if (tr) trace[1024 + ((j - 6000) * 2 + m) * 32 + 16 + (ew & 7)] = clock64() + (top.i0 & 0);
@@ -496,7 +505,10 @@ int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_
   int dev = 0;
   HPUSM_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    HPUSM_CUDA_OK(cudaFuncSetAttribute(l2_i8_knn2_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
     attr_done[dev].store(true, std::memory_order_release);
   }
   const int q_blocks = (int)((nq + I8_QB - 1) / I8_QB);
@@ -509,8 +521,21 @@ int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_
   const char* trace_path = getenv("HPUSM_I8_TRACE");
   if (trace_path) { HPUSM_CUDA_OK(cudaMalloc(&trace, 8192 * 8)); HPUSM_CUDA_OK(cudaMemset(trace, 0, 8192 * 8)); }
 #endif
-  HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
-                     rows_per_split, par, part, trace, require ? flag : nullptr);
+  const char* dbg_env = getenv("HPUSM_I8_DBG");   // experiment switches (wrong answers), see the kernel
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  const int* gate = require ? flag : nullptr;
+  if (dbg == 1)
+    HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel<1>, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, par, part, trace, gate);
+  else if (dbg == 2)
+    HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel<2>, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, par, part, trace, gate);
+  else if (dbg == 10)
+    HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel<10>, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, par, part, trace, gate);
+  else
+    HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel<0>, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
+                       rows_per_split, par, part, trace, gate);
   HPUSM_CHECK_LAUNCH();
   if (require) {
     int rc2 = async_report(flag, HPUSM_ERR_UNSUPPORTED, st);
