@@ -9,7 +9,16 @@ namespace hpusm {
 static thread_local int t_last_mode = HPUSM_L2_SIMT;
 static thread_local int64_t t_last_fallback = 0;
 
-static bool tc_shape_ok(int d) { return d == 128; }  // SIFT width; other widths take the FP32 engine
+static bool tc_shape_ok(int d) { return d == 128; }  // SIFT width; other widths take the FP32 engine ...
+
+// ... unless HPUSM_L2_AUTO sees a NARROWER descriptor (SURF: 64 floats, reference features.py:16) on a problem large enough
+// to pay for it: the rows are zero-padded to 128 columns inside the workspace and take the tensor path.  Zeros change no
+// distance, and the FP32 re-rank adds fma(0, 0, s) = s for them: the answer is bit for bit the d-wide one.
+constexpr int64_t kPadMinPairs = (int64_t)1 << 24;
+static bool pad_to_tc(int d, int mode, int64_t nq, int64_t nt) {
+  return mode == HPUSM_L2_AUTO && d < 128 && l2_tc_available() && nt >= 2 && nq > 0 && nq * nt >= kPadMinPairs;
+}
+static size_t pad_bytes(int64_t n) { return align_up((size_t)n * 128 * sizeof(float), 1024); }
 
 }  // namespace hpusm
 
@@ -26,6 +35,10 @@ size_t hpusm_knn2_l2_workspace_bytes(int64_t nq, int64_t nt, int d, int mode) {
   {
     const int s = l2_simt_splits(nq, nt > 0 ? nt : 1);
     simt = align_up((size_t)s * nq * 2 * sizeof(int32_t), 256) + 256;
+  }
+  if (pad_to_tc(d, mode, nq, nt)) {
+    const size_t tc = l2_tc_workspace_bytes(nq, nt, 128, mode) + pad_bytes(nq) + pad_bytes(nt);
+    return tc > simt ? tc : simt;
   }
   if (mode == HPUSM_L2_SIMT || !tc_shape_ok(d)) return simt;
   const size_t tc = l2_tc_workspace_bytes(nq, nt, d, mode);
@@ -50,6 +63,23 @@ int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d,
   cudaStream_t st = as_stream(stream);
   t_last_fallback = 0;
 
+  if (pad_to_tc(d, mode, nq, nt)) {
+    char* base = reinterpret_cast<char*>(ws);
+    float* qp = reinterpret_cast<float*>(base);
+    float* tp = reinterpret_cast<float*>(base + pad_bytes(nq));
+    const size_t used = pad_bytes(nq) + pad_bytes(nt);
+    HPUSM_CUDA_OK(cudaMemsetAsync(base, 0, used, st));
+    HPUSM_CUDA_OK(cudaMemcpy2DAsync(qp, 128 * sizeof(float), q, (size_t)d * sizeof(float), (size_t)d * sizeof(float), (size_t)nq,
+                                    cudaMemcpyDeviceToDevice, st));
+    HPUSM_CUDA_OK(cudaMemcpy2DAsync(tp, 128 * sizeof(float), t, (size_t)d * sizeof(float), (size_t)d * sizeof(float), (size_t)nt,
+                                    cudaMemcpyDeviceToDevice, st));
+    int resolved = HPUSM_L2_AUTO;
+    int64_t fallback = 0;
+    int rc = l2_tc_knn2(qp, nq, tp, nt, 128, HPUSM_L2_AUTO, idx, dist, base + used, ws_bytes - used, st, &resolved, &fallback);
+    t_last_mode = resolved;
+    t_last_fallback = fallback;
+    return rc;
+  }
   int engine = mode;
   if (mode == HPUSM_L2_AUTO) engine = (l2_tc_available() && tc_shape_ok(d) && nt >= 2) ? HPUSM_L2_AUTO : HPUSM_L2_SIMT;
   if (mode == HPUSM_L2_TC_INT || mode == HPUSM_L2_TC_SPLIT || mode == HPUSM_L2_TC_I8 || mode == HPUSM_L2_TC_Q16)

@@ -112,8 +112,9 @@ int hpusm_knn2_hamming_segmented(const uint8_t* q, int64_t nq, const uint8_t* t,
  * K1  Float-descriptor kNN, k=2, L2 norm.
  * Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) (features.py:42,:59).
  *   q [nq][d], t [nt][d] float32, C-contiguous, 16-byte aligned, d a multiple of 4, d <= 512.
- *   The tensor-core engines are built for d == 128 (SIFT); HPUSM_L2_AUTO takes the exact FP32 engine for other
- *   widths, HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 / HPUSM_L2_TC_Q16 return HPUSM_ERR_UNSUPPORTED there.
+ *   The tensor-core engines are built for d == 128 (SIFT); HPUSM_L2_AUTO zero-pads narrower rows (SURF: d = 64) to 128
+ *   columns inside the workspace when nq * nt >= 2^24 (same answer bit for bit) and takes the exact FP32 engine otherwise;
+ *   HPUSM_L2_TC_INT / HPUSM_L2_TC_SPLIT / HPUSM_L2_TC_I8 / HPUSM_L2_TC_Q16 return HPUSM_ERR_UNSUPPORTED for d != 128.
  *   HPUSM_L2_TC_INT / HPUSM_L2_TC_I8 never synchronise: their value-range check runs on the device (see hpusm_async_status);
  *   HPUSM_L2_AUTO checks the value range on the device: integers in [0,255] (what OpenCV SIFT emits) run on the u8
  *   integer tensor pipe, integers in [0,256] on the bf16 engine, anything else (mixed signs included) on the fixed-point engine HPUSM_L2_TC_Q16, whose

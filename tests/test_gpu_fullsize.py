@@ -49,6 +49,44 @@ def test_c2_sift_1m_x_1m_properties(hpusm, cuda_device):
     assert int(count.item()) >= 95000  # the planted queries pass the ratio test
 
 
+def test_c2_float_1m_x_1m_properties(hpusm, cuda_device):
+    """The general-float variant of C2 (rows x 1.0137, no longer integers) at full size: HPUSM_L2_AUTO takes the
+    fixed-point integer engine; planted neighbours, true + ordered distances, sharding invariance, and -- on a 16 384-query
+    slice -- the same answer as round 1's bf16 split engine and as the exact FP32 engine on 2 048 of those rows."""
+    n = 1 << 20
+    t = _sift_like(n, 1, cuda_device)
+    q = _sift_like(n, 2, cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    planted_q = torch.randperm(n, generator=g, device=cuda_device)[:100000]
+    planted_t = torch.randint(0, n, (100000,), generator=g, device=cuda_device)
+    q[planted_q] = torch.clamp(t[planted_t] + torch.randn((100000, 128), generator=g, device=cuda_device) * 2.0, 0, 255)
+    q *= 1.0137
+    t *= 1.0137
+    idx, dist = hpusm.knn2_l2(q, t)
+    E = hpusm.engine
+    assert E.knn2_l2_last_mode() == E.L2_TC_Q16
+    assert E.knn2_l2_last_fallback_rows() < 2000     # the proof covers the rows: the tensor path did the work
+    assert torch.equal(idx[planted_q, 0].long(), planted_t) or (
+        (dist[planted_q, 0] <= (q[planted_q] - t[planted_t]).norm(dim=1) * (1 + 1e-6)).all())
+    exact0 = (q - t[idx[:, 0].long()]).norm(dim=1)
+    exact1 = (q - t[idx[:, 1].long()]).norm(dim=1)
+    assert torch.allclose(dist[:, 0], exact0, rtol=1e-5, atol=1e-4) and torch.allclose(dist[:, 1], exact1, rtol=1e-5, atol=1e-4)
+    assert (dist[:, 0] <= dist[:, 1]).all() and (idx[:, 0] != idx[:, 1]).all() and (idx >= 0).all() and (idx < n).all()
+    h = n // 2
+    ia, da = hpusm.knn2_l2(q, t[:h].contiguous())
+    ib, db = hpusm.knn2_l2(q, t[h:].contiguous())
+    mi, md = E.knn2_merge(torch.stack([ia, torch.where(ib >= 0, ib + h, ib)]), torch.stack([da, db]))
+    # the merge orders by (sqrtf(d2), index), one pass by (d2, index): they part ways only where two rows' d2 differ below
+    # the resolution of the float32 square root (13 of 2^20 rows on this data) -- the distances must be identical
+    assert torch.equal(md, dist) and int((mi != idx).any(1).sum()) < 200
+    del ia, da, ib, db, mi, md
+    qs = q[:16384].contiguous()
+    si, sd = hpusm.knn2_l2(qs, t, mode=E.L2_TC_SPLIT)
+    assert torch.equal(si, idx[:16384]) and torch.equal(sd, dist[:16384])
+    xi, xd = hpusm.knn2_l2(qs[:2048].contiguous(), t, mode=E.L2_SIMT)
+    assert torch.equal(xi, idx[:2048]) and torch.equal(xd, dist[:2048])
+
+
 def test_c3_orb_10k_images_properties(hpusm, cuda_device):
     nimg, per = 10000, 2048
     g = torch.Generator(device=cuda_device).manual_seed(11)

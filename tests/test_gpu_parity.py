@@ -1030,6 +1030,35 @@ def test_l2_q16_near_ties_and_bad_values_take_the_exact_fallback(hpusm, cuda_dev
     assert hpusm.engine.knn2_l2_last_fallback_rows() == nq
 
 
+def test_l2_auto_pads_narrow_descriptors_onto_the_tensor_path(hpusm, cuda_device):
+    """SURF rows are 64 floats (reference features.py:16).  On a problem of >= 2^24 pairs HPUSM_L2_AUTO zero-pads rows
+    narrower than 128 inside its workspace and runs the tensor path: the answer is the d-wide exact engine's bit for
+    bit (zeros change no distance and add fma(0, 0, s) = s to the re-rank); smaller problems stay on the FP32 engine."""
+    rng = np.random.default_rng(180)
+    E = hpusm.engine
+    for d, nq, nt in [(64, 5000, 4000), (36, 4100, 4100), (124, 3000, 6000)]:
+        q = rng.standard_normal((nq, d)).astype(np.float32)
+        t = rng.standard_normal((nt, d)).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)     # SURF descriptors are unit vectors
+        t /= np.linalg.norm(t, axis=1, keepdims=True)
+        t[:1000] = q[:1000] + 0.02 * rng.standard_normal((1000, d)).astype(np.float32)
+        dq, dt = dev(q, cuda_device), dev(t, cuda_device)
+        idx, dist = hpusm.knn2_l2(dq, dt, mode=E.L2_AUTO)
+        assert E.knn2_l2_last_mode() == E.L2_TC_Q16
+        sidx, sdist = hpusm.knn2_l2(dq, dt, mode=E.L2_SIMT)
+        assert torch.equal(idx, sidx) and torch.equal(dist, sdist)
+        ri, rd = knn_oracle.knn2_l2(q, t)
+        assert_l2_parity(idx, dist, ri, rd, q, t)
+    small = dev(rng.standard_normal((300, 64)).astype(np.float32), cuda_device)
+    hpusm.knn2_l2(small, small, mode=E.L2_AUTO)
+    assert E.knn2_l2_last_mode() == E.L2_SIMT
+    ints = dev(rng.integers(0, 200, (5000, 64)).astype(np.float32), cuda_device)   # narrow AND integer: the u8 engine
+    idx, dist = hpusm.knn2_l2(ints, ints[:4000].contiguous(), mode=E.L2_AUTO)
+    assert E.knn2_l2_last_mode() == E.L2_TC_I8
+    sidx, sdist = hpusm.knn2_l2(ints, ints[:4000].contiguous(), mode=E.L2_SIMT)
+    assert torch.equal(idx, sidx) and torch.equal(dist, sdist)
+
+
 def test_scene_score_batch_reference(hpusm, cuda_device):
     """Batched scene score vs the reference's perspective_correction + affine_multi (recorded, picks pinned), and the
     seeded picks vs the oracle."""
