@@ -119,6 +119,8 @@ l2_q16_stats_kernel(const float* __restrict__ x, int64_t n, int is_db, QParams* 
 __global__ void l2_q16_params_kernel(QParams* __restrict__ P) {
   const float amax = __int_as_float(P->amax_bits), tmax = __int_as_float(P->tmax_bits);
   float d = fmaxf(amax / (float)Q_XMAX, sqrtf(tmax / Q_TSCALE)) * 1.00001f;
+  // magnitudes whose squares leave the normal FP32 range: the FP32 norms the bound is built from would be wrong
+  if (amax > 0.f && (amax < 1e-18f || amax > 1e18f)) P->bad = 1;
   if (!(d > 0.f) || !(d <= FLT_MAX)) d = 1.f;   // all-zero input (or flagged bad): any scale will do
   if (d < 1e-30f) d = 1e-30f;                   // keep 1 / delta^2 finite
   P->delta = d;

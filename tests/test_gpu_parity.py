@@ -1024,6 +1024,9 @@ def test_l2_q16_near_ties_and_bad_values_take_the_exact_fallback(hpusm, cuda_dev
         t[100 * r:100 * r + 20] = q[r] + 1e-4 * rng.standard_normal((20, 128)).astype(np.float32)
     _, _, fb = _q16_equals_exact(hpusm, cuda_device, q, t)
     assert fb >= 30
+    tiny = (q * np.float32(1e-24)).astype(np.float32), (t * np.float32(1e-24)).astype(np.float32)
+    _, _, fb = _q16_equals_exact(hpusm, cuda_device, *tiny)   # squares underflow FP32: no bound can be built, all rows exact
+    assert fb == nq
     t[17, 5] = np.inf
     dq, dt = dev(q, cuda_device), dev(t, cuda_device)
     hpusm.knn2_l2(dq, dt, mode=hpusm.engine.L2_TC_Q16)
