@@ -12,8 +12,8 @@ the 16 B/query partial results followed by the lexicographic merge + ratio kerne
 The headline `value` is WEAK scaling (every rank owns `--nt` rows, config.nt_global = N x nt); the same line carries
 `strong_scaling` (the fixed nq x nt problem with the database rows divided over the ranks), `nccl_parity` (rank 0
 checks the merged answer of a query slice against one single-GPU pass over the gathered database) and `others`: the
-remaining BASELINE.json configs (ORB retrieval, batched RANSAC, pose database), each with its own value / e2e /
-roofline / clocks and, at N = 1, cpu_baseline.  Prints ONE JSON line on rank 0.
+remaining BASELINE.json configs (the general-float variant of this one, ORB retrieval, batched RANSAC, pose database), each
+with its own value / e2e / roofline / clocks and, at N = 1, cpu_baseline.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import importlib
@@ -416,6 +416,36 @@ def _i8_sustained_peak(hp, device, seconds):
     torch.cuda.synchronize(device)
     clocks = sampler.stop()
     return ops * n / (e0.elapsed_time(e1) * 1e-3) / 1e12, clocks
+
+
+def run_sift_float(args, rank, world, device, hp, i8_peak=None):
+    """SURVEY 8d's "general float" variant of C2 (the same rows x 1.0137: no longer integers) as one of `others`:
+    HPUSM_L2_AUTO takes the fixed-point integer engine (l2_tc_q16.cu).  Weak form at N > 1 (1 M database rows per GPU)."""
+    import copy
+    a = copy.copy(args)
+    a.descriptors, a.l2_engine, a.steps = "float", "auto", max(3, min(args.steps, 10))
+    r = sift_pass(a, rank, world, device, hp, a.nt, rank * a.nt, "weak-float")
+    r.pop("answer", None)
+    if rank != 0:
+        return None
+    pairs = float(a.nq) * a.nt * world
+    k_ms = r["kernel_ms"] / max(r["kernel_n"], 1)
+    achieved = FLOP_PER_PAIR * float(a.nq) * a.nt * a.steps / max(r["kernel_n"], 1) / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    peak = i8_peak or 0.0
+    key = "sift:%s:%dx%d" % (r["mode"], a.nq, a.nt)
+    return {"metric": "descriptor-pairs/sec (kNN+ratio)", "value": pairs * a.steps / (r["ms"] * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": a.steps, "ms_per_step": r["ms"] / a.steps, "scaling": "weak", "dtype": DTYPE_OF.get(r["mode"], "f32"), "data": "synthetic",
+            "config": dict(sift_config(a, world), workload="C2 general-float variant: the same synthetic rows x 1.0137 (not integers), 1M x 1M kNN k=2 ratio test"),
+            "detail": {"engine": r["mode"], "fallback_rows": r["fallback_rows"], "ratio_survivors": r["survivors"]},
+            "e2e": {"value": pairs * a.steps / (r["e2e_ms"] * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "gpu_launches": int(r["launches"]),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "frac_issued": achieved / peak * 832.0 / FLOP_PER_PAIR if peak and r["mode"] == "tcgen05-i8-q16-split" else None,
+                         "traffic": measured_traffic(key), "kernel_ms": k_ms, "kernel_launches": int(r["kernel_n"]),
+                         "peak_source": "the sustained kind::i8 issue rate measured for the headline line of this run; frac counts the 256 "
+                                        "algorithmic op per pair, frac_issued the 832 the 13 MMAs per tile issue",
+                         "ncu": measured_traffic(key, "ncu")},
+            "clocks": r["clocks"]}
 
 
 def run_sift(args, rank, world, device, hp):
@@ -954,7 +984,11 @@ def main():
                                                                     "--descriptors", args.descriptors])
         if not args.no_others:
             others = {}
-            for name in ("orb", "ransac", "pose"):
+            i8_peak = (out or {}).get("roofline", {}).get("peak") if rank == 0 and (out or {}).get("detail", {}).get("engine") == "tcgen05-i8-exact-int" else None
+            runners["sift_float"] = lambda *a: run_sift_float(*a, i8_peak=i8_peak)
+            for name in ("sift_float", "orb", "ransac", "pose"):
+                if name == "sift_float" and args.descriptors == "float":
+                    continue
                 torch.cuda.empty_cache()
                 log("others: %s" % name)
                 try:
