@@ -104,8 +104,9 @@ class StreamedL2Matcher:
     q0, t0, q1 .. qN, t1, t2 .. and the compute stream sweeps every query chunk against t0 while t1 is still in
     flight, then against t1, ...  Only q0 and t0 are exposed.  The per-database-chunk top-2 lists are merged once at
     the end by the lexicographic merge kernel, which is exact because the global top-2 lies in the union of the
-    per-chunk top-2s.  The database is cut in few pieces on purpose: every piece adds a candidate pair per query to
-    the exact re-rank.
+    per-chunk top-2s.  The database is cut in few pieces on purpose: every piece restarts the running top-2 lists of
+    the sweep and adds a candidate pair per query to the exact re-rank (measured: a third piece that would keep the GPU
+    busy while the rest of the database is still in flight costs 3.5 ms more than the idle time it removes).
 
     Callable as knn_fn(q_host, t_host) -> (idx [nq,2] int32, dist [nq,2] float32) on the device, so it drops into
     knn2_sharded.  Buffers, streams and events are created once; the returned tensors may alias them and are valid
@@ -120,12 +121,23 @@ class StreamedL2Matcher:
         rank, nranks = world()
         self.q_per = -(-self.nq // nranks) if self.query_slices else self.nq
         self.q_lo, self.q_hi = shard_range(self.nq, rank, nranks) if self.query_slices else (0, self.nq)
-        if q_chunk is None:
-            # a query chunk = 7 full waves of the persistent kernel's 256-query units: chunks that are not a multiple of
-            # (SM count x 256) rows leave the last wave partly empty (measured: 134 ms with 131072-row chunks, 124 ms so)
-            q_chunk = 7 * 256 * torch.cuda.get_device_properties(self.device).multi_processor_count
         self.mode = engine.L2_AUTO if mode is None else mode
-        self.q_bounds = self._bounds(self.nq, 0, q_chunk)
+        if q_chunk is None:
+            # Query chunks are whole waves of the persistent kernel's 256-query units (chunks that are not a multiple of
+            # SM count x 256 rows leave the last wave partly empty: 134 ms with 131072-row chunks, 124 ms with 7-wave ones),
+            # and they GROW: 1, 1, 2, 3, 4, 6, 9 ... waves.  Only the first chunk's upload is exposed, and a chunk 1.5 x
+            # the size of the one being matched against the first database chunk still lands before that match is done
+            # (PCIe delivers ~107 k rows/ms, the sweep over 131072 database rows consumes ~71 k query rows/ms).
+            wave = 256 * torch.cuda.get_device_properties(self.device).multi_processor_count
+            cuts, k = [0], [1, 1, 2, 3, 4, 6, 9]
+            while cuts[-1] < self.nq:
+                w = k[len(cuts) - 1] if len(cuts) - 1 < len(k) else 9
+                cuts.append(min(self.nq, cuts[-1] + w * wave))
+            if len(cuts) > 2 and cuts[-1] - cuts[-2] < wave // 2:   # a sliver joins its neighbour
+                del cuts[-2]
+            self.q_bounds = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+        else:
+            self.q_bounds = self._bounds(self.nq, 0, q_chunk)
         self.t_bounds = self._bounds(self.nt, t_first, t_chunk)
         dev = self.device
         nrows = self.q_per * nranks if self.query_slices else self.nq
@@ -137,7 +149,10 @@ class StreamedL2Matcher:
         nparts = max(len(self.t_bounds), 1)
         self.part_idx = torch.empty((nparts, self.nq, 2), dtype=torch.int32, device=dev)
         self.part_dist = torch.empty((nparts, self.nq, 2), dtype=torch.float32, device=dev)
-        self.ws = engine.knn2_l2_workspace(qmax, tmax, self.d, self.mode, dev) if qmax and tmax else None
+        # database chunks after the first are matched against ALL queries in one call (they have all landed by then): one
+        # operand preparation of the big chunk instead of one per query chunk
+        self.ws = engine.knn2_l2_workspace(self.nq if len(self.t_bounds) > 1 or self.query_slices else qmax, tmax, self.d,
+                                           self.mode, dev) if qmax and tmax else None
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.q_ready = [torch.cuda.Event() for _ in self.q_bounds]
         self.t_ready = [torch.cuda.Event() for _ in self.t_bounds]
@@ -191,11 +206,14 @@ class StreamedL2Matcher:
             dist.all_gather_into_tensor(self.dq, self.dq_slice)  # rank r's rows land at [r * q_per, (r + 1) * q_per)
         for j, (ta, tb) in enumerate(self.t_bounds):
             cur.wait_event(self.t_ready[j])
-            for i, (qa, qb) in enumerate(self.q_bounds):
-                if j == 0 and not self.query_slices:
+            if j > 0 or self.query_slices:   # every query row is on the device: one call per database chunk
+                engine.knn2_l2(self.dq[:self.nq], self.dt[ta:tb], mode=self.mode, out=(self.part_idx[j], self.part_dist[j]),
+                               workspace=self.ws)
+            else:
+                for i, (qa, qb) in enumerate(self.q_bounds):
                     cur.wait_event(self.q_ready[i])
-                pi, pd = self.part_idx[j, qa:qb], self.part_dist[j, qa:qb]
-                engine.knn2_l2(self.dq[qa:qb], self.dt[ta:tb], mode=self.mode, out=(pi, pd), workspace=self.ws)
+                    pi, pd = self.part_idx[j, qa:qb], self.part_dist[j, qa:qb]
+                    engine.knn2_l2(self.dq[qa:qb], self.dt[ta:tb], mode=self.mode, out=(pi, pd), workspace=self.ws)
             if ta:
                 self.part_idx[j] = globalize(self.part_idx[j], ta)
         if ntc == 1:

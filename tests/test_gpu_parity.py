@@ -399,6 +399,14 @@ def test_l2_streamed_host_matcher(hpusm, cuda_device):
             assert torch.equal(idx, ri) and torch.equal(dist, rd)
     with pytest.raises(ValueError):
         m(dev(q, cuda_device), dev(t, cuda_device))
+    # default chunking: growing whole-wave query chunks against the first database chunk, then ONE call per later chunk
+    nq, nt = 3 * 256 * 148 + 77, 300001
+    q, t = hpusm.synth.sift_like(nq, nt, seed=9, planted=0.2)
+    m = hpusm.retrieval.StreamedL2Matcher(nq, nt, 128, cuda_device, t_chunk=100000)
+    assert len(m.q_bounds) >= 3 and len(m.t_bounds) >= 3
+    idx, dist = m(torch.from_numpy(q).pin_memory(), torch.from_numpy(t).pin_memory())
+    ri, rd = hpusm.knn2_l2(dev(q, cuda_device), dev(t, cuda_device))
+    assert torch.equal(idx, ri) and torch.equal(dist, rd)
 
 
 def test_l2_auto_equals_simt_at_scale(hpusm, cuda_device):
