@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HPUSM_ABI_VERSION 201
+#define HPUSM_ABI_VERSION 202
 
 #define HPUSM_OK 0
 #define HPUSM_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported width) */

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(hpusm):
 
 def test_version_and_error_string(hpusm):
     lib = hpusm._lib.lib
-    assert lib.hpusm_version() == 201
+    assert lib.hpusm_version() == 202
     rc = lib.hpusm_knn2_hamming(None, 4, None, 4, 48, None, None, None, 0, None)  # unsupported width, no GPU needed
     assert rc == hpusm._lib.ERR_UNSUPPORTED
     assert "48" in hpusm._lib.last_error()
