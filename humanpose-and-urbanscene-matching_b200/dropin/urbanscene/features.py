@@ -1,6 +1,7 @@
 """urbanscene/features.py of the reference with the same signatures; kNN, ratio filter, RANSAC homography, inlier
 gather and the corner projection run on the GPU (features.py:42,:45-55,:57-105,:177-234)."""
 import logging
+import os
 
 import numpy as np
 import torch
@@ -100,13 +101,23 @@ class OrbGpu(object):
     """The reference's ORB (features.py:19-20) on the GPU: `detectAndCompute(img, None)` returns cv2's keypoints (same
     order, identical pt / octave / size / response / angle, as a KeyPointArray) and cv2's descriptors bit for bit --
     pyramid, FAST + non-maximum suppression, orientation, smoothing and the rBRIEF tests all run on the device
-    (hpusm_orb_detect_and_compute).  Masks, and images dense enough for OpenCV's per-level keypoint cap to bite, go to
-    the OpenCV detector for detection (description still on the GPU).  `last_descriptors` keeps the device tensor of the
-    last call so a caller that goes on to match can skip the upload."""
+    (hpusm_orb_detect_and_compute).  There is NO silent CPU path: a detection mask (the reference never passes one) and an
+    image dense enough for OpenCV's per-level keypoint cap to bite (its cull is a partial sort whose tie order is not
+    specified, so it cannot be reproduced bit for bit) raise, with the two explicit ways out in the message --
+    HPUSM_ORB_CPU_DETECT=1 (OpenCV detects on the CPU for exactly those calls, description stays on the GPU) or
+    HPUSM_ORB=cv2 (OpenCV's ORB altogether).  `last_descriptors` keeps the device tensor of the last call so a caller that
+    goes on to match can skip the upload."""
 
     def __init__(self, cv_detector):
         self.cv = cv_detector
         self.last_descriptors = None
+
+    def _cpu_detect(self, image, mask, why):
+        if os.environ.get("HPUSM_ORB_CPU_DETECT", "") != "1":
+            raise NotImplementedError("OrbGpu: %s is not done on the device; set HPUSM_ORB_CPU_DETECT=1 to let OpenCV detect on "
+                                      "the CPU for such calls (description stays on the GPU), or HPUSM_ORB=cv2 for OpenCV's ORB" % why)
+        logging.warning("OrbGpu: %s: detection by OpenCV on the CPU (HPUSM_ORB_CPU_DETECT=1)", why)
+        return self.cv.detect(image, mask)
 
     @staticmethod
     def _gray(image):
@@ -117,7 +128,7 @@ class OrbGpu(object):
 
     def detect(self, image, mask=None):
         if mask is not None:
-            return self.cv.detect(image, mask)
+            return self._cpu_detect(image, mask, "detection under a mask")
         return self.detectAndCompute(image, None, want_descriptors=False)[0]
 
     def compute(self, image, keypoints):
@@ -137,10 +148,11 @@ class OrbGpu(object):
 
     def detectAndCompute(self, image, mask=None, want_descriptors=True):
         if mask is not None:
-            return self.compute(image, self.cv.detect(image, mask))
+            return self.compute(image, self._cpu_detect(image, mask, "detection under a mask"))
         out = engine.orb_detect_and_compute(up(self._gray(image), np.uint8), want_descriptors=want_descriptors)
-        if out["over_quota"]:  # OpenCV would cull this level by response: let it
-            return self.compute(image, self.cv.detect(image, None)) if want_descriptors else (self.cv.detect(image, None), None)
+        if out["over_quota"]:  # OpenCV would cull this level by response (retainBest): not reproducible bit for bit
+            kps = self._cpu_detect(image, None, "a pyramid level with more keypoints than OpenCV's per-level quota")
+            return self.compute(image, kps) if want_descriptors else (kps, None)
         kps = KeyPointArray(down(out["pt"]), down(out["size"]), down(out["angle"]), down(out["response"]), down(out["octave"]))
         self.last_descriptors = out["desc"]
         return kps, (down(out["desc"]) if want_descriptors else None)
@@ -155,7 +167,6 @@ def init_feature(name):
     jochen_deel.py:14, dataset/dataset_urbanscene.py:11) get the same exact brute-force GPU matcher: FLANN's KD-tree / LSH
     index only approximates the k=2 neighbours that this matcher returns exactly, and match_and_draw consumes both through
     the same knnMatch contract.  Set HPUSM_FLANN=cv2 to get the reference's own cv2.FlannBasedMatcher instead."""
-    import os
     import cv2
     chunks = name.split('-')
     if chunks[0] == 'sift':

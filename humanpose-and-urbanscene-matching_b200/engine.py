@@ -351,7 +351,8 @@ def orb_detect_and_compute(img, capacity=None, want_descriptors=True, nlevels=OR
     """cv2.ORB.detectAndCompute(img, None) of the reference's ORB on the device.  img [h,w] uint8 CUDA tensor.
     Returns a dict of device tensors cut to the keypoint count: pt [n,2] f32, octave [n] i32, angle / response / size
     [n] f32, desc [n,32] u8 (None when not wanted), plus level_counts (host list), and over_quota (a level exceeded
-    OpenCV's per-level cap: cv2 would have culled by response, the device path does not -- fall back)."""
+    OpenCV's per-level cap: cv2 would have culled by response with an unspecified tie order, the device path does not -- the
+    drop-in raises unless the caller opted into OpenCV's detector)."""
     img = _cuda(img, torch.uint8, "img")
     if img.dim() != 2:
         raise ValueError("img must be [height, width] uint8")

@@ -1,6 +1,8 @@
 """The drop-in modules (reference names and signatures) against the golden vectors recorded from the reference."""
 import importlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -164,6 +166,16 @@ def test_orb_detector_dropin_equals_cv2(mods):
         np.testing.assert_array_equal(desc, desc_ref)
         np.testing.assert_array_equal(desc, g["desc_%d" % k])
     assert detector.getNLevels() == 8  # attribute access falls through to the OpenCV detector
+    # no silent CPU path: a detection mask (the reference never passes one) raises unless the caller opts in explicitly
+    mask = np.full(img.shape, 255, np.uint8)
+    with pytest.raises(NotImplementedError):
+        detector.detectAndCompute(img, mask)
+    os.environ["HPUSM_ORB_CPU_DETECT"] = "1"
+    try:
+        kp_m, desc_m = detector.detectAndCompute(img, mask)   # OpenCV detects, the GPU describes: still cv2's answer
+        np.testing.assert_array_equal(desc_m, desc_ref)
+    finally:
+        del os.environ["HPUSM_ORB_CPU_DETECT"]
 
 
 def test_transformation_functions(mods):
