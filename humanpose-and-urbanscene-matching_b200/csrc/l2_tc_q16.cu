@@ -22,7 +22,8 @@
 // row, takes the lexicographic (d2, index) top-2 and checks
 //      d2(second) + E(q) < ||q||^2 - 256 delta^2 max_lists key(M-th)
 // which proves that no row outside the lists is as close as the second neighbour.  Rows failing the check are redone by
-// the exact FP32 engine (l2_simt.cu) after one host read of their count, so the answer is the exact FP32 one.
+// the exact FP32 engine (l2_simt.cu) after one host read of their count, so the answer is the exact FP32 one; when there
+// are many of them (clustered data) they first go through the bf16 split engine, whose bound is 20 x tighter.
 //
 // Kernel shape: l2_tc_i8.cu's (persistent CTA per SM, TMA ring, one elected MMA issuer, query rows in TENSOR memory, three
 // accumulator sets in rotation, 16 epilogue warps), with N = 64 tiles: a set = [a1 | a2] = 2 x 64 columns, the 2 x 64
@@ -563,6 +564,25 @@ l2_q16_finalize_kernel(const float* __restrict__ q, int64_t nq, const float* __r
   }
 }
 
+// ---- cascade: many unproven rows go through the bf16 split engine (20 x tighter bound) before the exact engine --------------
+__global__ void __launch_bounds__(256)
+l2_q16_gather_rows_kernel(const float* __restrict__ q, const int32_t* __restrict__ list, int64_t m, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= m) return;
+  reinterpret_cast<float4*>(out + i * Q_D)[lane] = __ldg(reinterpret_cast<const float4*>(q + (int64_t)list[i] * Q_D) + lane);
+}
+
+__global__ void __launch_bounds__(256)
+l2_q16_scatter_rows_kernel(const int32_t* __restrict__ list, int64_t m, const int32_t* __restrict__ idx_sub,
+                           const float* __restrict__ dist_sub, int32_t* __restrict__ idx, float* __restrict__ dist) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const int64_t row = list[i];
+  idx[row * 2] = idx_sub[i * 2]; idx[row * 2 + 1] = idx_sub[i * 2 + 1];
+  dist[row * 2] = dist_sub[i * 2]; dist[row * 2 + 1] = dist_sub[i * 2 + 1];
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static int q16_splits(int64_t nq, int64_t nt) {
   const int64_t qbs = (nq + Q_QB - 1) / Q_QB;
@@ -582,10 +602,13 @@ static int q16_splits(int64_t nq, int64_t nt) {
   return (int)s;
 }
 
+constexpr int64_t Q_CASCADE_MIN = 1024;   // unproven rows from which the split engine is worth its database preparation
+constexpr int64_t Q_CASCADE_ROWS = 65536;  // rows per pass of the cascade
+
 struct Q16Layout {
-  size_t qb, tb, par, cand, kth, list, fb, total;
+  size_t qb, tb, par, cand, kth, list, fb, sub_q, sub_idx, sub_dist, sub_ws, sub_ws_bytes, total;
   int splits, fb_splits;
-  int64_t nt_pad;
+  int64_t nt_pad, sub_rows;
 };
 
 static Q16Layout q16_layout(int64_t nq, int64_t nt) {
@@ -601,6 +624,17 @@ static Q16Layout q16_layout(int64_t nq, int64_t nt) {
   L.kth = off; off += align_up((size_t)L.splits * Q_CGS * nq * sizeof(int32_t), 1024);
   L.list = off; off += align_up((size_t)nq * sizeof(int32_t), 1024);
   L.fb = off; off += align_up((size_t)L.fb_splits * (nq < Q_FB_ROWS ? nq : Q_FB_ROWS) * 2 * sizeof(int32_t), 1024);
+  // cascade buffers: only when the query set can produce that many unproven rows at all
+  L.sub_rows = nq >= Q_CASCADE_MIN ? (nq < Q_CASCADE_ROWS ? nq : Q_CASCADE_ROWS) : 0;
+  L.sub_q = L.sub_idx = L.sub_dist = L.sub_ws = off;
+  L.sub_ws_bytes = 0;
+  if (L.sub_rows > 0) {
+    L.sub_q = off; off += align_up((size_t)L.sub_rows * Q_D * sizeof(float), 1024);
+    L.sub_idx = off; off += align_up((size_t)L.sub_rows * 2 * sizeof(int32_t), 1024);
+    L.sub_dist = off; off += align_up((size_t)L.sub_rows * 2 * sizeof(float), 1024);
+    L.sub_ws_bytes = align_up(l2_tc_split_workspace_bytes(L.sub_rows, nt), 1024);
+    L.sub_ws = off; off += L.sub_ws_bytes;
+  }
   L.total = off;
   return L;
 }
@@ -676,6 +710,29 @@ int l2_tc_q16_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32
   HPUSM_CUDA_OK(cudaMemcpyAsync(&h_list, &P->n_list, sizeof(int), cudaMemcpyDeviceToHost, st));
   HPUSM_CUDA_OK(cudaStreamSynchronize(st));
   *fallback_rows = h_list;
+  const char* casc_env = getenv("HPUSM_Q16_CASCADE");   // "0": unproven rows go straight to the exact engine (tests, A/B)
+  if (h_list >= Q_CASCADE_MIN && L.sub_rows > 0 && !(casc_env && casc_env[0] == '0')) {
+    // Many rows the fixed-point bound cannot cover (clustered data: neighbours closer together than E): the bf16 split
+    // engine, whose bound is 20 x tighter, takes them before anything reaches the CUDA-core engine (1.3e12 against 1.5e11
+    // pairs/s).  Its own unproven rows take its own exact fallback; the answers are scattered back to their rows.
+    float* sub_q = reinterpret_cast<float*>(base + L.sub_q);
+    int32_t* sub_idx = reinterpret_cast<int32_t*>(base + L.sub_idx);
+    float* sub_dist = reinterpret_cast<float*>(base + L.sub_dist);
+    int64_t exact_rows = 0;
+    for (int64_t lo = 0; lo < h_list; lo += L.sub_rows) {
+      const int64_t m = h_list - lo < L.sub_rows ? h_list - lo : L.sub_rows;
+      HPUSM_LAUNCH(l2_q16_gather_rows_kernel, (unsigned)((m + 7) / 8), 256, 0, st, q, list + lo, m, sub_q);
+      HPUSM_CHECK_LAUNCH();
+      int64_t fb2 = 0;
+      rc = l2_tc_split_knn2(sub_q, m, t, nt, sub_idx, sub_dist, base + L.sub_ws, L.sub_ws_bytes, st, &fb2);
+      if (rc != HPUSM_OK) return rc;
+      exact_rows += fb2;
+      HPUSM_LAUNCH(l2_q16_scatter_rows_kernel, (unsigned)((m + 255) / 256), 256, 0, st, list + lo, m, sub_idx, sub_dist, idx, dist);
+      HPUSM_CHECK_LAUNCH();
+    }
+    *fallback_rows = exact_rows;   // rows that needed the exact engine in the end
+    return HPUSM_OK;
+  }
   for (int64_t lo = 0; lo < h_list; lo += Q_FB_ROWS) {
     const int64_t m = h_list - lo < Q_FB_ROWS ? h_list - lo : Q_FB_ROWS;
     rc = l2_simt_candidates(q, nq, t, nt, Q_D, list + lo, m, L.fb_splits, fb, st);

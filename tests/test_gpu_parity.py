@@ -1041,6 +1041,29 @@ def test_l2_q16_near_ties_and_bad_values_take_the_exact_fallback(hpusm, cuda_dev
     assert hpusm.engine.knn2_l2_last_fallback_rows() == nq
 
 
+def test_l2_q16_cascade_through_the_split_engine(hpusm, cuda_device):
+    """Clustered data: every query has 7 database rows at squared distances 0.05 (1 + 0.25 k): the 6th is within the
+    fixed-point bound (~0.1) of the 2nd, so a 6-deep list cannot be proven complete, while the 4th is farther from the 2nd
+    than the bf16 split engine's bound (~0.01).  With >= 1024 unproven rows the fixed-point engine hands them to the split
+    engine (only ITS unproven rows reach the CUDA-core engine): the answer is still the exact engine's, and few rows needed it."""
+    rng = np.random.default_rng(181)
+    nq, nt = 3000, 30000
+    q = rng.standard_normal((nq, 128)).astype(np.float32)
+    t = rng.standard_normal((nt, 128)).astype(np.float32)
+    for r in range(nq):
+        u = rng.standard_normal((7, 128))
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        t[8 * r:8 * r + 7] = (q[r] + np.sqrt(0.05 * (1 + 0.25 * np.arange(7)))[:, None] * u).astype(np.float32)
+    os.environ["HPUSM_Q16_CASCADE"] = "0"
+    try:
+        _, _, direct = _q16_equals_exact(hpusm, cuda_device, q, t)
+    finally:
+        del os.environ["HPUSM_Q16_CASCADE"]
+    assert direct >= 1024, direct     # the fixed-point proof fails on (nearly) every row of this data ...
+    _, _, fb = _q16_equals_exact(hpusm, cuda_device, q, t)
+    assert fb < direct // 4, (fb, direct)   # ... and the split engine in between settles most of them
+
+
 def test_l2_auto_pads_narrow_descriptors_onto_the_tensor_path(hpusm, cuda_device):
     """SURF rows are 64 floats (reference features.py:16).  On a problem of >= 2^24 pairs HPUSM_L2_AUTO zero-pads rows
     narrower than 128 inside its workspace and runs the tensor path: the answer is the d-wide exact engine's bit for
