@@ -85,6 +85,10 @@ int hpusm_knn2_l2(const float* q, int64_t nq, const float* t, int64_t nt, int d,
   if (mode == HPUSM_L2_TC_INT || mode == HPUSM_L2_TC_SPLIT || mode == HPUSM_L2_TC_I8 || mode == HPUSM_L2_TC_Q16)
     HPUSM_REQUIRE(tc_shape_ok(d), HPUSM_ERR_UNSUPPORTED,
                   "hpusm_knn2_l2: the tensor-core engine is built for d == 128, got %d", d);
+  if (engine != HPUSM_L2_SIMT && nt < 2)
+    HPUSM_REQUIRE(false, HPUSM_ERR_UNSUPPORTED,
+                  "hpusm_knn2_l2: the tensor-core engines need at least 2 database rows (got %lld); use HPUSM_L2_AUTO or HPUSM_L2_SIMT",
+                  (long long)nt);
 
   if (engine == HPUSM_L2_SIMT) {
     t_last_mode = HPUSM_L2_SIMT;
