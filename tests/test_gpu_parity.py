@@ -363,6 +363,15 @@ def test_ransac_streamed_batch_equals_one_call(hpusm, cuda_device):
         H, mask, ninl = sb(torch.from_numpy(src).pin_memory(), torch.from_numpy(dst).pin_memory())
         assert torch.equal(torch.nan_to_num(H, nan=-7.0), torch.nan_to_num(want[0], nan=-7.0))
         assert torch.equal(mask, want[1]) and torch.equal(ninl, want[2])
+    # default chunking: a first run of one wave of the one-CTA-per-pair kernel (3 CTAs per SM), then runs of two waves
+    src2, dst2, offs2 = hpusm.synth.ransac_batch(1000, 64, 0.5, seed=4)
+    want2 = hpusm.engine.ransac_homography_batch(dev(src2, cuda_device), dev(dst2, cuda_device), dev(offs2, cuda_device), 5.0, 64,
+                                                 0.995, seed=8)
+    sb2 = hpusm.retrieval.StreamedHomographyBatch(offs2, cuda_device, 5.0, 64, 0.995, seed=8)
+    assert len(sb2.chunks) >= 2 and sb2.chunks[0][1] == 3 * torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    H2, mask2, ninl2 = sb2(torch.from_numpy(src2).pin_memory(), torch.from_numpy(dst2).pin_memory())
+    assert torch.equal(torch.nan_to_num(H2, nan=-7.0), torch.nan_to_num(want2[0], nan=-7.0))
+    assert torch.equal(mask2, want2[1]) and torch.equal(ninl2, want2[2])
     # and the slice entry point on its own: pairs 5.. of the batch, scored as pairs 5.. of the sample table
     p0 = 5
     r0 = int(offs[p0])
