@@ -293,6 +293,8 @@ def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
         return rt.knn2_sharded(q, t, row0, kind="l2", ratio=0.8, knn_fn=local_knn)
 
     tm = Timer(args, rank, world, device, hp)
+    if label == "strong":   # 1/N of the work per step: raise the step count until the region lasts --min-region-ms
+        tm.fit_region(step)
     r = tm.run(step)
     mi, md, keep, count = r["out"]
     survivors = int(count.item())
@@ -331,7 +333,9 @@ def sift_pass(args, rank, world, device, hp, nt_rank, row0, label):
     e = tm.run(e2e_step, profile=False)
     assert int(h_keep.sum()) == survivors, "e2e pass disagrees with the resident pass"
     del streamed
-    return {"ms": r["ms"], "e2e_ms": e["ms"], "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "launches": r["launches"],
+    k = float(args.steps) / float(r["steps"])   # the callers' formulas count args.steps steps: scale the regions to that
+    return {"ms": r["ms"] * k, "e2e_ms": e["ms"] * k, "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "launches": int(r["launches"] * k),
+            "steps_timed": int(r["steps"]),
             "clocks": r["clocks"], "survivors": survivors, "mode": mode, "parity": parity, "nt_rank": nt_rank,
             "h2d": int(hq.numel() * 4 + ht.numel() * 4), "d2h": int(h_idx.numel() * 4 + h_dst.numel() * 4 + h_keep.numel()),
             "fallback_rows": eng.knn2_l2_last_fallback_rows(), "answer": (mi.clone(), md.clone())}
@@ -362,6 +366,7 @@ def sift_query_sharded_pass(args, rank, world, device, hp, nt_rank, row0, db_sha
         return rt.knn2_query_sharded(q_slice, t_full, nq, kind="l2", ratio=0.8, knn_fn=local_knn)
 
     tm = Timer(args, rank, world, device, hp)
+    tm.fit_region(step)
     r = tm.run(step)
     mi, md, keep, count = r["out"]
     same = bool(torch.equal(mi, db_sharded_answer[0]) and torch.equal(md, db_sharded_answer[1]))
@@ -381,8 +386,9 @@ def sift_query_sharded_pass(args, rank, world, device, hp, nt_rank, row0, db_sha
     e = tm.run(e2e_step, profile=False)
     assert int(h_keep.sum()) == int(count.item()), "e2e pass disagrees with the resident pass"
     del streamed
-    return {"ms": r["ms"], "e2e_ms": e["ms"], "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "identical": same,
-            "nt_rank": int(t_full.shape[0]), "h2d": int(hq.numel() * 4 + ht.numel() * 4)}
+    k = float(args.steps) / float(r["steps"])
+    return {"ms": r["ms"] * k, "e2e_ms": e["ms"] * k, "kernel_ms": r["kernel_ms"], "kernel_n": r["kernel_n"], "identical": same,
+            "steps_timed": int(r["steps"]), "nt_rank": int(t_full.shape[0]), "h2d": int(hq.numel() * 4 + ht.numel() * 4)}
 
 
 _I8_PEAK = {}
@@ -470,7 +476,7 @@ def run_sift(args, rank, world, device, hp):
     pk = peaks()
     bf16_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
     k_ms = head["kernel_ms"] / max(head["kernel_n"], 1)
-    flops_per_launch = FLOP_PER_PAIR * float(nq) * head["nt_rank"] * args.steps / max(head["kernel_n"], 1)
+    flops_per_launch = FLOP_PER_PAIR * float(nq) * head["nt_rank"] * head.get("steps_timed", args.steps) / max(head["kernel_n"], 1)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     mode = head["mode"]
     peak_tf, peak_clocks = bf16_tf, None
@@ -514,6 +520,7 @@ def run_sift(args, rank, world, device, hp):
             "value": pairs_strong * args.steps / (strong_q["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": strong_q["ms"] / args.steps,
             "e2e": pairs_strong * args.steps / (strong_q["e2e_ms"] * 1e-3), "nq_per_gpu": -(-nq // world), "nt_per_gpu": strong_q["nt_rank"],
             "kernel_ms": strong_q["kernel_ms"] / max(strong_q["kernel_n"], 1), "h2d_bytes_per_step": strong_q["h2d"],
+            "steps_timed": strong_q["steps_timed"],
             "identical_to_row_sharded": strong_q["identical"],
             "note": "same nq x nt pairs, retrieval.knn2_query_sharded: 1/N of the queries per rank against the replicated database, "
                     "one all-gather of the answers; the form for databases that fit every GPU"}
