@@ -4,7 +4,7 @@
 //
 // Replaces cv2.BFMatcher(cv2.NORM_L2).knnMatch(..., k=2) at reference urbanscene/features.py:59 for descriptors that are
 // not small integers (SURF, RootSIFT, re-scaled SIFT ...).  The bf16 split engine (l2_tc_split.cu) needs 25 kind::f16
-// MMAs of K = 16 per 128 x 128 tile; this engine needs 13 kind::i8 MMAs of K = 32 at twice the issue rate per column.
+// MMAs of K = 16 per tile of pairs; this engine needs 13 kind::i8 MMAs of K = 32 (same pipe time per MMA).
 //
 //   x = delta X + e,  X = round(x / delta) in [-16256, 16256],  X = 128 H + L,  H in [-127, 127],  L in [-64, 63]
 //   delta = max(max|x| / 16256, sqrt(max||t||^2 / 1.55e10))                (one scale for queries and database)

@@ -48,7 +48,7 @@ extern "C" {
                              norms below 4,000,000.  Fully asynchronous: the range check runs on the device and gates
                              the sweep there; a violation leaves every idx at -1 and is reported by hpusm_async_status() */
 #define HPUSM_L2_TC_Q16 5 /* tcgen05 kind::i8 for GENERAL floats: 15-bit fixed point split into two signed bytes, two s32
-                             accumulators per tile (13 integer MMAs where the bf16 split needs 25 at half the rate),
+                             accumulators per tile (13 integer MMAs of K = 32 where the bf16 split needs 25 of K = 16),
                              top-6 per list + verified FP32 re-rank with error bounds measured on the data; synchronises
                              the stream once (count of rows sent to the exact fallback)                             */
 
