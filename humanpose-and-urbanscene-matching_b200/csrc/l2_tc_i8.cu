@@ -521,8 +521,12 @@ int l2_tc_i8_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32_
   const char* trace_path = getenv("HPUSM_I8_TRACE");
   if (trace_path) { HPUSM_CUDA_OK(cudaMalloc(&trace, 8192 * 8)); HPUSM_CUDA_OK(cudaMemset(trace, 0, 8192 * 8)); }
 #endif
+#ifdef HPUSM_DEV_SWITCHES   // development builds only (HPUSM_EXTRA_FLAGS=-DHPUSM_DEV_SWITCHES bash build.sh): tools/q16_time.py
   const char* dbg_env = getenv("HPUSM_I8_DBG");   // experiment switches (wrong answers), see the kernel
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+  const int dbg = 0;                               // the product library ignores the variable
+#endif
   const int* gate = require ? flag : nullptr;
   if (dbg == 1)
     HPUSM_LAUNCH_TIMED(l2_i8_knn2_kernel<1>, grid, I8_THREADS, I8_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,

@@ -687,8 +687,12 @@ int l2_tc_q16_knn2(const float* q, int64_t nq, const float* t, int64_t nt, int32
   rows_per_split = (rows_per_split + Q_TN - 1) / Q_TN * Q_TN;
   const int units = q_blocks * L.splits;
   const int grid = units < sm_count() ? units : sm_count();
+#ifdef HPUSM_DEV_SWITCHES   // development builds only (HPUSM_EXTRA_FLAGS=-DHPUSM_DEV_SWITCHES bash build.sh): tools/q16_time.py
   const char* dbg_env = getenv("HPUSM_Q16_DBG");   // experiment switches (wrong answers), see the kernel
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+  const int dbg = 0;                               // the product library ignores the variable
+#endif
   if (dbg == 1)
     HPUSM_LAUNCH_TIMED(l2_q16_knn_kernel<1>, grid, Q_THREADS, Q_SMEM_BYTES, st, qb, map_t, map_ta, nq, nt, q_blocks, L.splits,
                        rows_per_split, cand, kth);

@@ -24,6 +24,7 @@ python tools/microbench.py > $O/r2_microbench.txt 2>/dev/null; echo "microbench 
 # general-float variant of C2 (fixed-point integer engine) + the decompositions of both kNN kernels + MMA issue rates at their shapes
 python bench.py --descriptors float --steps 6 --warmup 3 --no-others > $O/r2_bench_float_q16.json 2> $O/r2_bench_float_q16.err; echo "bench float rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:l2_q16_knn -s 1 -c 1 -o $O/r2_l2_q16 $SHORT --descriptors float --no-others > $O/ncu_q16.log 2>&1; echo "ncu q16 rc=$?"
+# (the two decompositions need a library built with HPUSM_EXTRA_FLAGS=-DHPUSM_DEV_SWITCHES)
 python tools/q16_time.py 262144 10 2 1 0 > $O/r2_q16_decomposition.txt 2>&1; echo "q16 decomposition rc=$?"
 python tools/q16_time.py --engine i8 524288 10 2 1 0 > $O/r2_i8_decomposition.txt 2>&1; echo "i8 decomposition rc=$?"
 python tools/mma_shapes.py > $O/r2_mma_shapes.txt 2>&1; echo "mma shapes rc=$?"

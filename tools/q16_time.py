@@ -1,5 +1,7 @@
 """Kernel time of the Q16 engine under its experiment switches (HPUSM_Q16_DBG) at a given size.
-    python tools/q16_time.py [n] [dbg values...]
+    python tools/q16_time.py [--engine i8] [n] [dbg values...]
+Needs a development build of the library: HPUSM_EXTRA_FLAGS=-DHPUSM_DEV_SWITCHES bash humanpose-and-urbanscene-matching_b200/csrc/build.sh
+(the product build ignores HPUSM_Q16_DBG / HPUSM_I8_DBG: every variant but 0 gives WRONG answers).
 """
 import importlib, os, sys
 import numpy as np, torch
