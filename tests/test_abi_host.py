@@ -36,6 +36,18 @@ def test_version_and_error_string(hpusm):
         hpusm._lib.check(rc)
 
 
+def test_l2_mode_constants_match_the_header():
+    """The Python layer names the engines by the header's numbers (a new engine must be added in both places)."""
+    import importlib
+    import re
+    lib = importlib.import_module("humanpose-and-urbanscene-matching_b200._lib")
+    text = open(os.path.join(ROOT, "include", "hpusm.h")).read()
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define HPUSM_(L2_[A-Z0-9_]+)\s+(\d+)", text)}
+    assert set(header) == {"L2_AUTO", "L2_SIMT", "L2_TC_INT", "L2_TC_SPLIT", "L2_TC_I8", "L2_TC_Q16"}
+    for name, value in header.items():
+        assert getattr(lib, name) == value, name
+
+
 def test_workspace_queries_are_pure(hpusm):
     lib = hpusm._lib.lib
     assert lib.hpusm_knn2_hamming_workspace_bytes(0, 0, 32) == 256
